@@ -1,0 +1,128 @@
+/* splendor_b200.h - C ABI of the B200-native batched Splendor environment (libsplendor_b200.so).
+ *
+ * The reference (kuboyoo/alphazero-general-ori) has no FFI for this path: its boundary is the
+ * duck-typed Python `Game` protocol (Game.py:14-155, implemented by SplendorGame.py:11-86) over a
+ * Numba jitclass `Board` (SplendorLogicNumba.py:84-774). This library is what sits underneath our
+ * Python mirror of that protocol (alphazero-general-ori_b200/game.py); every entry point names the
+ * reference call(s) it replaces. INTEGRATION.md shows the ctypes stub a reference maintainer adds.
+ *
+ * Conventions
+ *  - plain C types only; all buffers are caller-owned DEVICE pointers (e.g. torch tensors' data_ptr)
+ *  - every call takes the CUDA stream to launch on (cudaStream_t passed as void*; NULL = default stream)
+ *    and returns 0 or a negative SPL_E_* code; nothing throws across the ABI; spl_last_error() gives text
+ *  - no global state: a spl_ctx carries (n_players, rules, device); contexts are thread-compatible
+ *  - there is no CPU fallback: without a CUDA device spl_ctx_create fails with SPL_E_NOGPU
+ *
+ * Data layouts (DESIGN.md "data layout")
+ *  - AoS state  : int8[L][R][7], R = 32 + 10n + n^2  -- byte-identical to the reference's state array
+ *                 (SplendorLogicNumba.py:291-303); used only at the API boundary
+ *  - lane planes: int8[7R][Lpad], Lpad = L rounded up to 128 -- structure-of-arrays, one plane per
+ *                 state cell; the resident form in HBM, staged through shared memory by TMA tiles
+ *  - mask planes: uint32[13][Lpad] -- the 406 legality flags, bit a of the mask = action a
+ */
+#ifndef SPLENDOR_B200_H
+#define SPLENDOR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPL_ABI_VERSION 1
+#define SPL_NUM_ACTIONS 406     /* action_size(), SplendorLogicNumba.py:29-36 with patch P2 */
+#define SPL_MASK_WORDS32 13
+#define SPL_LANE_TILE 128
+
+#define SPL_OK 0
+#define SPL_E_ARG (-1)          /* bad argument */
+#define SPL_E_CUDA (-2)         /* a CUDA call failed; see spl_last_error() */
+#define SPL_E_NOGPU (-3)        /* no CUDA device / driver */
+
+/* rule switches = Board fields ENABLE_ACTION_RESERVE / ENABLE_ACTION_GIVEBACK (SplendorLogicNumba.py:96-97);
+ * REFCOMPAT reproduces the reference's n>=3 quirks (noble stride 3 at :219/:345, int8(999) at :313) */
+#define SPL_RULE_RESERVE 1u
+#define SPL_RULE_GIVEBACK 2u
+#define SPL_RULE_REFCOMPAT 4u
+#define SPL_RULES_DEFAULT (SPL_RULE_RESERVE | SPL_RULE_GIVEBACK | SPL_RULE_REFCOMPAT)
+
+/* chance modes of a move (make_move's `deterministic` flag, :267, plus the replay used for parity) */
+#define SPL_CHANCE_DETERMINISTIC 0   /* no deck reveal: the in-tree MCTS step (MCTS.py:228) */
+#define SPL_CHANCE_REPLAY 1          /* reveal the given card: colour*8+idx per lane, 255 = none */
+#define SPL_CHANCE_PHILOX 2          /* Philox4x32-10 keyed by (seed, game, episode, ply) */
+
+typedef struct spl_ctx spl_ctx;
+
+int         spl_abi_version(void);
+const char* spl_last_error(void);
+
+/* Board.__init__ (:86-98): n_players in {2,3,4}; token_limit = NUM_TOKEN_LIMIT (10) */
+int  spl_ctx_create(int n_players, int token_limit, uint32_t rule_flags, int device, spl_ctx** out);
+/* setNumTokenLim (:214), SplendorGame.disableReserve/enableReserve (SplendorGame.py:82-86) */
+int  spl_ctx_set_rules(spl_ctx* ctx, int token_limit, uint32_t rule_flags);
+/* 1 (default): the step kernel stages tiles with TMA; 0: plain vectorised copies (A/B and debugging) */
+int  spl_ctx_set_tma(spl_ctx* ctx, int enabled);
+void spl_ctx_destroy(spl_ctx* ctx);
+
+/* observation_size (:25-27) and derived sizes */
+int    spl_state_rows(int n_players);
+int    spl_state_bytes(int n_players);
+int    spl_lanes_padded(int n_lanes);
+size_t spl_planes_bytes(int n_players, int n_lanes);
+size_t spl_mask_planes_bytes(int n_lanes);
+
+/* AoS <-> lane planes (Board.copy_state :291-303 is the reference's "bind this array") */
+int spl_pack(spl_ctx* ctx, const int8_t* aos, int8_t* planes, int n_lanes, void* stream);
+int spl_unpack(spl_ctx* ctx, const int8_t* planes, int8_t* aos, int n_lanes, void* stream);
+/* mask planes -> bool[L][406] as the reference's valid_moves returns (:251-265) */
+int spl_mask_unpack(spl_ctx* ctx, const uint32_t* mask_planes, uint8_t* valids, int n_lanes, void* stream);
+
+/* init_game (:222-246). Philox: 12 deals + n+1 nobles from (seed, game_base+lane, episode[lane]).
+ * lane_select (may be NULL) restricts the reset to lanes with a non-zero byte. */
+int spl_reset_philox(spl_ctx* ctx, int8_t* planes, int n_lanes, uint64_t seed, uint32_t game_base,
+                     const uint32_t* episodes, const uint8_t* lane_select, void* stream);
+/* explicit start for replaying a reference game: deals uint8[L][12] (colour*8+idx per visible slot),
+ * nobles uint8[L][5] (first n+1 used) */
+int spl_reset_explicit(spl_ctx* ctx, int8_t* planes, int n_lanes, const uint8_t* deals,
+                       const uint8_t* nobles, void* stream);
+
+/* One fused pass over every lane (one thread per game lane):
+ *   make_move (:267-289) -> [swap_players (:338-347)] -> check_end_game (:320-334) -> [auto reset]
+ *   -> valid_moves (:251-265) for the player to move -> [uniform random pick for the next ply]
+ * i.e. SplendorGame.getNextState + getCanonicalForm + getGameEnded + getValidMoves
+ * (SplendorGame.py:30-57) for all lanes in one launch. Any output pointer may be NULL. */
+typedef struct {
+    int8_t*        planes;        /* in/out lane planes */
+    int            n_lanes;
+    const int16_t* actions;       /* [L] action per lane; <0 or NULL: no move (query only) */
+    const uint8_t* players;       /* [L] index of the mover / queried player; NULL: `player` for all */
+    int            player;
+    int            chance_mode;   /* SPL_CHANCE_* */
+    const uint8_t* reveals;       /* [L] for SPL_CHANCE_REPLAY */
+    uint64_t       seed;          /* Philox key */
+    uint32_t       game_base;     /* game id of lane 0 (global lane index when sharded over GPUs) */
+    uint32_t*      episodes;      /* [L] in/out episode counters (NULL: 0) */
+    int            rotate;        /* 1: rotate so that the next player becomes player 0 (canonical form) */
+    int            auto_reset;    /* 1 (needs rotate=1, episodes): finished lanes start a new Philox game */
+    int            store_state;   /* 0: leave planes untouched (pure queries) */
+    uint32_t*      mask_out;      /* mask planes for the player to move after this call */
+    float*         ended_out;     /* [L][n] check_end_game of the state as stored (before any auto reset) */
+    int16_t*       next_actions;  /* [L] uniform random legal action for the next ply (Philox stream 1) */
+    int32_t*       status_out;    /* [L] next player in the caller's frame, or <0 if the move was refused */
+    unsigned long long* counters; /* [2] += finished games, += plies played (may be NULL) */
+} spl_step_args;
+
+int spl_step(spl_ctx* ctx, const spl_step_args* args, void* stream);
+
+/* get_score (:217-220) and get_round (:397-398) for every lane: scores int32[L][n], rounds int32[L] */
+int spl_scores(spl_ctx* ctx, const int8_t* planes, int n_lanes, int32_t* scores, int32_t* rounds, void* stream);
+
+/* get_symmetries (:349-395) on AoS input: for each of L states emits up to 1+9+2n variants.
+ * out_states int8[L][18][R*7], out_pi float[L][18][406], out_valids uint8[L][18][406], out_count int32[L] */
+int spl_symmetries(spl_ctx* ctx, const int8_t* aos, const float* pi, const uint8_t* valids, int n_lanes,
+                   int8_t* out_states, float* out_pi, uint8_t* out_valids, int32_t* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
