@@ -1,0 +1,11 @@
+"""B200-native batched Splendor environment + MCTS self-play engine behind the reference's Game / MCTS API.
+
+    from azg_b200 import SplendorGame, SplendorEnv      (import alias: azg_b200.py at the repo root)
+
+The compute path is hand-written sm_100a CUDA in csrc/, reached through the C ABI in include/splendor_b200.h.
+"""
+from . import _native
+from .engine import SplendorEnv, rows
+from .game import Board, SplendorGame, action_size, observation_size
+
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "observation_size", "action_size", "rows", "_native"]

@@ -1,0 +1,282 @@
+"""Drop-in mirror of the reference's `SplendorGame` (SplendorGame.py:11-86; protocol Game.py:14-155).
+
+Same method names, argument meaning and return types (numpy int8[R,7] boards, bool[406] masks,
+float32[n] end vectors) so Coach / Arena / MCTS-style callers drive it unchanged; every call runs
+the sm_100a kernels through the C ABI (one game lane for the per-game methods, L lanes for the
+`*_batch` methods). No CPU path: constructing it without a CUDA device raises.
+
+Differences that are part of the contract:
+  * action space 406, pass (405) = no-op + ply counter
+  * chance comes from Philox4x32-10 keyed (seed, game id, episode, ply), not Numba's MT19937;
+    `getNextState(..., reveal=code)` replays a given draw (colour*8+idx) for bit-exact comparison
+  * the n>=3 quirks of the reference are reproduced while `ref_compat=True` (default)
+"""
+import numpy as np
+import torch
+
+from . import _native as nat
+from .engine import SplendorEnv, rows
+
+
+def observation_size(num_players):
+    """SplendorLogicNumba.py:25-27"""
+    return (rows(num_players), 7)
+
+
+def action_size():
+    """SplendorLogicNumba.py:29-36 with patch P2"""
+    return nat.NUM_ACTIONS
+
+
+class Board:
+    """Shim of the jitclass `Board` surface that callers reach through `game.board`
+    (Arena.py:116,173; MCTS.py:161; SplendorPlayers.py). Holds one state as numpy int8[R,7]."""
+
+    def __init__(self, num_players, seed=0, ref_compat=True, device=0):
+        self.num_players = num_players
+        self.n = num_players
+        self._flags = nat.RULE_RESERVE | nat.RULE_GIVEBACK | (nat.RULE_REFCOMPAT if ref_compat else 0)
+        self._limit = 10
+        self._env = SplendorEnv(num_players, 1, device=device, seed=seed, token_limit=self._limit, rule_flags=self._flags)
+        self._game_id = 0
+        self.max_moves = np.uint8(62 * num_players)
+        self.score_win = 15
+        self.state = np.zeros(observation_size(num_players), dtype=np.int8)
+
+    # ---- rule switches (Board fields :96-98, setter :214)
+    @property
+    def ENABLE_ACTION_RESERVE(self):
+        return bool(self._flags & nat.RULE_RESERVE)
+
+    @ENABLE_ACTION_RESERVE.setter
+    def ENABLE_ACTION_RESERVE(self, v):
+        self._flags = (self._flags | nat.RULE_RESERVE) if v else (self._flags & ~nat.RULE_RESERVE)
+        self._env.set_rules(self._limit, self._flags)
+
+    @property
+    def ENABLE_ACTION_GIVEBACK(self):
+        return bool(self._flags & nat.RULE_GIVEBACK)
+
+    @ENABLE_ACTION_GIVEBACK.setter
+    def ENABLE_ACTION_GIVEBACK(self, v):
+        self._flags = (self._flags | nat.RULE_GIVEBACK) if v else (self._flags & ~nat.RULE_GIVEBACK)
+        self._env.set_rules(self._limit, self._flags)
+
+    @property
+    def NUM_TOKEN_LIMIT(self):
+        return self._limit
+
+    def setNumTokenLim(self, n):
+        self._limit = int(n)
+        self._env.set_rules(self._limit, self._flags)
+
+    # ---- state binding (:291-303)
+    def get_state(self):
+        return self.state
+
+    def copy_state(self, state, copy_or_not):
+        if self.state is state and not copy_or_not:
+            return
+        self.state = state.copy() if copy_or_not else state
+
+    def _upload(self):
+        self._env.set_states(torch.from_numpy(np.ascontiguousarray(self.state, dtype=np.int8)))
+
+    def _download(self):
+        self.state = self._env.states().cpu().numpy()[0]
+
+    # ---- game start (:222-246)
+    def init_game(self, game_id=None):
+        if game_id is not None:
+            self._game_id = int(game_id)
+        self._env.game_base = self._game_id
+        self._env.episodes.zero_()
+        self._env.reset()
+        self._download()
+        self._game_id += 1
+
+    # ---- rules
+    def valid_moves(self, player):
+        self._upload()
+        self._env.step(None, player=int(player), store_state=False, want_ended=False, want_status=False)
+        return self._env.valids().cpu().numpy()[0].astype(np.bool_)
+
+    def make_move(self, move, player, deterministic, reveal=None):
+        self._upload()
+        act = torch.tensor([int(move)], dtype=torch.int16, device=self._env.device)
+        rv = None
+        if deterministic:
+            chance = "det"
+        elif reveal is not None:
+            chance, rv = "replay", torch.tensor([int(reveal)], dtype=torch.uint8, device=self._env.device)
+        else:
+            chance = "philox"
+        self._env.step(act, player=int(player), chance=chance, reveals=rv, want_mask=False, want_ended=False)
+        status = int(self._env.status.cpu()[0])
+        if status < 0:
+            raise ValueError(f"move {move} is undefined in this state (status {status})")
+        self._download()
+        return status
+
+    def check_end_game(self):
+        self._upload()
+        self._env.step(None, store_state=False, want_mask=False, want_status=False)
+        return self._env.ended.cpu().numpy()[0].copy()
+
+    def get_score(self, player):
+        self._upload()
+        return int(self._env.scores()[0].cpu()[0, int(player)])
+
+    def get_round(self):
+        return np.uint8(self.state[0, 6])   # :397-398 reads the int8 ply counter as uint8
+
+    def swap_players(self, nb_swaps):
+        self._upload()
+        self._env.step(None, player=int(nb_swaps) % self.n, rotate=True, want_mask=False, want_ended=False, want_status=False)
+        self._download()
+
+    def get_symmetries(self, policy, valid_actions):
+        os_, op, ov, cnt = self._env.symmetries(torch.from_numpy(np.ascontiguousarray(self.state)),
+                                                torch.from_numpy(np.ascontiguousarray(policy, dtype=np.float32)),
+                                                torch.from_numpy(np.ascontiguousarray(valid_actions).astype(np.uint8)))
+        k = int(cnt.cpu()[0])
+        os_, op, ov = os_.cpu().numpy()[0], op.cpu().numpy()[0], ov.cpu().numpy()[0]
+        return [(os_[i].copy(), op[i].copy(), ov[i].astype(np.bool_)) for i in range(k)]
+
+
+class SplendorGame:
+    """Game protocol (Game.py:14-155) as implemented by the reference's SplendorGame (SplendorGame.py:11-86)."""
+
+    def __init__(self, N, is_fill=True, seed=0, ref_compat=True, device=0):
+        self.NUMBER_PLAYERS = N
+        self.num_players = N
+        self.board = Board(N, seed=seed, ref_compat=ref_compat, device=device)
+        self._batch_envs = {}
+        self._seed, self._ref_compat, self._device = seed, ref_compat, device
+
+    def getInitBoard(self):
+        self.board.init_game()
+        return self.board.get_state()
+
+    def getBoardSize(self):
+        return observation_size(self.num_players)
+
+    def getActionSize(self):
+        return action_size()
+
+    def getMaxScoreDiff(self):
+        return 15
+
+    def getNextState(self, board, player, action, deterministic=False, reveal=None):
+        self.board.copy_state(board, True)
+        next_player = self.board.make_move(action, player, deterministic, reveal=reveal)
+        return (self.board.get_state(), next_player)
+
+    def getValidMoves(self, board, player):
+        self.board.copy_state(board, False)
+        return self.board.valid_moves(player)
+
+    def getGameEnded(self, board, next_player):
+        self.board.copy_state(board, False)
+        return self.board.check_end_game()
+
+    def getScore(self, board, player):
+        self.board.copy_state(board, False)
+        return self.board.get_score(player)
+
+    def getRound(self, board):
+        self.board.copy_state(board, False)
+        return self.board.get_round()
+
+    def getCanonicalForm(self, board, player):
+        if player == 0:
+            return board   # the reference returns the same object (SplendorGame.py:52-53)
+        self.board.copy_state(board, True)
+        self.board.swap_players(player)
+        return self.board.get_state()
+
+    def getSymmetries(self, board, pi, valid_actions):
+        self.board.copy_state(board, True)
+        return self.board.get_symmetries(np.array(pi, dtype=np.float32), valid_actions)
+
+    def stringRepresentation(self, board):
+        return board.tobytes()
+
+    def getNumberOfPlayers(self):
+        return self.NUMBER_PLAYERS
+
+    def moveToString(self, move, current_player):
+        return move_to_str(move)
+
+    def disableReserve(self):
+        self.board.ENABLE_ACTION_RESERVE = False
+
+    def enableReserve(self):
+        self.board.ENABLE_ACTION_RESERVE = True
+
+    # ------------------------------------------------------------------ batched forms (host buffers in, host buffers out)
+    def _env_for(self, n_lanes):
+        env = self._batch_envs.get(n_lanes)
+        if env is None:
+            env = SplendorEnv(self.num_players, n_lanes, device=self._device, seed=self._seed,
+                              token_limit=self.board.NUM_TOKEN_LIMIT, rule_flags=self.board._flags)
+            env._h_in = torch.empty((n_lanes, env.R, 7), dtype=torch.int8).pin_memory()
+            env._h_act = torch.empty(n_lanes, dtype=torch.int16).pin_memory()
+            env._h_out = torch.empty((n_lanes, env.R, 7), dtype=torch.int8).pin_memory()
+            env._h_valid = torch.empty((n_lanes, nat.NUM_ACTIONS), dtype=torch.uint8).pin_memory()
+            env._h_ended = torch.empty((n_lanes, self.num_players), dtype=torch.float32).pin_memory()
+            env._d_in = torch.empty((n_lanes, env.R, 7), dtype=torch.int8, device=env.device)
+            env._d_act = torch.empty(n_lanes, dtype=torch.int16, device=env.device)
+            env._d_out = torch.empty((n_lanes, env.R, 7), dtype=torch.int8, device=env.device)
+            env._d_valid = torch.empty((n_lanes, nat.NUM_ACTIONS), dtype=torch.uint8, device=env.device)
+            self._batch_envs[n_lanes] = env
+        return env
+
+    def getNextStateBatch(self, boards, player, actions, deterministic=False, canonical=True):
+        """L games at once, host arrays in and out: boards int8[L,R,7], actions int[L], all moved by `player`.
+        Returns (next boards int8[L,R,7] (rotated to the next player's canonical form when `canonical`),
+        valid masks bool[L,406] for the player to move, end vectors float32[L,n]) =
+        getNextState + getCanonicalForm + getValidMoves + getGameEnded of the reference, per lane."""
+        boards = np.ascontiguousarray(boards, dtype=np.int8)
+        L = boards.shape[0]
+        env = self._env_for(L)
+        env._h_in.numpy()[...] = boards
+        env._h_act.numpy()[...] = np.asarray(actions, dtype=np.int16)
+        return self._step_pinned(env, player, deterministic, canonical)
+
+    def _step_pinned(self, env, player, deterministic, canonical):
+        env._d_in.copy_(env._h_in, non_blocking=True)
+        env._d_act.copy_(env._h_act, non_blocking=True)
+        env.set_states(env._d_in)
+        env.step(env._d_act, player=int(player), chance="det" if deterministic else "philox", rotate=canonical, want_status=False)
+        env.states(out=env._d_out)
+        env.valids(out=env._d_valid)
+        env._h_out.copy_(env._d_out, non_blocking=True)
+        env._h_valid.copy_(env._d_valid, non_blocking=True)
+        env._h_ended.copy_(env.ended, non_blocking=True)
+        torch.cuda.current_stream(env.device).synchronize()
+        return env._h_out.numpy(), env._h_valid.numpy().view(np.bool_), env._h_ended.numpy()
+
+
+_COLORS = ["white", "blue", "green", "red", "black"]
+
+
+def move_to_str(move):
+    """plain-text action names (the reference's coloured console rendering, SplendorLogic.py:60-223, is out of scope)"""
+    if move < 12:
+        return f"buy tier {move // 4} index {move % 4}"
+    if move < 24:
+        return f"reserve tier {(move - 12) // 4} index {(move - 12) % 4}"
+    if move < 27:
+        return f"reserve from deck of tier {move - 24}"
+    if move < 30:
+        return f"buy reserved card {move - 27}"
+    if move < 60:
+        return f"take gems (combination {move - 30})"
+    if move < 290:
+        return f"take and give back gems (exchange {move - 60})"
+    if move < 365:
+        return f"reserve {(move - 290) // 5} and give back 1 {_COLORS[(move - 290) % 5]}"
+    if move < 405:
+        return f"take 3 and give back 3 (exchange {move - 365})"
+    return "do nothing"

@@ -16,8 +16,10 @@
  * Data layouts (DESIGN.md "data layout")
  *  - AoS state  : int8[L][R][7], R = 32 + 10n + n^2  -- byte-identical to the reference's state array
  *                 (SplendorLogicNumba.py:291-303); used only at the API boundary
- *  - lane planes: int8[7R][Lpad], Lpad = L rounded up to 128 -- structure-of-arrays, one plane per
- *                 state cell; the resident form in HBM, staged through shared memory by TMA tiles
+ *  - lane tiles : int8[Lpad/32][7R][32], Lpad = L rounded up to 32 -- the resident form in HBM. Games are
+ *                 grouped in tiles of 32 lanes (one warp); inside a tile the state is structure-of-arrays
+ *                 (cell-major), so a tile is one contiguous 7R*32-byte block that a single TMA bulk copy
+ *                 stages into shared memory and lane l reads byte [cell][l]. Called "planes" below.
  *  - mask planes: uint32[13][Lpad] -- the 406 legality flags, bit a of the mask = action a
  */
 #ifndef SPLENDOR_B200_H
@@ -32,7 +34,8 @@ extern "C" {
 #define SPL_ABI_VERSION 1
 #define SPL_NUM_ACTIONS 406     /* action_size(), SplendorLogicNumba.py:29-36 with patch P2 */
 #define SPL_MASK_WORDS32 13
-#define SPL_LANE_TILE 128
+#define SPL_LANE_TILE 32
+#define SPL_MAX_SYMMETRIES 18   /* 1 + 9 + 2n, get_symmetries :349-395 */
 
 #define SPL_OK 0
 #define SPL_E_ARG (-1)          /* bad argument */
@@ -113,6 +116,27 @@ typedef struct {
 } spl_step_args;
 
 int spl_step(spl_ctx* ctx, const spl_step_args* args, void* stream);
+
+/* Persistent multi-ply pass: every lane plays `plies` plies of uniformly random legal moves
+ * (Philox stream 1) with Philox deck reveals, end-game detection and auto reset, the tile staying in
+ * shared memory for the whole call. This is the loop the reference runs one Python call at a time in
+ * Arena.playGame (Arena.py:99-160) with SplendorPlayers.RandomPlayer (SplendorPlayers.py:20-27):
+ * getValidMoves -> pick -> getNextState -> getGameEnded [-> getCanonicalForm]. */
+typedef struct {
+    int8_t*   planes;        /* in/out lane tiles */
+    int       n_lanes;
+    int       plies;         /* plies to play per lane in this call */
+    uint64_t  seed;
+    uint32_t  game_base;
+    uint32_t* episodes;      /* [L] in/out (NULL: every lane starts at episode 0 and the count is dropped) */
+    uint8_t*  players;       /* [L] in/out player to move; required when rotate=0, may be NULL when rotate=1 */
+    int       rotate;        /* 1: keep the state canonical (player to move is always index 0) */
+    int32_t*  first_plies;   /* [L] plies of the first game each lane finished in this call (0: none); may be NULL */
+    float*    first_result;  /* [L][n] its check_end_game vector (in the stored frame); may be NULL */
+    unsigned long long* counters; /* [2] += finished games, += plies played (may be NULL) */
+} spl_rollout_args;
+
+int spl_rollout(spl_ctx* ctx, const spl_rollout_args* args, void* stream);
 
 /* get_score (:217-220) and get_round (:397-398) for every lane: scores int32[L][n], rounds int32[L] */
 int spl_scores(spl_ctx* ctx, const int8_t* planes, int n_lanes, int32_t* scores, int32_t* rounds, void* stream);
