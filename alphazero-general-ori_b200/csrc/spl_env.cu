@@ -140,8 +140,8 @@ struct StepParams {
     int n_tiles;
 };
 
-template <int N, bool TMA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) spl_step_kernel(const StepParams P) {
+template <int N, bool TMA, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) spl_step_kernel(const StepParams P) {
     typedef SplLay<N> L;
     constexpr int TB = L::CELLS * TL;
     extern __shared__ __align__(128) int8_t smem[];
@@ -239,8 +239,8 @@ struct RolloutParams {
     int n_tiles;
 };
 
-template <int N, bool TMA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) spl_rollout_kernel(const RolloutParams P) {
+template <int N, bool TMA, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) spl_rollout_kernel(const RolloutParams P) {
     typedef SplLay<N> L;
     constexpr int TB = L::CELLS * TL;
     extern __shared__ __align__(128) int8_t smem[];
@@ -496,9 +496,10 @@ __global__ void __launch_bounds__(128) spl_sym_kernel(const int8_t* __restrict__
         default: { constexpr int N = 4; __VA_ARGS__; } break;\
     }
 
-template <int N> struct Cfg {   // warps per CTA such that a CTA's tiles fit and several CTAs share an SM
-    static constexpr int WARPS = 4;
+template <int N> struct Cfg {   // small CTAs (2 warps = 2 tiles) so that shared memory packs tightly: 9 / 7 / 5 CTAs per SM
+    static constexpr int WARPS = 2;
     static constexpr int SMEM = WARPS * SplLay<N>::CELLS * TL;
+    static constexpr int MINB = (227 * 1024) / (SMEM + 1024);
 };
 
 template <typename K>
@@ -614,7 +615,7 @@ static int launch_step(spl_ctx* c, const spl_step_args* a, cudaStream_t st) {
     constexpr int W = Cfg<N>::WARPS;
     StepParams P;
     P.a = *a; P.rules = c->rules; P.n_tiles = spl_lanes_padded(a->n_lanes) / TL;
-    auto k = spl_step_kernel<N, TMA, W>;
+    auto k = spl_step_kernel<N, TMA, W, Cfg<N>::MINB>;
     CU(set_smem(k, Cfg<N>::SMEM));
     k<<<(P.n_tiles + W - 1) / W, W * 32, Cfg<N>::SMEM, st>>>(P);
     CU(cudaGetLastError());
@@ -639,7 +640,7 @@ static int launch_rollout(spl_ctx* c, const spl_rollout_args* a, cudaStream_t st
     constexpr int W = Cfg<N>::WARPS;
     RolloutParams P;
     P.a = *a; P.rules = c->rules; P.n_tiles = spl_lanes_padded(a->n_lanes) / TL;
-    auto k = spl_rollout_kernel<N, TMA, W>;
+    auto k = spl_rollout_kernel<N, TMA, W, Cfg<N>::MINB>;
     CU(set_smem(k, Cfg<N>::SMEM));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, W * 32, Cfg<N>::SMEM));

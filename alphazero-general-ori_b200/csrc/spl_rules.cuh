@@ -19,17 +19,22 @@
 // evaluated once with nibble-SWAR compares, the 345 exchange actions are table-ANDs of those.
 #pragma once
 #include <stdint.h>
+#include <utility>
 
 #ifdef __CUDACC__
 #define SPL_D __device__ __forceinline__
 #define SPL_CTABLE static __constant__
 #define SPL_GTABLE static __device__ const
+#define SPL_KTABLE static constexpr
+#define SPL_FFS(x) __ffs(x)
 #define SPL_POPC(x) __popc(x)
 #define SPL_MULHI(a, b) __umulhi((a), (b))
 #else
 #define SPL_D static inline
 #define SPL_CTABLE static const
 #define SPL_GTABLE static const
+#define SPL_KTABLE static constexpr
+#define SPL_FFS(x) __builtin_ffs(x)
 #define SPL_POPC(x) __builtin_popcount(x)
 #define SPL_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
 #endif
@@ -119,14 +124,53 @@ SPL_D void spl_mask_or(uint32_t* m, int pos, uint32_t bits, int nbits) {   // po
     if ((pos & 31) + nbits > 32) m[(pos >> 5) + 1] |= bits >> (32 - (pos & 31));
 }
 
-template <int A0, int CNT>
-SPL_D void spl_ex_block(uint32_t* m, uint32_t T, uint32_t G) {   // _valid_exchange :634-669: take flag AND give flag
+// exchanges 60..289 (_valid_exchange :634-669), word-parallel: action a is legal iff its take flag AND its give
+// flag are set, so mask = OR_t(T_t ? EXM_TAKE[t]) & OR_g(G_g ? EXM_GIVE[g]) & regime. The tables are compile-time
+// constants: after unrolling every (flag, word) pair with a non-zero table entry is one LOP3 with an immediate.
+template <int F, int W>
+SPL_D void spl_ex_take_fw(uint32_t* ts, uint32_t sel) {
+    constexpr uint32_t v = SPL_EXM_TAKE[F][W];
+    if constexpr (v != 0u) ts[W] |= sel & v;
+}
+template <int F, int W>
+SPL_D void spl_ex_give_fw(uint32_t* gs, uint32_t sel) {
+    constexpr uint32_t v = SPL_EXM_GIVE[F][W];
+    if constexpr (v != 0u) gs[W] |= sel & v;
+}
+template <int F, int... W>
+SPL_D void spl_ex_take_f(uint32_t* ts, uint32_t T, std::integer_sequence<int, W...>) {
+    const uint32_t sel = 0u - ((T >> F) & 1u);
+    (spl_ex_take_fw<F, W + 1>(ts, sel), ...);
+}
+template <int F, int... W>
+SPL_D void spl_ex_give_f(uint32_t* gs, uint32_t G, std::integer_sequence<int, W...>) {
+    const uint32_t sel = 0u - ((G >> F) & 1u);
+    (spl_ex_give_fw<F, W + 1>(gs, sel), ...);
+}
+template <int... F>
+SPL_D void spl_ex_take_all(uint32_t* ts, uint32_t T, std::integer_sequence<int, F...>) {
+    (spl_ex_take_f<F>(ts, T, std::make_integer_sequence<int, 9>{}), ...);
+}
+template <int... F>
+SPL_D void spl_ex_give_all(uint32_t* gs, uint32_t G, std::integer_sequence<int, F...>) {
+    (spl_ex_give_f<F>(gs, G, std::make_integer_sequence<int, 9>{}), ...);
+}
+template <int W>
+SPL_D uint32_t spl_ex_regime_w(int regime) {
+    constexpr uint32_t r0 = SPL_EXM_REGIME[0][W], r1 = SPL_EXM_REGIME[1][W], r2 = SPL_EXM_REGIME[2][W];
+    return regime == 0 ? r0 : (regime == 1 ? r1 : r2);
+}
+template <int... W>
+SPL_D void spl_ex_combine(uint32_t* m, const uint32_t* ts, const uint32_t* gs, int regime, std::integer_sequence<int, W...>) {
+    ((m[W + 1] |= ts[W + 1] & gs[W + 1] & spl_ex_regime_w<W + 1>(regime)), ...);
+}
+SPL_D void spl_ex_words(uint32_t* m, uint32_t T, uint32_t G, int regime) {   // mask words 1..9 hold actions 60..289
+    uint32_t ts[SPL_MASK_WORDS], gs[SPL_MASK_WORDS];
 #pragma unroll
-    for (int k = 0; k < CNT; k++) {
-        const int a = A0 + k;
-        uint32_t bit = (T >> SPL_EX_TAKE[a]) & (G >> SPL_EX_GIVE[a]) & 1u;
-        m[a >> 5] |= bit << (a & 31);
-    }
+    for (int w = 0; w < SPL_MASK_WORDS; w++) ts[w] = gs[w] = 0u;
+    spl_ex_take_all(ts, T, std::make_integer_sequence<int, 30>{});
+    spl_ex_give_all(gs, G, std::make_integer_sequence<int, 20>{});
+    spl_ex_combine(m, ts, gs, regime, std::make_integer_sequence<int, 9>{});
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,16 +265,9 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
 
     // --- exchanges 60..404 (_valid_exchange :615-680): the regime is chosen by the token total
     if (tokens > 7) {
-        if (tokens == r.limit - 2) {
-            spl_ex_block<60, 20>(m, T, G);            // take 3 / give 1
-        } else if (tokens == r.limit - 1) {
-            spl_ex_block<80, 30>(m, T, G);            // take 3 / give 2
-            spl_ex_block<220, 30>(m, T, G);           // take 2 different / give 1
-            spl_ex_block<250, 20>(m, T, G);           // take 2 identical / give 1
-        } else {
-            spl_ex_block<110, 60>(m, T, G);           // take 2 different / give 2
-            spl_ex_block<170, 50>(m, T, G);           // take 2 identical / give 2
-            spl_ex_block<270, 20>(m, T, G);           // take 1 / give 1
+        const int regime = tokens == r.limit - 2 ? 0 : (tokens == r.limit - 1 ? 1 : 2);
+        spl_ex_words(m, T, G, regime);
+        if (regime == 2) {
             if (r.flags & SPL_F_GIVEBACK) {           // take 3 / give 3 (:672, _valid_give_gems3 :602-607)
                 bool g_neg = false;
 #pragma unroll
@@ -604,10 +641,13 @@ SPL_D int spl_pick_random(const uint32_t* m, uint64_t seed, uint32_t game, uint3
         int pc = SPL_POPC(m[w]);
         if (action < 0) {
             if (k < pc) {
-                uint32_t x = m[w];
-                for (int t = 0; t < k; t++) x &= x - 1;   // drop the k lowest set bits
-                int bitpos = 0;
-                while (!((x >> bitpos) & 1u)) bitpos++;
+                const uint32_t x = m[w];   // position of the k-th (0-based) set bit: popcount binary search
+                int bitpos = 0, kk = k;
+#pragma unroll
+                for (int sh = 16; sh >= 1; sh >>= 1) {
+                    const int c = SPL_POPC((x >> bitpos) & ((1u << sh) - 1u));
+                    if (kk >= c) { kk -= c; bitpos += sh; }
+                }
                 action = 32 * w + bitpos;
             } else k -= pc;
         }

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tma", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=300, help="untimed plies per lane before warm-up (de-synchronises the games)")
     ap.add_argument("--seed", type=int, default=20261018)
     return ap.parse_args()
 
@@ -181,6 +183,8 @@ def main():
     # games shard over ranks by global game id: lane l of rank r is game r*L + l (results independent of N)
     env = azg_b200.SplendorEnv(n, L, device=local, seed=args.seed, game_base=rank * L, use_tma=not args.no_tma)
     env.reset()
+    # burn-in: games start in lock-step; play until the lanes are spread over all game phases (steady state)
+    env.rollout(args.burn_in, rotate=True)
     if args.mode == "step":
         env.step(None, want_next=True, want_ended=False, want_status=False)
 
@@ -249,7 +253,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "players": n, "lanes_per_gpu": L, "plies_per_launch": P, "mode": args.mode,
+        "config": {"workload": workload_name(args), "players": n, "lanes_per_gpu": L, "plies_per_launch": P, "mode": args.mode, "burn_in_plies": args.burn_in,
                    "tma": not args.no_tma, "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: {L * env.S / 1e6:.0f} MB of lane tiles per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": launches, "wall_s": wall, "games_finished": cnt[0] * world,
@@ -283,7 +287,8 @@ def main():
 
     # ---- sweep point named by the metric: 64k lanes, L2 flushed between timed launches
     if rank == 0:
-        line["sweep"] = sweep(azg_b200, torch, n, local, args)
+        if not args.no_sweep:
+            line["sweep"] = sweep(azg_b200, torch, n, local, args)
         if not args.no_cpu:
             v, cores, games, plies, dtc = cpu_rollouts(n, args.seed, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -301,6 +306,7 @@ def sweep(azg_b200, torch, n, local, args):
     for Ls in (1 << 10, 1 << 13, 1 << 16, 1 << 18):
         e = azg_b200.SplendorEnv(n, Ls, device=local, seed=args.seed, use_tma=not args.no_tma)
         e.reset()
+        e.rollout(args.burn_in, rotate=True)
         for _ in range(3):
             e.rollout(args.plies, rotate=True)
         tot = 0.0

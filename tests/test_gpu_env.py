@@ -185,24 +185,29 @@ def test_philox_steps_vs_oracle(n, compat, rotate):
 
 
 @pytest.mark.parametrize("use_tma", [True, False])
-@pytest.mark.parametrize("n,rotate", [(2, False), (2, True), (3, False), (4, True)])
-def test_rollout_kernel_vs_oracle(n, rotate, use_tma):
-    """the persistent multi-ply kernel plays whole games; plies and results of every lane's first game equal spo_rollout's"""
+@pytest.mark.parametrize("n,rotate,compat", [(2, False, True), (2, True, True), (3, False, True), (4, False, True), (4, True, False), (3, True, False)])
+def test_rollout_kernel_vs_oracle(n, rotate, compat, use_tma):
+    """the persistent multi-ply kernel plays whole games; plies and results of every lane's first game equal spo_rollout's
+    (which plays in the absolute frame). Games end only when player 0 is to move, so the canonical-rotating kernel gives
+    the same vectors - except under ref_compat with n>=3, where the reference's stride-3 noble rotation (F7a) is not a
+    true rotation; that combination is covered ply by ply in test_philox_steps_vs_oracle."""
     az = _az()
+    nat = az._native
     L, seed, base = 1000, 77 + n, 5
-    env = az.SplendorEnv(n, L, seed=seed, game_base=base, use_tma=use_tma)
+    flags = nat.RULE_RESERVE | nat.RULE_GIVEBACK | (nat.RULE_REFCOMPAT if compat else 0)
+    env = az.SplendorEnv(n, L, seed=seed, game_base=base, use_tma=use_tma, rule_flags=flags)
     env.reset()
     fp = torch.zeros(L, dtype=torch.int32, device=env.device)
     fr = torch.zeros((L, n), dtype=torch.float32, device=env.device)
     K = 62 * n + 2
     env.rollout(K, rotate=rotate, first_plies=fp, first_result=fr)
-    total, plies, res = po.rollout(n, seed, base, L)
+    total, plies, res = po.rollout(n, seed, base, L, ref_compat=compat)
     assert np.array_equal(fp.cpu().numpy(), plies)
     assert np.array_equal(fr.cpu().numpy(), res)
     cnt = env.counters.cpu().numpy()
     assert cnt[1] == L * K and cnt[0] >= L
     # split into two launches: identical final state (the kernel is a pure function of (state, episode, player))
-    env2 = az.SplendorEnv(n, L, seed=seed, game_base=base, use_tma=use_tma)
+    env2 = az.SplendorEnv(n, L, seed=seed, game_base=base, use_tma=use_tma, rule_flags=flags)
     env2.reset()
     env2.rollout(K // 2, rotate=rotate)
     env2.rollout(K - K // 2, rotate=rotate)
