@@ -150,3 +150,85 @@ def rollout(n, seed, game0, games, ref_compat=True):
     plies = np.zeros(games, dtype=np.int32); res = np.zeros((games, n), dtype=np.float32)
     total = lib().spo_rollout(r, seed, game0, games, _p(plies, C.c_int32), _p(res, C.c_float))
     return total, plies, res
+
+
+# ---------------------------------------------------------------------------------------------- search oracle (mcts_oracle.h)
+class MoArgs(C.Structure):
+    _fields_ = [("num_sims", C.c_int), ("ratio_full", C.c_int), ("forced_playouts", C.c_int), ("dirichlet_noise", C.c_int),
+                ("cpuct", C.c_double), ("fpu", C.c_double), ("temperature0", C.c_double)]
+
+
+PREDICT_FN = C.CFUNCTYPE(None, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+
+
+def _mo():
+    L = lib()
+    if not getattr(L, "_mo_ready", False):
+        L.mo_create.restype = C.c_void_p
+        L.mo_create.argtypes = [C.POINTER(Rules), C.POINTER(MoArgs), C.c_void_p, C.c_void_p]
+        L.mo_destroy.argtypes = [C.c_void_p]
+        L.mo_reset.argtypes = [C.c_void_p]
+        L.mo_num_nodes.argtypes = [C.c_void_p]; L.mo_num_nodes.restype = C.c_long
+        L.mo_nn_calls.argtypes = [C.c_void_p]; L.mo_nn_calls.restype = C.c_long
+        L.mo_get_action_prob.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_double, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_float)]
+        L.mo_search.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+        L.mo_fake_predict.argtypes = [C.POINTER(C.c_int8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L._mo_ready = True
+    return L
+
+
+class MCTSOracle:
+    """the reference's MCTS (MCTS.py) restated in C; `predict(board int8[R,7], valids bool[406]) -> (Ps, v)` or None = fakenn"""
+
+    def __init__(self, n, num_sims, cpuct=1.0, fpu=0.0, forced_playouts=False, dirichlet_noise=False, ratio_full=5,
+                 temperature0=1.0, ref_compat=True, predict=None):
+        self.n = n
+        self.rules = Rules(n, 10, 1, 1, int(ref_compat))
+        self.args = MoArgs(num_sims, ratio_full, int(forced_playouts), int(dirichlet_noise), cpuct, fpu, temperature0)
+        self._cb = None
+        if predict is not None:
+            R = rows(n)
+
+            def cb(sp, vp, pp, vvp, _u):
+                st = np.ctypeslib.as_array(sp, shape=(R, 7)); va = np.ctypeslib.as_array(vp, shape=(ACTIONS,)).astype(np.bool_)
+                ps, v = predict(st, va)
+                np.ctypeslib.as_array(pp, shape=(ACTIONS,))[:] = ps
+                np.ctypeslib.as_array(vvp, shape=(n,))[:] = v
+            self._cb = PREDICT_FN(cb)
+        self._h = _mo().mo_create(self.rules, self.args, C.cast(self._cb, C.c_void_p) if self._cb else None, None)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _mo().mo_destroy(self._h); self._h = None
+
+    def reset(self):
+        _mo().mo_reset(self._h)
+
+    @property
+    def num_nodes(self):
+        return _mo().mo_num_nodes(self._h)
+
+    @property
+    def nn_calls(self):
+        return _mo().mo_nn_calls(self._h)
+
+    def get_action_prob(self, canonical, temp=1.0, full_search=True, dir_values=None):
+        st = np.ascontiguousarray(canonical, dtype=np.int8)
+        probs = np.zeros(ACTIONS); q = np.zeros(self.n); nsa = np.zeros(ACTIONS, dtype=np.int64); qsa = np.zeros(ACTIONS)
+        ns = C.c_long(); qs = C.c_float()
+        d = None if dir_values is None else np.ascontiguousarray(dir_values, dtype=np.float64)
+        rc = _mo().mo_get_action_prob(self._h, _p(st, C.c_int8), float(temp), int(full_search), None if d is None else _p(d, C.c_double),
+                                      _p(probs, C.c_double), _p(q, C.c_double), _p(nsa, C.c_int64), _p(qsa, C.c_double),
+                                      C.byref(ns), C.byref(qs))
+        if rc:
+            raise RuntimeError(f"mo_get_action_prob: {rc}")
+        return dict(probs=probs, q=q, nsa=nsa, qsa=qsa, ns=ns.value, qs=np.float32(qs.value))
+
+
+def fake_predict(state, valids, n):
+    st = np.ascontiguousarray(state, dtype=np.int8); va = np.ascontiguousarray(valids, dtype=np.uint8)
+    ps = np.zeros(ACTIONS, dtype=np.float32); v = np.zeros(n, dtype=np.float32)
+    _mo().mo_fake_predict(_p(st, C.c_int8), st.size, _p(va, C.c_uint8), n, _p(ps, C.c_float), _p(v, C.c_float))
+    return ps, v
