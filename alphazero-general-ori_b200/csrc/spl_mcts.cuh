@@ -1,0 +1,823 @@
+// GPU tree arena for MCTS - per-tree logic (device code; also compiled by g++ with a one-lane "warp"
+// for the test-only host simulator in tests/hostsim/, never by the product's host path).
+//
+// What it replaces in the reference (MCTS.py):
+//   mcts_select_tree   <- MCTS.search :99-177 down to the first unevaluated node, incl. pick_highest_UCB :199-219 and
+//                         get_next_best_action_and_canonical_state :222-237 (make_move deterministic + swap_players)
+//   mcts_expand_tree   <- the "first time that we explore state s" branch :134-148 (Ps from the network, normalise,
+//                         root softmax + Dirichlet noise :141-144,180-186) followed by the backup :168-177
+//   mcts_begin_tree    <- the dictionary lookup of the root (nodes_data.get :119-120) + tree cleaning :80-85
+//   mcts_policy_tree   <- getActionProb's tail :61-97 (counts, policy-target pruning, temperature)
+//
+// One tree = one game lane = one warp. The reference's `nodes_data` dictionary (exact state bytes -> node, a DAG with
+// transpositions that persists across moves) becomes a per-tree node pool + open-addressing hash table keyed by a
+// 64-bit state hash with a full-state compare. Nodes are either TERMINAL (Es stored), NEEDS_NN (legal edges allocated,
+// waiting for the network) or EXPANDED. Edges are sparse (only legal actions, in action order) and cache the child node
+// index, so an inner traversal touches no rules code at all.
+//
+// Numerics follow the reference exactly: Ps float32, Qsa float64 running mean, Qs float32, Nsa/Ns integers, the -42
+// "unvisited" sentinel, strict > in the arg-max (lowest action wins ties), forced-playout early return. All
+// floating-point statements use explicitly rounded single operations (no FMA contraction).
+#pragma once
+#include <math.h>
+#include "spl_rules.cuh"
+
+#define MCTS_UNVISITED (-42.0)   // NAN sentinel, MCTS.py:9
+#define MCTS_EPS 1e-8            // :8
+#define MCTS_KFORCED 0.5         // :10
+
+#ifdef __CUDACC__
+#define MC_DMUL(a, b) __dmul_rn((a), (b))
+#define MC_DADD(a, b) __dadd_rn((a), (b))
+#define MC_DDIV(a, b) __ddiv_rn((a), (b))
+#define MC_DSQRT(a) __dsqrt_rn((a))
+#define MC_FMUL(a, b) __fmul_rn((a), (b))
+#define MC_FADD(a, b) __fadd_rn((a), (b))
+#define MC_FDIV(a, b) __fdiv_rn((a), (b))
+#else   // host simulator: compiled with -ffp-contract=off
+#define MC_DMUL(a, b) ((a) * (b))
+#define MC_DADD(a, b) ((a) + (b))
+#define MC_DDIV(a, b) ((a) / (b))
+#define MC_DSQRT(a) sqrt((a))
+#define MC_FMUL(a, b) ((a) * (b))
+#define MC_FADD(a, b) ((a) + (b))
+#define MC_FDIV(a, b) ((a) / (b))
+#endif
+
+// ------------------------------------------------------------------------------------------
+// warp policy: 32 lanes on the device, 1 lane in the host simulator
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+struct MctsWarp {
+    int lane;
+    static constexpr int W = 32;
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ uint32_t lanemask_lt() const { return (1u << lane) - 1u; }
+    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+    __device__ __forceinline__ uint64_t sum64(uint64_t v) const {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ double sumd_tree(double v) const {   // fixed butterfly order (production-only sums)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v = MC_DADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ void best(double& u, int& idx) const {   // arg-max, lowest index wins ties; idx < 0 = none
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double ou = __shfl_xor_sync(0xffffffffu, u, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (oi >= 0 && (idx < 0 || ou > u || (ou == u && oi < idx))) { u = ou; idx = oi; }
+        }
+    }
+};
+#else
+struct MctsWarp {
+    int lane;
+    static constexpr int W = 1;
+    void sync() const {}
+    uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    uint32_t lanemask_lt() const { return 0u; }
+    int sum(int v) const { return v; }
+    uint64_t sum64(uint64_t v) const { return v; }
+    double sumd_tree(double v) const { return v; }
+    int shfl(int v, int) const { return v; }
+    void best(double&, int&) const {}
+};
+#endif
+
+// ------------------------------------------------------------------------------------------
+// arena layout (all in caller-owned HBM)
+// ------------------------------------------------------------------------------------------
+enum { MCTS_NODE_TERMINAL = 1, MCTS_NODE_NEEDS_NN = 2, MCTS_NODE_EXPANDED = 3 };
+enum { MCTS_F_FORCED = 1u, MCTS_F_NOISE = 2u };                       // per-move flags (getActionProb :54-58)
+enum { MCTS_S_OVERFLOW_NODES = 1u, MCTS_S_OVERFLOW_EDGES = 2u, MCTS_S_PROTOCOL = 4u };   // sticky status bits
+
+struct MctsNode {   // 32 B
+    uint64_t hash;
+    uint8_t ply, kind;
+    uint16_t n_edges;
+    uint32_t edge_off;
+    union {
+        struct { int32_t Ns; float Qs; uint32_t pad[2]; } x;   // EXPANDED / NEEDS_NN
+        float es[4];                                          // TERMINAL: getGameEnded vector
+    } u;
+};
+struct MctsEdge {   // 24 B
+    double Q;        // Qsa (float64, -42 = unvisited)
+    float P;         // Ps[a]
+    int32_t N;       // Nsa
+    uint32_t child;  // node index + 1 (0 = not linked yet)
+    uint16_t action, pad;
+};
+struct MctsTree {   // 64 B
+    int32_t n_nodes, n_edges, root, leaf;
+    int32_t sims_done, sims_target, path_len;
+    uint32_t flags, status;
+    int32_t nn_calls, resets, compactions;
+    int32_t pad[4];
+};
+struct MctsArena {
+    int n_trees, cap, ecap, hcap, sp, max_depth;
+    int8_t* states;    // [T][cap][sp]   node states, the reference's int8[R,7] bytes + zero padding to 16
+    MctsNode* nodes;   // [T][cap]
+    MctsEdge* edges;   // [T][ecap]
+    uint32_t* htab;    // [T][hcap]      node index + 1, linear probing
+    MctsTree* trees;   // [T]
+    uint32_t* path;    // [T][max_depth][2]  (node, absolute edge index) of the current simulation
+};
+struct MctsSearchParams {
+    double cpuct, fpu, temperature0, dirichlet_alpha;
+    uint64_t seed;
+    uint32_t game_base;
+    SplRules rules;
+};
+
+template <int N> struct MctsLay {
+    static constexpr int S = SplLay<N>::CELLS;
+    static constexpr int SP = (S + 15) / 16 * 16;
+    static constexpr int MAX_DEPTH = 62 * N + 8;
+};
+
+#ifdef __CUDACC__
+#define SPL_M __device__ __forceinline__
+#else
+#define SPL_M inline
+#endif
+struct AosAcc {   // the reference's own array order: cell (row, col) = byte 7*row + col
+    int8_t* p;
+    SPL_M int get(int row, int col) const { return p[7 * row + col]; }
+    SPL_M void set(int row, int col, int v) { p[7 * row + col] = (int8_t)v; }
+};
+
+SPL_D uint64_t mcts_mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return x;
+}
+
+// 64-bit hash of a padded state (sp bytes, 8-byte aligned): a sum of position-salted word mixes, so that any
+// partition of the words over lanes gives the same value
+template <class W>
+SPL_D uint64_t mcts_hash(const W& w, const int8_t* st, int sp) {
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(st);
+    uint64_t h = 0;
+    for (int i = w.lane; i < sp / 8; i += W::W) h += mcts_mix64(q[i] + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull);
+    return mcts_mix64(w.sum64(h));
+}
+
+template <class W>
+SPL_D void mcts_copy16(const W& w, void* dst, const void* src, int bytes) {   // bytes % 16 == 0, both 16-aligned
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = w.lane; i < bytes / 16; i += W::W) d[i] = s[i];
+}
+
+template <class W>
+SPL_D bool mcts_equal16(const W& w, const void* a, const void* b, int bytes) {
+    const uint4* x = reinterpret_cast<const uint4*>(a);
+    const uint4* y = reinterpret_cast<const uint4*>(b);
+    bool diff = false;
+    for (int i = w.lane; i < bytes / 16; i += W::W) {
+        const uint4 p = x[i], q = y[i];
+        diff |= (p.x != q.x) | (p.y != q.y) | (p.z != q.z) | (p.w != q.w);
+    }
+    return w.ballot(diff) == 0u;
+}
+
+// nodes_data.get(s) :120
+template <class W>
+SPL_D int mcts_lookup(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h) {
+    const uint32_t* tab = A.htab + (size_t)t * A.hcap;
+    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    uint32_t slot = (uint32_t)h & (uint32_t)(A.hcap - 1);
+    for (;;) {
+        const uint32_t e = tab[slot];
+        if (e == 0u) return -1;
+        const int idx = (int)e - 1;
+        if (nodes[idx].hash == h && mcts_equal16(w, A.states + ((size_t)t * A.cap + idx) * A.sp, st, A.sp)) return idx;
+        slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
+    }
+}
+
+template <class W>
+SPL_D void mcts_table_insert(const W& w, const MctsArena& A, int t, int idx, uint64_t h) {
+    if (w.lane == 0) {
+        uint32_t* tab = A.htab + (size_t)t * A.hcap;
+        uint32_t slot = (uint32_t)h & (uint32_t)(A.hcap - 1);
+        while (tab[slot] != 0u) slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
+        tab[slot] = (uint32_t)idx + 1u;
+    }
+    w.sync();
+}
+
+// New node for the state in `st` (sp bytes, zero padded): stores the bytes, computes getGameEnded (:124) and, for a
+// live position, getValidMoves (:136) -> one edge per legal action. Returns the node index or -1 on pool overflow.
+// `scratch` = 16 uint32 of per-warp scratch.
+template <int N, class W>
+SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
+    MctsTree* T = A.trees + t;
+    const int idx = T->n_nodes;
+    if (idx >= A.cap) {
+        if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_NODES;
+        w.sync();
+        return -1;
+    }
+    MctsNode* nd = A.nodes + (size_t)t * A.cap + idx;
+    if (w.lane == 0) {
+        AosAcc s{st};
+        float es[N];
+        const bool ended = spl_game_ended<N>(s, P.rules, es);
+        uint32_t* m = scratch;
+        int k = 0;
+        if (!ended) {
+            spl_valid_mask<N>(s, 0, P.rules, m);
+            for (int i = 0; i < SPL_MASK_WORDS; i++) k += SPL_POPC(m[i]);
+        }
+        scratch[13] = ended ? 1u : 0u;
+        scratch[14] = (uint32_t)k;
+        nd->hash = h;
+        nd->ply = (uint8_t)st[6];
+        nd->n_edges = (uint16_t)k;
+        nd->edge_off = (uint32_t)T->n_edges;
+        if (ended) {
+            nd->kind = MCTS_NODE_TERMINAL;
+            for (int i = 0; i < 4; i++) nd->u.es[i] = i < N ? es[i] : 0.f;
+        } else {
+            nd->kind = MCTS_NODE_NEEDS_NN;
+            nd->u.x.Ns = 0; nd->u.x.Qs = 0.f; nd->u.x.pad[0] = nd->u.x.pad[1] = 0u;
+        }
+    }
+    w.sync();
+    const bool ended = scratch[13] != 0u;
+    const int k = (int)scratch[14];
+    const int e0 = T->n_edges;
+    if (!ended && e0 + k > A.ecap) {
+        if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_EDGES;
+        w.sync();
+        return -1;
+    }
+    mcts_copy16(w, A.states + ((size_t)t * A.cap + idx) * A.sp, st, A.sp);
+    if (!ended) {   // edges in action order: word i of the mask owns a contiguous run
+        MctsEdge* ed = A.edges + (size_t)t * A.ecap + e0;
+        for (int i = w.lane; i < SPL_MASK_WORDS; i += W::W) {
+            int off = 0;
+            for (int j = 0; j < i; j++) off += SPL_POPC(scratch[j]);
+            uint32_t bits = scratch[i];
+            while (bits) {
+                const int b = SPL_FFS(bits) - 1;
+                bits &= bits - 1u;
+                MctsEdge e;
+                e.Q = MCTS_UNVISITED; e.P = 0.f; e.N = 0; e.child = 0u; e.action = (uint16_t)(32 * i + b); e.pad = 0;
+                ed[off++] = e;
+            }
+        }
+    }
+    w.sync();
+    if (w.lane == 0) {
+        T->n_nodes = idx + 1;
+        if (!ended) T->n_edges = e0 + k;
+    }
+    mcts_table_insert(w, A, t, idx, h);
+    return idx;
+}
+
+// ------------------------------------------------------------------------------------------
+// root softmax + Dirichlet noise (softmax :244-250, applyDirNoise :180-186, normalise :239-242)
+// ------------------------------------------------------------------------------------------
+// Marsaglia-Tsang gamma(alpha,1) for the on-device Dirichlet sampler (production; parity runs inject the vector)
+SPL_D double mcts_u01(uint32_t a, uint32_t b) { return ((double)(((uint64_t)a << 21) ^ (uint64_t)(b >> 11)) + 0.5) * (1.0 / 9007199254740992.0); }
+SPL_D double mcts_gamma(double alpha, uint64_t seed, uint32_t game, uint32_t ply, uint32_t k) {
+    const double a1 = alpha < 1.0 ? alpha + 1.0 : alpha;
+    const double d = a1 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double g = d;
+    for (uint32_t attempt = 0; attempt < 64u; attempt++) {
+        const SplPhilox r0 = spl_philox(seed, game, ply, k * 128u + 2u * attempt, 4);
+        const SplPhilox r1 = spl_philox(seed, game, ply, k * 128u + 2u * attempt + 1u, 4);
+        const double u1 = mcts_u01(r0.v[0], r0.v[1]), u2 = mcts_u01(r0.v[2], r0.v[3]), u3 = mcts_u01(r1.v[0], r1.v[1]);
+        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) {
+            g = d * v;
+            if (alpha < 1.0) g *= pow(mcts_u01(r1.v[2], r1.v[3]), 1.0 / alpha);
+            break;
+        }
+    }
+    return g;
+}
+
+// Ps <- normalise(0.75 * softmax(Ps, T0) + 0.25 * Dir) on the node's edges. dir (may be NULL): the vector
+// rng.dirichlet returned, one value per legal action in action order.
+template <class W>
+SPL_D void mcts_root_noise(const W& w, MctsEdge* ed, int k, const MctsSearchParams& P, const double* dir, uint32_t game, uint32_t ply,
+                           double* dscratch /* >= 2 doubles per warp */) {
+    if (P.temperature0 != 1.0) {   // Ps ** (1/T) in float64, normalised, back to float32 (softmax :247-250)
+        const double inv_t = 1.0 / P.temperature0;
+        if (w.lane == 0) {
+            double s = 0.0;
+            for (int i = 0; i < k; i++) s = MC_DADD(s, pow((double)ed[i].P, inv_t));
+            dscratch[0] = s;
+        }
+        w.sync();
+        const double s = dscratch[0];
+        for (int i = w.lane; i < k; i += W::W) ed[i].P = (float)MC_DDIV(pow((double)ed[i].P, inv_t), s);
+        w.sync();
+    }
+    double gsum = 1.0;
+    if (!dir) {   // Dirichlet(alpha) = iid gamma(alpha) / their sum; the gammas are recomputed below (counter-based)
+        double part = 0.0;
+        for (int i = w.lane; i < k; i += W::W) part = MC_DADD(part, mcts_gamma(P.dirichlet_alpha, P.seed, game, ply, (uint32_t)i));
+        gsum = w.sumd_tree(part);
+    }
+    for (int i = w.lane; i < k; i += W::W) {
+        const double dv = dir ? dir[i] : MC_DDIV(mcts_gamma(P.dirichlet_alpha, P.seed, game, ply, (uint32_t)i), gsum);
+        ed[i].P = (float)MC_DADD((double)MC_FMUL(0.75f, ed[i].P), MC_DMUL(0.25, dv));
+    }
+    w.sync();
+    if (w.lane == 0) {   // np.sum in float32, action order
+        float s = 0.f;
+        for (int i = 0; i < k; i++) s = MC_FADD(s, ed[i].P);
+        reinterpret_cast<float*>(dscratch)[0] = s;
+    }
+    w.sync();
+    const float s = reinterpret_cast<float*>(dscratch)[0];
+    for (int i = w.lane; i < k; i += W::W) ed[i].P = MC_FDIV(ed[i].P, s);
+    w.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// pick_highest_UCB :199-219 over the node's edges (already restricted to legal actions, in action order)
+// returns the edge position inside the node
+// ------------------------------------------------------------------------------------------
+template <class W>
+SPL_D int mcts_pick(const W& w, const MctsEdge* ed, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced, int n_iter) {
+    const double fpu_init = P.fpu > 0.0 ? MC_DADD((double)Qs, -P.fpu) : P.fpu;   // :202
+    const double sq_ns = MC_DSQRT((double)Ns), sq_ns_eps = MC_DSQRT(MC_DADD((double)Ns, MCTS_EPS));
+    double best_u = 0.0;
+    int best_i = -1, forced_i = 0x7fffffff;
+    for (int i = w.lane; i < k; i += W::W) {
+        const MctsEdge e = ed[i];
+        if (forced && forced_i == 0x7fffffff) {   // :207-208 - the first legal action short of its forced visits wins outright
+            const long long quota = (long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)n_iter));
+            if ((long long)e.N < quota) forced_i = i;
+        }
+        double u;
+        if (e.Q != MCTS_UNVISITED) u = MC_DADD(e.Q, MC_DDIV(MC_DMUL(MC_DMUL(P.cpuct, (double)e.P), sq_ns), (double)(1 + e.N)));   // :211
+        else u = MC_DADD(fpu_init, MC_DMUL(MC_DMUL(P.cpuct, (double)e.P), sq_ns_eps));                                                 // :213
+        if (best_i < 0 ? (u > -INFINITY) : (u > best_u)) { best_u = u; best_i = i; }                                                   // :215 strict >
+    }
+    if (forced) {
+        int f = forced_i;
+#ifdef __CUDACC__
+        f = __reduce_min_sync(0xffffffffu, f);
+#endif
+        if (f != 0x7fffffff) return f;
+    }
+    w.best(best_u, best_i);
+    return best_i;
+}
+
+// backup along the recorded path (:168-177). v = value vector in the frame of the node below the last edge;
+// executed by lane 0 only. np.roll(v, next_player) with next_player = 1 after every in-tree move.
+template <int N>
+SPL_D void mcts_backup(const MctsArena& A, int t, int depth, float* v) {
+    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+    const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    for (int d = depth - 1; d >= 0; d--) {
+        float r[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) r[(i + 1) % N] = v[i];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = r[i];
+        MctsNode* nd = nodes + path[2 * d];
+        MctsEdge* e = edges + path[2 * d + 1];
+        e->Q = MC_DDIV(MC_DADD(MC_DMUL((double)e->N, e->Q), (double)v[0]), (double)(e->N + 1));                               // :171
+        nd->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nd->u.x.Ns + 1), nd->u.x.Qs), v[0]), (float)(nd->u.x.Ns + 2));          // :172
+        e->N += 1;
+        nd->u.x.Ns += 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// selection: runs simulations of tree t until one reaches a node that needs the network (its state and legal
+// mask are written to the leaf row and 1 is returned) or the move's budget is spent (returns 0).
+// Simulations that end in a terminal node are backed up on the spot.
+// st: per-warp scratch of MctsLay<N>::SP bytes (16-aligned); scratch: 16 uint32; dscratch: 4 doubles
+// ------------------------------------------------------------------------------------------
+template <int N, class W>
+SPL_D int mcts_select_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint32_t* scratch, double* dscratch,
+                           const double* dir, int8_t* leaf_state, uint8_t* leaf_valid) {
+    typedef MctsLay<N> ML;
+    MctsTree* T = A.trees + t;
+    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    if (T->leaf >= 0) {   // the previous leaf was never expanded
+        if (w.lane == 0) T->status |= MCTS_S_PROTOCOL;
+        w.sync();
+        return 0;
+    }
+    int sims_done = T->sims_done;
+    const int target = T->sims_target;
+    const uint32_t flags = T->flags;
+    const int root = T->root;
+    while (sims_done < target && T->status == 0u) {
+        int cur = root, depth = 0;
+        bool aborted = false;
+        for (;;) {
+            MctsNode* nd = nodes + cur;
+            const int kind = nd->kind;
+            if (kind == MCTS_NODE_NEEDS_NN) {   // hand the position to the network (:136-138)
+                const int8_t* src = A.states + ((size_t)t * A.cap + cur) * A.sp;
+                for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
+                for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
+                w.sync();
+                const MctsEdge* ed = edges + nd->edge_off;
+                for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
+                if (w.lane == 0) { T->leaf = cur; T->path_len = depth; T->sims_done = sims_done; }
+                w.sync();
+                return 1;
+            }
+            if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
+            MctsEdge* ed = edges + nd->edge_off;
+            const int k = nd->n_edges;
+            if (depth == 0 && sims_done == 0 && (flags & MCTS_F_NOISE))   // revisited root, first simulation of a full search :150-154
+                mcts_root_noise(w, ed, k, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
+            const int ei = mcts_pick(w, ed, k, nd->u.x.Ns, nd->u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
+            if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd->edge_off + (uint32_t)ei; }
+            depth++;
+            MctsEdge* e = ed + ei;
+            uint32_t child = e->child;
+            if (child == 0u) {   // first traversal of this edge: make_move(a, 0, deterministic) + swap_players (:226-235)
+                mcts_copy16(w, st, A.states + ((size_t)t * A.cap + cur) * A.sp, A.sp);
+                w.sync();
+                if (w.lane == 0) {
+                    AosAcc s{st};
+                    SplChance ch;
+                    ch.mode = 0; ch.code = 0; ch.seed = 0; ch.game = 0; ch.episode = 0; ch.ply = 0;
+                    const int nxt = spl_apply_move<N>(s, (int)e->action, 0, ch);
+                    if (nxt > 0) spl_rotate<N>(s, nxt, P.rules);
+                }
+                w.sync();
+                const uint64_t h = mcts_hash(w, st, A.sp);
+                int idx = mcts_lookup(w, A, t, st, h);   // transposition: the dictionary may already hold this state
+                if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
+                if (idx < 0) { aborted = true; break; }
+                child = (uint32_t)idx + 1u;
+                if (w.lane == 0) e->child = child;
+                w.sync();
+            }
+            cur = (int)child - 1;
+        }
+        if (aborted) break;
+        if (w.lane == 0) {   // terminal: return Es up the path
+            float v[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = nodes[cur].u.es[i];
+            mcts_backup<N>(A, t, depth, v);
+        }
+        w.sync();
+        sims_done++;
+    }
+    if (w.lane == 0) T->sims_done = sims_done;
+    w.sync();
+    return 0;
+}
+
+// expansion + backup: pi = the network's probability row for the leaf (float32[406], masked softmax), v = float32[N]
+template <int N, class W>
+SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const float* pi, const float* vin,
+                            const double* dir, double* dscratch) {
+    MctsTree* T = A.trees + t;
+    const int leaf = T->leaf;
+    if (leaf < 0) return;
+    MctsNode* nd = A.nodes + (size_t)t * A.cap + leaf;
+    MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+    const int k = nd->n_edges;
+    for (int i = w.lane; i < k; i += W::W) ed[i].P = pi[ed[i].action];
+    w.sync();
+    if (leaf == T->root && T->sims_done == 0 && (T->flags & MCTS_F_NOISE)) {   // :141-143
+        mcts_root_noise(w, ed, k, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
+    } else {                                                                      // normalise :144
+        if (w.lane == 0) {
+            float s = 0.f;
+            for (int i = 0; i < k; i++) s = MC_FADD(s, ed[i].P);
+            reinterpret_cast<float*>(dscratch)[0] = s;
+        }
+        w.sync();
+        const float s = reinterpret_cast<float*>(dscratch)[0];
+        for (int i = w.lane; i < k; i += W::W) ed[i].P = MC_FDIV(ed[i].P, s);
+        w.sync();
+    }
+    if (w.lane == 0) {
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = vin[i];
+        nd->u.x.Ns = 0;
+        nd->u.x.Qs = v[0];   // :147
+        nd->kind = MCTS_NODE_EXPANDED;
+        mcts_backup<N>(A, t, T->path_len, v);
+        T->sims_done += 1;
+        T->leaf = -1;
+        T->nn_calls += 1;
+    }
+    w.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// start of a move: find or create the root; make room first if the pools could run out
+// ------------------------------------------------------------------------------------------
+// In-place compaction keeping nodes with ply >= min_ply. A node below the root's ply can never be looked up again
+// (every key carries its ply), so this is result-neutral - the reference's own cleaning (:80-85) relies on the same
+// fact. Node indices and edge offsets both grow in creation order, so every block only moves towards the front.
+template <class W>
+SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool use_marks) {
+    MctsTree* T = A.trees + t;
+    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+    uint32_t* remap = A.htab + (size_t)t * A.hcap;   // the table is rebuilt below; hcap >= 2 cap
+    int8_t* states = A.states + (size_t)t * A.cap * A.sp;
+    const int n_old = T->n_nodes;
+    int n_new = 0;
+    for (int base = 0; base < n_old; base += W::W) {
+        const int i = base + w.lane;
+        const bool live = i < n_old && (use_marks ? remap[i] != 0u : (int)nodes[i].ply >= min_ply);
+        const uint32_t b = w.ballot(live);
+        if (i < n_old) remap[i] = live ? (uint32_t)(n_new + SPL_POPC(b & w.lanemask_lt())) + 1u : 0u;
+        n_new += SPL_POPC(b);
+    }
+    w.sync();
+    int e_new = 0;
+    for (int i = 0; i < n_old; i++) {
+        const uint32_t r = remap[i];
+        if (r == 0u) continue;
+        const int j = (int)r - 1;
+        MctsNode nd = nodes[i];
+        const int ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
+        const int off = (int)nd.edge_off;
+        for (int c = 0; c < ne; c += W::W) {   // chunk-wise: read, sync, write (destination never passes the source)
+            const int k = c + w.lane;
+            MctsEdge e;
+            if (k < ne) {
+                e = edges[off + k];
+                if (e.child) e.child = remap[e.child - 1u];
+            }
+            w.sync();
+            if (k < ne) edges[e_new + k] = e;
+            w.sync();
+        }
+        if (j != i) {
+            for (int c = 0; c < A.sp / 16; c += W::W) {
+                const int k = c + w.lane;
+                uint4 x;
+                if (k < A.sp / 16) x = reinterpret_cast<const uint4*>(states + (size_t)i * A.sp)[k];
+                w.sync();
+                if (k < A.sp / 16) reinterpret_cast<uint4*>(states + (size_t)j * A.sp)[k] = x;
+            }
+        }
+        w.sync();
+        if (w.lane == 0) {
+            if (nd.kind != MCTS_NODE_TERMINAL) nd.edge_off = (uint32_t)e_new;
+            nodes[j] = nd;
+        }
+        e_new += ne;
+        w.sync();
+    }
+    for (int i = w.lane; i < A.hcap; i += W::W) remap[i] = 0u;
+    w.sync();
+    if (w.lane == 0) {
+        uint32_t* tab = remap;
+        for (int i = 0; i < n_new; i++) {
+            uint32_t slot = (uint32_t)nodes[i].hash & (uint32_t)(A.hcap - 1);
+            while (tab[slot] != 0u) slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
+            tab[slot] = (uint32_t)i + 1u;
+        }
+        T->n_nodes = n_new;
+        T->n_edges = e_new;
+        T->compactions += 1;
+    }
+    w.sync();
+}
+
+// marks (in the hash-table region, which the compaction rebuilds anyway) every node reachable from `root` through
+// linked edges: breadth-first, one node per step, its edges spread over the lanes. Tighter than the ply rule, but it
+// also drops nodes that a not-yet-linked edge could still transpose into (production mode; see mcts_begin_tree).
+template <class W>
+SPL_D void mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) {
+    MctsTree* T = A.trees + t;
+    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    const MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+    uint32_t* mark = A.htab + (size_t)t * A.hcap;
+    uint32_t* queue = mark + A.cap;   // hcap >= 2 cap
+    const int n_old = T->n_nodes;
+    for (int i = w.lane; i < n_old; i += W::W) mark[i] = i == root ? 1u : 0u;
+    if (w.lane == 0) queue[0] = (uint32_t)root;
+    w.sync();
+    int head = 0, tail = 1;
+    while (head < tail) {
+        const MctsNode nd = nodes[queue[head++]];
+        const int ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
+        for (int c = 0; c < ne; c += W::W) {
+            const int k = c + w.lane;
+            bool fresh = false;
+            uint32_t child = 0u;
+            if (k < ne) {
+                child = edges[nd.edge_off + k].child;
+                if (child) {
+#ifdef __CUDACC__
+                    fresh = atomicExch(&mark[child - 1u], 1u) == 0u;
+#else
+                    fresh = mark[child - 1u] == 0u;
+                    mark[child - 1u] = 1u;
+#endif
+                }
+            }
+            const uint32_t b = w.ballot(fresh);
+            if (fresh) queue[tail + SPL_POPC(b & w.lanemask_lt())] = child - 1u;
+            tail += SPL_POPC(b);
+            w.sync();
+        }
+    }
+    w.sync();
+}
+
+template <class W>
+SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_all_search_trees :188-192 for one tree
+    uint32_t* tab = A.htab + (size_t)t * A.hcap;
+    for (int i = w.lane; i < A.hcap; i += W::W) tab[i] = 0u;
+    if (w.lane == 0) {
+        MctsTree* T = A.trees + t;
+        T->n_nodes = 0; T->n_edges = 0; T->root = -1; T->leaf = -1; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
+        T->flags = 0u; T->status = 0u;
+    }
+    w.sync();
+}
+
+// root_state: the reference's int8[R,7] bytes. edge_reserve: edges budgeted per new node when deciding to clean.
+// gc_reachable = 0: cleaning keeps every node with ply >= the root's (exactly result-neutral, the parity mode);
+// gc_reachable = 1: keeps only what is reachable from the new root (production: far smaller pools; a node that only a
+// not-yet-linked edge transposes into is re-created instead of found, which the reference's dictionary would not do).
+template <int N, class W>
+SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* root_state, int sims_target,
+                           uint32_t flags, int edge_reserve, int gc_reachable, int8_t* st, uint32_t* scratch) {
+    typedef MctsLay<N> ML;
+    MctsTree* T = A.trees + t;
+    for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
+    w.sync();
+    const int root_ply = (int)(uint8_t)st[6];
+    const uint64_t h = mcts_hash(w, st, A.sp);
+    const int need_nodes = sims_target + 2, need_edges = (sims_target + 2) * edge_reserve;
+    if (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
+        bool cleared = false;
+        if (gc_reachable) {
+            const int old_root = mcts_lookup(w, A, t, st, h);
+            if (old_root >= 0) {
+                mcts_mark_reachable(w, A, t, old_root);
+                mcts_compact(w, A, t, 0, true);
+            } else {   // a root the tree has never seen (a card was revealed): nothing of the old tree can be reached
+                const int resets = T->resets;
+                mcts_clear_tree(w, A, t);
+                if (w.lane == 0) T->resets = resets;
+                w.sync();
+                cleared = true;
+            }
+        } else {
+            mcts_compact(w, A, t, root_ply, false);
+        }
+        if (!cleared && (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap)) {   // still no room: forget the tree (counted)
+            const int resets = T->resets;
+            mcts_clear_tree(w, A, t);
+            if (w.lane == 0) T->resets = resets + 1;
+            w.sync();
+        }
+    }
+    int idx = mcts_lookup(w, A, t, st, h);
+    if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
+    if (w.lane == 0) {
+        T->root = idx; T->leaf = -1; T->sims_done = 0; T->sims_target = idx < 0 ? 0 : sims_target; T->path_len = 0;
+        T->flags = flags;
+    }
+    w.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// getActionProb's tail (:61-97) for one tree: probs double[406], q double[N]
+// temp == 0 -> one-hot of the FIRST best action (the reference picks a random one among ties)
+// ------------------------------------------------------------------------------------------
+template <int N, class W>
+SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, double* probs, double* q, double* dscratch) {
+    const MctsTree* T = A.trees + t;
+    for (int a = w.lane; a < SPL_ACTIONS; a += W::W) probs[a] = 0.0;
+    w.sync();
+    if (T->root < 0) return;
+    const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+    if (nd->kind != MCTS_NODE_EXPANDED) return;
+    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+    const int k = nd->n_edges;
+    const bool forced = (T->flags & MCTS_F_FORCED) != 0u;
+    if (w.lane == 0) {
+        const float qs = nd->u.x.Qs;
+        for (int p = 0; p < N; p++) q[p] = p == 0 ? (double)qs : (double)MC_FDIV(-qs, (float)(N - 1));   // :65-66
+        int best = 0;
+        for (int i = 0; i < k; i++) best = ed[i].N > best ? ed[i].N : best;
+        double sum = 0.0;
+        int besti = -1;
+        double bestc = -1.0;
+        for (int i = 0; i < k; i++) {
+            double c = (double)ed[i].N;
+            if (forced) {   // policy target pruning :69-74
+                if (ed[i].N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)ed[i].P), (double)T->sims_target));
+                c = c > 1.0 ? c : 0.0;
+            }
+            if (c > bestc) { bestc = c; besti = i; }
+            if (temp != 0.0) {
+                c = temp == 1.0 ? c : pow(c, 1.0 / temp);   // :94
+                sum = MC_DADD(sum, c);
+            }
+            probs[ed[i].action] = c;
+        }
+        if (temp == 0.0) {   // :87-92
+            for (int i = 0; i < k; i++) probs[ed[i].action] = i == besti ? 1.0 : 0.0;
+        } else {
+            for (int i = 0; i < k; i++) probs[ed[i].action] = MC_DDIV(probs[ed[i].action], sum);   // :95-96
+        }
+    }
+    (void)dscratch;
+    w.sync();
+}
+
+// raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[8]
+template <class W>
+SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* nsa, double* qsa, float* ps, int32_t* info) {
+    const MctsTree* T = A.trees + t;
+    for (int a = w.lane; a < SPL_ACTIONS; a += W::W) {
+        if (nsa) nsa[a] = 0;
+        if (qsa) qsa[a] = MCTS_UNVISITED;
+        if (ps) ps[a] = 0.f;
+    }
+    w.sync();
+    int ns = 0;
+    float qs = 0.f;
+    if (T->root >= 0) {
+        const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+        if (nd->kind == MCTS_NODE_EXPANDED) {
+            const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+            for (int i = w.lane; i < (int)nd->n_edges; i += W::W) {
+                if (nsa) nsa[ed[i].action] = ed[i].N;
+                if (qsa) qsa[ed[i].action] = ed[i].Q;
+                if (ps) ps[ed[i].action] = ed[i].P;
+            }
+            ns = nd->u.x.Ns; qs = nd->u.x.Qs;
+        }
+    }
+    if (info && w.lane == 0) {
+        info[0] = T->n_nodes; info[1] = T->n_edges; info[2] = ns; info[3] = T->sims_done; info[4] = T->nn_calls;
+        info[5] = (int32_t)T->status; info[6] = T->resets * 65536 + T->compactions;
+        memcpy(&info[7], &qs, 4);
+    }
+    w.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// deterministic stand-in network ("fixed NN outputs"): policy and values are a pure function of the state bytes,
+// all probabilities multiples of 2^-13 that sum to exactly 1 (tests/golden/mcts_*.npz were produced by the
+// reference's own MCTS.py with the same function as its network)
+// ------------------------------------------------------------------------------------------
+template <int N, class W>
+SPL_D void mcts_fixed_net_row(const W& w, const int8_t* state, const uint8_t* valid, float* pi, float* v, uint32_t* scratch) {
+    typedef MctsLay<N> ML;
+    if (w.lane == 0) {
+        uint64_t h = 0xCBF29CE484222325ull;   // FNV-1a 64 over the state bytes
+        for (int i = 0; i < ML::S; i++) { h ^= (uint64_t)(uint8_t)state[i]; h *= 0x100000001B3ull; }
+        scratch[0] = (uint32_t)h; scratch[1] = (uint32_t)(h >> 32);
+    }
+    w.sync();
+    const uint64_t h = (uint64_t)scratch[0] | ((uint64_t)scratch[1] << 32);
+    int part = 0, first = SPL_ACTIONS;
+    for (int a = w.lane; a < SPL_ACTIONS; a += W::W) {
+        float p = 0.f;
+        if (valid[a]) {
+            const int wgt = 1 + (int)(mcts_mix64(h + (uint64_t)a * 0x9E3779B97F4A7C15ull) >> 58);
+            p = (float)wgt;
+            part += wgt;
+            if (first == SPL_ACTIONS) first = a;
+        }
+        pi[a] = p;
+    }
+    const int total = w.sum(part);
+#ifdef __CUDACC__
+    first = __reduce_min_sync(0xffffffffu, first);
+#endif
+    w.sync();
+    if (w.lane == 0 && first < SPL_ACTIONS) pi[first] += (float)(8192 - total);
+    w.sync();
+    for (int a = w.lane; a < SPL_ACTIONS; a += W::W) pi[a] = pi[a] / 8192.f;
+    for (int p = w.lane; p < N; p += W::W) v[p] = (float)((double)((long long)((h >> (8 * p + 3)) & 0x7Full) - 64) / 64.0);
+    w.sync();
+}

@@ -1,0 +1,85 @@
+// TEST-ONLY: compiles the tree-arena logic (csrc/spl_mcts.cuh) with g++ and a one-lane "warp" so that the search
+// semantics can be checked against the golden fixtures in the GPU-less build container. Never loaded by the product.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+struct uint4 { uint32_t x, y, z, w; };
+#include "../../alphazero-general-ori_b200/csrc/spl_mcts.cuh"
+
+#define DISPATCH(n, CALL) switch (n) { case 2: { constexpr int N = 2; CALL; } break; case 3: { constexpr int N = 3; CALL; } break; default: { constexpr int N = 4; CALL; } }
+
+struct HsMcts {
+    int n;
+    MctsArena A;
+    MctsSearchParams P;
+    int edge_reserve, gc_reachable;
+    int8_t* leaf_state;
+    uint8_t* leaf_valid;
+    float *pi, *v;
+};
+
+extern "C" {
+HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, double cpuct, double fpu, double temperature0, int edge_reserve, int gc_reachable) {
+    HsMcts* m = (HsMcts*)calloc(1, sizeof *m);
+    m->n = n;
+    MctsArena& A = m->A;
+    A.n_trees = 1; A.cap = cap; A.ecap = ecap;
+    A.hcap = 1; while (A.hcap < 2 * cap) A.hcap *= 2;
+    A.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
+    A.max_depth = 62 * n + 8;
+    A.states = (int8_t*)aligned_alloc(16, (size_t)cap * A.sp);
+    A.nodes = (MctsNode*)calloc(cap, sizeof(MctsNode));
+    A.edges = (MctsEdge*)calloc(ecap, sizeof(MctsEdge));
+    A.htab = (uint32_t*)calloc(A.hcap, 4);
+    A.trees = (MctsTree*)calloc(1, sizeof(MctsTree));
+    A.path = (uint32_t*)calloc((size_t)A.max_depth * 2, 4);
+    A.trees[0].root = -1; A.trees[0].leaf = -1;
+    m->P.cpuct = cpuct; m->P.fpu = fpu; m->P.temperature0 = temperature0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
+    m->P.rules.limit = limit; m->P.rules.flags = rule_flags;
+    m->edge_reserve = edge_reserve; m->gc_reachable = gc_reachable;
+    m->leaf_state = (int8_t*)calloc(A.sp, 1);
+    m->leaf_valid = (uint8_t*)calloc(SPL_ACTIONS, 1);
+    m->pi = (float*)calloc(SPL_ACTIONS, 4);
+    m->v = (float*)calloc(4, 4);
+    return m;
+}
+void hm_destroy(HsMcts* m) {
+    free(m->A.states); free(m->A.nodes); free(m->A.edges); free(m->A.htab); free(m->A.trees); free(m->A.path);
+    free(m->leaf_state); free(m->leaf_valid); free(m->pi); free(m->v); free(m);
+}
+void hm_reset(HsMcts* m) {
+    MctsWarp w{0};
+    mcts_clear_tree(w, m->A, 0);
+    m->A.trees[0].nn_calls = 0;
+}
+// one getActionProb: begin + (select, fixed network, expand) until the budget is spent. Returns the tree status bits.
+int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const double* dir) {
+    MctsWarp w{0};
+    alignas(16) int8_t st[640];
+    uint32_t scratch[16];
+    double dscratch[4];
+    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->edge_reserve, m->gc_reachable, st, scratch));
+    for (;;) {
+        int leaf = 0;
+        DISPATCH(m->n, leaf = mcts_select_tree<N>(w, m->A, 0, m->P, st, scratch, dscratch, dir, m->leaf_state, m->leaf_valid));
+        if (!leaf) break;
+        DISPATCH(m->n, mcts_fixed_net_row<N>(w, m->leaf_state, m->leaf_valid, m->pi, m->v, scratch));
+        DISPATCH(m->n, mcts_expand_tree<N>(w, m->A, 0, m->P, m->pi, m->v, dir, dscratch));
+    }
+    return (int)m->A.trees[0].status;
+}
+void hm_policy(HsMcts* m, double temp, double* probs, double* q) {
+    MctsWarp w{0};
+    double dscratch[4];
+    DISPATCH(m->n, mcts_policy_tree<N>(w, m->A, 0, temp, probs, q, dscratch));
+}
+void hm_root_stats(HsMcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info8) {
+    MctsWarp w{0};
+    mcts_root_stats_tree(w, m->A, 0, nsa, qsa, ps, info8);
+}
+void hm_fixed_net(int n, const int8_t* state, const uint8_t* valid, float* pi, float* v) {
+    MctsWarp w{0};
+    uint32_t scratch[16];
+    DISPATCH(n, mcts_fixed_net_row<N>(w, state, valid, pi, v, scratch));
+}
+}

@@ -85,3 +85,67 @@ class Sim:
 def pick_random(words, seed, game, episode, ply):
     w = np.ascontiguousarray(words, dtype=np.uint32)
     return lib().hs_pick_random(_p(w, C.c_uint32), seed, game, episode, ply)
+
+
+# ---------------------------------------------------------------------------------------------- tree arena (csrc/spl_mcts.cuh)
+LIB_MCTS = os.path.join(HERE, "libhostsim_mcts.so")
+_lib_mcts = None
+MCTS_F_FORCED, MCTS_F_NOISE = 1, 2
+
+
+def lib_mcts():
+    global _lib_mcts
+    if _lib_mcts is None:
+        deps = [os.path.join(HERE, "hostsim_mcts.cpp")] + [os.path.join(CSRC, f) for f in ("spl_mcts.cuh", "spl_rules.cuh", "spl_tables.cuh")]
+        if not os.path.isfile(LIB_MCTS) or any(os.path.getmtime(d) > os.path.getmtime(LIB_MCTS) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-ffp-contract=off",
+                                   "-o", LIB_MCTS, os.path.join(HERE, "hostsim_mcts.cpp")])
+        L = C.CDLL(LIB_MCTS)
+        L.hm_create.restype = C.c_void_p
+        L.hm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.hm_destroy.argtypes = [C.c_void_p]
+        L.hm_reset.argtypes = [C.c_void_p]
+        L.hm_search.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.c_uint32, C.POINTER(C.c_double)]
+        L.hm_policy.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.hm_root_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.hm_fixed_net.argtypes = [C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib_mcts = L
+    return _lib_mcts
+
+
+class TreeSim:
+    """one tree of the arena driven on the host: getActionProb = begin + (select, fixed network, expand)*"""
+
+    def __init__(self, n, num_sims, cpuct=1.0, fpu=0.0, forced_playouts=False, dirichlet_noise=False, ratio_full=5,
+                 temperature0=1.0, cap=4096, ecap=None, edge_reserve=32, gc_reachable=False, limit=10, flags=F_RESERVE | F_GIVEBACK | F_REFCOMPAT):
+        self.n, self.num_sims, self.forced, self.noise, self.ratio = n, num_sims, forced_playouts, dirichlet_noise, ratio_full
+        self._h = lib_mcts().hm_create(n, cap, ecap or cap * 48, limit, flags, cpuct, fpu, temperature0, edge_reserve, int(gc_reachable))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib_mcts().hm_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib_mcts().hm_reset(self._h)
+
+    def get_action_prob(self, canonical, temp=1.0, full_search=True, dir_values=None):
+        st = np.ascontiguousarray(canonical, dtype=np.int8)
+        sims = self.num_sims if full_search else self.num_sims // self.ratio
+        fl = (MCTS_F_FORCED if (full_search and self.forced) else 0) | (MCTS_F_NOISE if (full_search and self.noise) else 0)
+        d = None if dir_values is None else np.ascontiguousarray(dir_values, dtype=np.float64)
+        status = lib_mcts().hm_search(self._h, _p(st, C.c_int8), sims, fl, None if d is None else _p(d, C.c_double))
+        probs = np.zeros(406); q = np.zeros(self.n)
+        lib_mcts().hm_policy(self._h, float(temp), _p(probs, C.c_double), _p(q, C.c_double))
+        nsa = np.zeros(406, dtype=np.int32); qsa = np.zeros(406); ps = np.zeros(406, dtype=np.float32); info = np.zeros(8, dtype=np.int32)
+        lib_mcts().hm_root_stats(self._h, _p(nsa, C.c_int32), _p(qsa, C.c_double), _p(ps, C.c_float), _p(info, C.c_int32))
+        return dict(probs=probs, q=q, nsa=nsa.astype(np.int64), qsa=qsa, ps=ps, ns=int(info[2]), qs=info[7:8].view(np.float32)[0],
+                    nodes=int(info[0]), edges=int(info[1]), nn_calls=int(info[4]), status=status, resets=int(info[6]) >> 16,
+                    compactions=int(info[6]) & 0xFFFF)
+
+
+def fixed_net(state, valids, n):
+    st = np.ascontiguousarray(state, dtype=np.int8); va = np.ascontiguousarray(valids, dtype=np.uint8)
+    pi = np.zeros(406, dtype=np.float32); v = np.zeros(4, dtype=np.float32)
+    lib_mcts().hm_fixed_net(n, _p(st, C.c_int8), _p(va, C.c_uint8), _p(pi, C.c_float), _p(v, C.c_float))
+    return pi, v[:n]

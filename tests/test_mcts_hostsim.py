@@ -1,0 +1,118 @@
+"""Tree-arena logic (csrc/spl_mcts.cuh) compiled for the host with a one-lane warp vs the golden fixtures produced by
+the reference's own MCTS.py and vs the C search oracle. This is how the CUDA tree code's *semantics* are checked in the
+GPU-less container; tests/test_gpu_mcts.py repeats it through the real kernels and the C ABI.
+Bar: visit counts, node count and network-call count exact; Qsa within 1e-12 (the spec asks 1e-6); Qs exact.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.hostsim import sim as hs
+
+SCEN = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mcts_*.npz")))
+
+
+def test_fixed_network_matches():
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 4):
+        b = po.Board(n); b.init_philox(11, n)
+        for _ in range(40):
+            v = b.valid_moves(0)
+            p0, v0 = po.fake_predict(b.state, v, n)
+            p1, v1 = hs.fixed_net(b.state, v, n)
+            assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+            b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -1); b.swap_players(1)
+
+
+def _check(out, g, i, name, nodes_exact=True):
+    assert out["status"] == 0
+    assert np.array_equal(out["nsa"], g["nsa"][i]), (name, i, "visit counts")
+    assert out["ns"] == g["ns"][i] and out["nn_calls"] == g["nn_calls"][i]
+    if nodes_exact:
+        assert out["nodes"] == g["nodes"][i]
+    assert np.allclose(out["qsa"], g["qsa"][i], rtol=0, atol=1e-12), (name, i, np.abs(out["qsa"] - g["qsa"][i]).max())
+    assert out["qs"] == g["qs"][i]
+    assert np.allclose(out["probs"], g["probs"][i], rtol=0, atol=1e-12)
+    assert np.allclose(out["q"], g["q"][i], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", SCEN)
+def test_tree_reproduces_reference_mcts(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
+    cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
+    m = hs.TreeSim(n, sims, cpuct=cpuct, fpu=fpu, forced_playouts=bool(forced), dirichlet_noise=bool(noise), ratio_full=ratio)
+    for i in range(len(g["ns"])):
+        d = g["dir"][i] if g["dir_len"][i] > 0 else (np.zeros(406) if noise else None)
+        out = m.get_action_prob(g["root"][i], temp=1.0, full_search=bool(g["full"][i]), dir_values=d)
+        _check(out, g, i, name)
+        assert out["compactions"] == 0 and out["resets"] == 0
+
+
+@pytest.mark.parametrize("n,seed,cap", [(2, 1, 8192), (2, 2, 8192), (3, 3, 8192), (4, 4, 8192), (2, 5, 2600), (3, 6, 4200), (4, 7, 3400)])
+def test_tree_vs_search_oracle_random_games(n, seed, cap):
+    """longer searches than the fixtures, mid-game roots with Philox reveals between moves (fresh roots + reuse).
+    The small pools force the ply-based cleaning before several moves: it must be result-neutral (the search oracle
+    never cleans)."""
+    rng = np.random.default_rng(seed)
+    sims = 500
+    kw = dict(cpuct=1.0 + 0.5 * seed, fpu=0.1 * (seed % 3), forced_playouts=bool(seed & 1), dirichlet_noise=bool(seed & 2), ratio_full=4)
+    mo = po.MCTSOracle(n, sims, **kw)
+    mt = hs.TreeSim(n, sims, cap=cap, **kw)
+    b = po.Board(n); b.init_philox(77, seed)
+    for _ in range(12 + 4 * n):    # random opening
+        v = b.valid_moves(0)
+        b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, 77, seed, 0); b.swap_players(1)
+    for mv in range(10):
+        if b.check_end_game().any():
+            break
+        full = bool(rng.random() < 0.7)
+        k = int(b.valid_moves(0).sum())
+        d = np.zeros(406); d[:k] = rng.dirichlet([0.3] * k)
+        o = mo.get_action_prob(b.state, temp=1.0, full_search=full, dir_values=d)
+        t = mt.get_action_prob(b.state, temp=1.0, full_search=full, dir_values=d)
+        assert t["status"] == 0
+        assert np.array_equal(o["nsa"], t["nsa"]), (mv, "visit counts")
+        assert o["ns"] == t["ns"] and mo.nn_calls == t["nn_calls"] and t["resets"] == 0
+        assert mo.num_nodes == t["nodes"] or (cap < 8192 and t["compactions"] > 0)
+        assert np.allclose(o["qsa"], t["qsa"], rtol=0, atol=1e-12) and o["qs"] == t["qs"]
+        assert np.allclose(o["probs"], t["probs"], rtol=0, atol=1e-12) and np.allclose(o["q"], t["q"], rtol=0, atol=1e-12)
+        a = int(np.argmax(o["nsa"]))
+        b.make_move(a, 0, -2 if mv % 2 else -1, 77, seed, 0); b.swap_players(1)
+    if cap < 8192:
+        assert t["compactions"] > 0
+
+
+@pytest.mark.parametrize("n,seed", [(2, 11), (3, 12), (4, 13)])
+def test_reachable_gc_keeps_a_consistent_tree(n, seed):
+    """production cleaning (keep only what the new root reaches) with a pool of a few moves: every search must still be a
+    complete, self-consistent search (budget spent, counts add up, no lossy reset) and the carried-over subtree must
+    keep its statistics (root Ns before the move's simulations >= the chosen child's visit count - 1 when no card was revealed)."""
+    rng = np.random.default_rng(seed)
+    sims, CAP = 400, 2400
+    mt = hs.TreeSim(n, sims, cap=CAP, cpuct=1.5, fpu=0.2, gc_reachable=True)
+    b = po.Board(n); b.init_philox(99, seed)
+    for _ in range(10 + 4 * n):
+        v = b.valid_moves(0)
+        b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, 99, seed, 0); b.swap_players(1)
+    prev_child_n, carried = None, 0
+    for mv in range(14):
+        if b.check_end_game().any():
+            break
+        t = mt.get_action_prob(b.state, temp=1.0, full_search=True)
+        assert t["status"] == 0 and t["resets"] == 0 and t["nodes"] <= CAP
+        assert t["nsa"].sum() == t["ns"] and abs(t["probs"].sum() - 1.0) < 1e-12
+        if prev_child_n is not None and prev_child_n > 1:       # reused root: its old visits are still there
+            assert t["ns"] >= sims + prev_child_n - 1     # (>: a transposition can feed the node from other parents)
+            carried += 1
+        else:
+            assert t["ns"] in (sims - 1, sims)
+        a = int(np.argmax(t["nsa"]))
+        before = b.state.copy()
+        b.make_move(a, 0, -1, 99, seed, 0)          # no reveal: the new root is a node of the tree
+        prev_child_n = int(t["nsa"][a])
+        b.swap_players(1)
+    assert carried >= 5 and t["compactions"] >= 1
