@@ -7,5 +7,7 @@ The compute path is hand-written sm_100a CUDA in csrc/, reached through the C AB
 from . import _native
 from .engine import SplendorEnv, rows
 from .game import Board, SplendorGame, action_size, observation_size
+from .mcts import MCTS, MCTSArena
+from .nnet import SplendorNNetB200
 
-__all__ = ["SplendorEnv", "SplendorGame", "Board", "observation_size", "action_size", "rows", "_native"]
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "observation_size", "action_size", "rows", "_native"]

@@ -27,7 +27,11 @@ EXPORTS = [
     "spl_state_rows", "spl_state_bytes", "spl_lanes_padded", "spl_planes_bytes", "spl_mask_planes_bytes",
     "spl_pack", "spl_unpack", "spl_mask_unpack", "spl_reset_philox", "spl_reset_explicit", "spl_step", "spl_rollout",
     "spl_scores", "spl_symmetries",
+    "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_begin",
+    "spl_mcts_select", "spl_mcts_expand", "spl_mcts_policy", "spl_mcts_root_stats", "spl_mcts_fixed_net",
 ]
+MCTS_MOVE_FORCED, MCTS_MOVE_NOISE = 1, 2
+MCTS_INFO_WORDS = 12
 
 
 class StepArgs(C.Structure):
@@ -48,6 +52,13 @@ class RolloutArgs(C.Structure):
     ]
 
 
+class MctsParams(C.Structure):
+    _fields_ = [
+        ("cpuct", C.c_double), ("fpu", C.c_double), ("temperature0", C.c_double), ("dirichlet_alpha", C.c_double),
+        ("seed", C.c_uint64), ("game_base", C.c_uint32), ("edge_reserve", C.c_int), ("gc_reachable", C.c_int),
+    ]
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + \
         sorted(os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f.endswith(".h"))
@@ -60,8 +71,18 @@ def is_stale():
 def build(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU"""
     if force or is_stale():
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "spl_env.cu")]
-        subprocess.check_call(cmd)
+        units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+        objdir = os.path.join(HERE, "build")
+        os.makedirs(objdir, exist_ok=True)
+        flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+        procs = []
+        for u in units:   # one nvcc per translation unit, in parallel
+            obj = os.path.join(objdir, u[:-3] + ".o")
+            procs.append((u, obj, subprocess.Popen(["nvcc"] + flags + ["-c", "-o", obj, os.path.join(CSRC, u)])))
+        for u, _, p in procs:
+            if p.wait() != 0:
+                raise RuntimeError(f"nvcc failed on {u}")
+        subprocess.check_call(["nvcc"] + NVCC_FLAGS + ["-o", LIB] + [obj for _, obj, _ in procs])
     return LIB
 
 
@@ -99,6 +120,19 @@ def lib():
         L.spl_rollout.argtypes = [vp, C.POINTER(RolloutArgs), vp]
         L.spl_scores.argtypes = [vp, vp, ci, vp, vp, vp]
         L.spl_symmetries.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+        L.spl_mcts_arena_bytes.argtypes = [ci, ci, ci, ci]
+        L.spl_mcts_arena_bytes.restype = C.c_size_t
+        L.spl_mcts_create.argtypes = [vp, ci, ci, ci, vp, C.c_size_t, C.POINTER(vp)]
+        L.spl_mcts_destroy.argtypes = [vp]
+        L.spl_mcts_destroy.restype = None
+        L.spl_mcts_set_params.argtypes = [vp, C.POINTER(MctsParams)]
+        L.spl_mcts_reset.argtypes = [vp, vp, vp]
+        L.spl_mcts_begin.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.spl_mcts_select.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.spl_mcts_expand.argtypes = [vp, vp, vp, vp, vp]
+        L.spl_mcts_policy.argtypes = [vp, C.c_double, vp, vp, vp]
+        L.spl_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.spl_mcts_fixed_net.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -20,21 +20,15 @@
 #define TL SPL_LANE_TILE   // 32 lanes per tile
 static_assert(TL == 32, "one warp per tile");
 
-struct spl_ctx {
-    int n;
-    SplRules rules;
-    int device;
-    int use_tma;
-    int sm_count;
-};
+#include "spl_internal.h"
 
 static thread_local char g_err[256] = "";
-static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+int spl_fail_(int code, const char* what, cudaError_t e) {
     if (e != cudaSuccess) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
     else snprintf(g_err, sizeof g_err, "%s", what);
     return code;
 }
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SPL_E_CUDA, #call, e_); } while (0)
+#define fail spl_fail_
 
 // ------------------------------------------------------------------------------------------
 // shared-memory tile accessor: cell (row, col) of this lane = byte [(7 row + col) * 32 + lane]
@@ -489,13 +483,6 @@ __global__ void __launch_bounds__(128) spl_sym_kernel(const int8_t* __restrict__
 // ==========================================================================================
 // host side of the C ABI
 // ==========================================================================================
-#define DISPATCH_N(n, ...)                                   \
-    switch (n) {                                             \
-        case 2: { constexpr int N = 2; __VA_ARGS__; } break; \
-        case 3: { constexpr int N = 3; __VA_ARGS__; } break; \
-        default: { constexpr int N = 4; __VA_ARGS__; } break;\
-    }
-
 template <int N> struct Cfg {   // small CTAs (2 warps = 2 tiles) so that shared memory packs tightly: 9 / 7 / 5 CTAs per SM
     static constexpr int WARPS = 2;
     static constexpr int SMEM = WARPS * SplLay<N>::CELLS * TL;

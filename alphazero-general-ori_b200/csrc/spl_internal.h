@@ -1,0 +1,23 @@
+// host-side internals shared by the translation units of libsplendor_b200.so (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/splendor_b200.h"
+#include "spl_rules.cuh"
+
+struct spl_ctx {
+    int n;
+    SplRules rules;
+    int device;
+    int use_tma;
+    int sm_count;
+};
+
+int spl_fail_(int code, const char* what, cudaError_t e = cudaSuccess);   // records spl_last_error() text, returns code
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return spl_fail_(SPL_E_CUDA, #call, e_); } while (0)
+
+#define DISPATCH_N(n, ...)                                   \
+    switch (n) {                                             \
+        case 2: { constexpr int N = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int N = 3; __VA_ARGS__; } break; \
+        default: { constexpr int N = 4; __VA_ARGS__; } break;\
+    }

@@ -119,7 +119,7 @@ struct MctsTree {   // 64 B
     int32_t sims_done, sims_target, path_len;
     uint32_t flags, status;
     int32_t nn_calls, resets, compactions;
-    int32_t pad[4];
+    float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
 };
 struct MctsArena {
     int n_trees, cap, ecap, hcap, sp, max_depth;
@@ -402,6 +402,9 @@ SPL_D void mcts_backup(const MctsArena& A, int t, int depth, float* v) {
         e->N += 1;
         nd->u.x.Ns += 1;
     }
+    MctsTree* T = A.trees + t;
+#pragma unroll
+    for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? v[i] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -752,7 +755,7 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
     w.sync();
 }
 
-// raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[8]
+// raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[12]
 template <class W>
 SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* nsa, double* qsa, float* ps, int32_t* info) {
     const MctsTree* T = A.trees + t;
@@ -780,6 +783,7 @@ SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* 
         info[0] = T->n_nodes; info[1] = T->n_edges; info[2] = ns; info[3] = T->sims_done; info[4] = T->nn_calls;
         info[5] = (int32_t)T->status; info[6] = T->resets * 65536 + T->compactions;
         memcpy(&info[7], &qs, 4);
+        memcpy(&info[8], T->last_v, 16);
     }
     w.sync();
 }

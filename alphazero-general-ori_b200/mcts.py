@@ -1,0 +1,281 @@
+"""MCTS on the GPU tree arena (C ABI: include/splendor_b200.h, "MCTS tree arena").
+
+Two surfaces:
+
+* `MCTSArena` - the batched engine: T trees (one per game lane) searched in lock-step waves
+  (`begin` -> repeat `select` -> network -> `expand` -> `policy`). Every tree runs exactly the reference's sequential
+  algorithm (MCTS.py:99-177); the batch is the number of trees. Leaves are handed to the network as device tensors
+  (`leaf_states` int8[T,R,7], `leaf_valids` uint8[T,406]) with no copy - they are torch tensors, i.e. DLPack-exportable.
+* `MCTS` - drop-in mirror of the reference class (MCTS.py:16-192): same constructor, `getActionProb(canonicalBoard, temp,
+  force_full_search, bias) -> (list, list, bool)`, `search`, `reset_all_search_trees`, attributes `step`, `last_cleaning`,
+  `rng`, so Coach.py:46,75,122 / Arena.py:171 / pit.py:54-91 drive it unchanged. It is an arena with one tree whose
+  network is whatever `nnet.predict(board, valids)` the caller supplies (GenericNNetWrapper.py:141).
+
+No CPU path: both raise without a CUDA device.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .engine import rows
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class MCTSArena:
+    def __init__(self, n_players, n_trees, node_cap, edge_cap=None, device=0, cpuct=1.0, fpu=0.0, temperature0=1.0,
+                 dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, token_limit=10,
+                 rule_flags=nat.RULES_DEFAULT):
+        if not torch.cuda.is_available():
+            raise RuntimeError("MCTSArena needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.n, self.T = int(n_players), int(n_trees)
+        self.R, self.S = rows(self.n), 7 * rows(self.n)
+        self.device = torch.device("cuda", device)
+        self.node_cap = int(node_cap)
+        self.edge_cap = int(edge_cap) if edge_cap else self.node_cap * 40
+        self._lib = nat.lib()
+        h = C.c_void_p()
+        nat.check(self._lib.spl_ctx_create(self.n, token_limit, rule_flags, device, C.byref(h)))
+        self._ctx = h
+        nbytes = self._lib.spl_mcts_arena_bytes(self.n, self.T, self.node_cap, self.edge_cap)
+        with torch.cuda.device(self.device):
+            self.arena = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.arena.data_ptr()) % 256
+            self._arena_ptr = self.arena.data_ptr() + off
+            self.leaf_states = torch.zeros((self.T, self.R, 7), dtype=torch.int8, device=self.device)
+            self.leaf_valids = torch.zeros((self.T, nat.NUM_ACTIONS), dtype=torch.uint8, device=self.device)
+            self.leaf_flags = torch.zeros(self.T, dtype=torch.uint8, device=self.device)
+            self.counters = torch.zeros(2, dtype=torch.int32, device=self.device)
+        m = C.c_void_p()
+        nat.check(self._lib.spl_mcts_create(self._ctx, self.T, self.node_cap, self.edge_cap, C.c_void_p(self._arena_ptr), nbytes, C.byref(m)))
+        self._m = m
+        self.arena_bytes = nbytes
+        self.params = dict(cpuct=cpuct, fpu=fpu, temperature0=temperature0, dirichlet_alpha=dirichlet_alpha, seed=seed,
+                           game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)))
+        self.set_params()
+        self.launches = 0
+        self.reset()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_m", None):
+                self._lib.spl_mcts_destroy(self._m); self._m = None
+            if getattr(self, "_ctx", None):
+                self._lib.spl_ctx_destroy(self._ctx); self._ctx = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_params(self, **kw):
+        self.params.update(kw)
+        p = nat.MctsParams(**{k: self.params[k] for k, _ in nat.MctsParams._fields_})
+        nat.check(self._lib.spl_mcts_set_params(self._m, C.byref(p)))
+
+    def set_rules(self, token_limit=10, rule_flags=nat.RULES_DEFAULT):
+        nat.check(self._lib.spl_ctx_set_rules(self._ctx, token_limit, rule_flags))
+
+    # ------------------------------------------------------------------ the wave protocol
+    def reset(self, tree_select=None):
+        """reset_all_search_trees (MCTS.py:188-192)"""
+        nat.check(self._lib.spl_mcts_reset(self._m, _ptr(tree_select), self._stream()))
+        self.launches += 1
+
+    def begin(self, roots, sims, move_flags=None, tree_select=None):
+        """roots int8[T,R,7] canonical boards (device), sims int32[T], move_flags uint8[T] (MCTS_MOVE_FORCED | MCTS_MOVE_NOISE)"""
+        assert roots.dtype == torch.int8 and roots.is_cuda and roots.is_contiguous() and roots.numel() == self.T * self.S
+        assert sims.dtype == torch.int32 and sims.numel() == self.T
+        self._hold = (roots, sims, move_flags, tree_select)
+        nat.check(self._lib.spl_mcts_begin(self._m, _ptr(roots), _ptr(sims), _ptr(move_flags), _ptr(tree_select), self._stream()))
+        self.launches += 1
+
+    def select(self, dir_values=None, count=False):
+        nat.check(self._lib.spl_mcts_select(self._m, _ptr(dir_values), _ptr(self.leaf_states), _ptr(self.leaf_valids),
+                                            _ptr(self.leaf_flags), _ptr(self.counters) if count else None, self._stream()))
+        self.launches += 1
+
+    def expand(self, pi, v, dir_values=None):
+        assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.numel() == self.T * nat.NUM_ACTIONS
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.numel() == self.T * self.n
+        nat.check(self._lib.spl_mcts_expand(self._m, _ptr(pi), _ptr(v), _ptr(dir_values), self._stream()))
+        self.launches += 1
+
+    def fixed_net(self, states=None, valids=None, pi=None, v=None):
+        """the deterministic stand-in network (exact dyadic outputs) on device rows"""
+        states = self.leaf_states if states is None else states
+        valids = self.leaf_valids if valids is None else valids
+        B = states.numel() // self.S
+        if pi is None:
+            pi = torch.empty((B, nat.NUM_ACTIONS), dtype=torch.float32, device=self.device)
+        if v is None:
+            v = torch.empty((B, self.n), dtype=torch.float32, device=self.device)
+        nat.check(self._lib.spl_mcts_fixed_net(self._ctx, _ptr(states), _ptr(valids), B, _ptr(pi), _ptr(v), self._stream()))
+        self.launches += 1
+        return pi, v
+
+    def search(self, roots, sims, evaluator, move_flags=None, dir_values=None, tree_select=None, waves=None):
+        """one getActionProb for every tree: `evaluator(leaf_states, leaf_valids) -> (pi float32[T,406], v float32[T,n])`
+        on the device. Runs max(sims) waves (every wave finishes at least one simulation of every unfinished tree), with
+        no host synchronisation inside."""
+        self.begin(roots, sims, move_flags, tree_select)
+        if waves is None:
+            waves = int(sims.max().item())
+        for _ in range(waves):
+            self.select(dir_values)
+            pi, v = evaluator(self.leaf_states, self.leaf_valids)
+            self.expand(pi, v, dir_values)
+        self.select(dir_values)   # drains simulations that end in terminal nodes; emits no leaf once the budgets are spent
+
+    def policy(self, temp=1.0):
+        """getActionProb's tail (MCTS.py:61-97) -> (probs float64[T,406], q float64[T,n])"""
+        probs = torch.empty((self.T, nat.NUM_ACTIONS), dtype=torch.float64, device=self.device)
+        q = torch.empty((self.T, self.n), dtype=torch.float64, device=self.device)
+        nat.check(self._lib.spl_mcts_policy(self._m, float(temp), _ptr(probs), _ptr(q), self._stream()))
+        self.launches += 1
+        return probs, q
+
+    def root_stats(self, want_arrays=True):
+        """-> dict of device tensors: nsa int32[T,406], qsa float64[T,406], ps float32[T,406], and per-tree scalars"""
+        T, A = self.T, nat.NUM_ACTIONS
+        nsa = torch.empty((T, A), dtype=torch.int32, device=self.device) if want_arrays else None
+        qsa = torch.empty((T, A), dtype=torch.float64, device=self.device) if want_arrays else None
+        ps = torch.empty((T, A), dtype=torch.float32, device=self.device) if want_arrays else None
+        info = torch.empty((T, nat.MCTS_INFO_WORDS), dtype=torch.int32, device=self.device)
+        nat.check(self._lib.spl_mcts_root_stats(self._m, _ptr(nsa), _ptr(qsa), _ptr(ps), _ptr(info), self._stream()))
+        self.launches += 1
+        return dict(nsa=nsa, qsa=qsa, ps=ps, nodes=info[:, 0], edges=info[:, 1], ns=info[:, 2], sims_done=info[:, 3],
+                    nn_calls=info[:, 4], status=info[:, 5], resets=info[:, 6] >> 16, cleanings=info[:, 6] & 0xFFFF,
+                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32))
+
+    def check_status(self):
+        st = self.root_stats(want_arrays=False)["status"]
+        bad = int(st.max().item())
+        if bad:
+            raise nat.NativeError(f"MCTS arena: tree status bits {bad} (1 node pool full, 2 edge pool full, 4 protocol): "
+                                  f"raise node_cap/edge_cap (now {self.node_cap}/{self.edge_cap})")
+
+
+class MCTS:
+    """Mirror of the reference's `MCTS` (MCTS.py:16-192) on a one-tree arena."""
+
+    _instances = weakref.WeakSet()
+
+    def __init__(self, game, nnet, args, dirichlet_noise=False, batch_info=None, node_cap=None, device=None):
+        self.game = game
+        self.nnet = nnet
+        self.args = args
+        self.dirichlet_noise = dirichlet_noise
+        self.batch_info = batch_info
+        self.rng = np.random.default_rng()
+        self.step = 0
+        self.last_cleaning = 0
+        n = game.num_players
+        sims = int(args.numMCTSSims)
+        dev = device if device is not None else getattr(game, "_device", 0)
+        board = getattr(game, "board", None)
+        limit = getattr(board, "NUM_TOKEN_LIMIT", 10)
+        flags = getattr(board, "_flags", nat.RULES_DEFAULT)
+        temperature0 = 1.0
+        if dirichlet_noise:
+            temperature0 = float(args.temperature[0])
+        self._arena = MCTSArena(n, 1, node_cap or max(4096, 10 * sims), device=dev, cpuct=float(args.cpuct), fpu=float(args.fpu),
+                                temperature0=temperature0, dirichlet_alpha=float(getattr(args, "dirichletAlpha", 0.3) or 0.3),
+                                token_limit=limit, rule_flags=flags)
+        self._dev = self._arena.device
+        self._root = torch.zeros((1, self._arena.R, 7), dtype=torch.int8, device=self._dev)
+        self._sims = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        self._flags = torch.zeros(1, dtype=torch.uint8, device=self._dev)
+        self._dir = torch.zeros((1, nat.NUM_ACTIONS), dtype=torch.float64, device=self._dev)
+        self._pi = torch.zeros((1, nat.NUM_ACTIONS), dtype=torch.float32, device=self._dev)
+        self._v = torch.zeros((1, n), dtype=torch.float32, device=self._dev)
+        MCTS._instances.add(self)
+
+    # ------------------------------------------------------------------
+    @property
+    def nodes_data(self):
+        """the reference exposes its dictionary; here only its size is meaningful"""
+        return range(int(self._arena.root_stats(want_arrays=False)["nodes"][0].item()))
+
+    @nodes_data.setter
+    def nodes_data(self, value):
+        if not value:
+            self._arena.reset()
+
+    def _sync_rules(self):
+        board = getattr(self.game, "board", None)
+        if board is not None and hasattr(board, "_flags"):
+            self._arena.set_rules(board.NUM_TOKEN_LIMIT, board._flags)
+
+    def _run(self, canonicalBoard, nb, forced, noise):
+        ar = self._arena
+        self._sync_rules()
+        self._root.copy_(torch.from_numpy(np.ascontiguousarray(canonicalBoard, dtype=np.int8)).view(1, ar.R, 7))
+        self._sims.fill_(int(nb))
+        self._flags.fill_((nat.MCTS_MOVE_FORCED if forced else 0) | (nat.MCTS_MOVE_NOISE if noise else 0))
+        dirv = None
+        if noise:   # applyDirNoise (:180-186): one value per legal action, drawn from the host generator like the reference
+            k = int(np.count_nonzero(self.game.getValidMoves(canonicalBoard, 0)))
+            d = np.zeros(nat.NUM_ACTIONS, dtype=np.float64)
+            d[:k] = self.rng.dirichlet([self.args.dirichletAlpha] * k)
+            self._dir.copy_(torch.from_numpy(d).view(1, -1))
+            dirv = self._dir
+        ar.begin(self._root, self._sims, self._flags)
+        while True:
+            ar.select(dirv)
+            if int(ar.leaf_flags[0].item()) == 0:
+                break
+            board = ar.leaf_states[0].cpu().numpy()
+            valids = ar.leaf_valids[0].cpu().numpy().astype(np.bool_)
+            if self.batch_info is None:
+                ps, v = self.nnet.predict(board, valids)
+            else:
+                ps, v = self.nnet.predict_client(board, valids, self.batch_info)
+            self._pi.copy_(torch.from_numpy(np.ascontiguousarray(ps, dtype=np.float32)).view(1, -1))
+            self._v.copy_(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).view(1, -1))
+            ar.expand(self._pi, self._v, dirv)
+        ar.check_status()
+
+    def getActionProb(self, canonicalBoard, temp=1, force_full_search=False, bias=None):
+        """MCTS.py:45-97 -> (probs list[float] len 406, q list[float] len n, is_full_search bool)"""
+        is_full_search = bool(force_full_search or (self.rng.random() < self.args.prob_fullMCTS))
+        nb = self.args.numMCTSSims if is_full_search else self.args.numMCTSSims // self.args.ratio_fullMCTS
+        forced = bool(is_full_search and self.args.forced_playouts)
+        noise = bool(is_full_search and self.dirichlet_noise)
+        self._run(canonicalBoard, nb, forced, noise)
+        self.step = max(0, int(nb) - 1)
+        if temp == 0:   # :87-92 - a random one among the most visited
+            st = self._arena.root_stats()
+            counts = st["nsa"][0].cpu().numpy().astype(np.int64)
+            if forced:
+                probs1, _ = self._arena.policy(1.0)
+                counts = probs1[0].cpu().numpy()
+            best = np.flatnonzero(counts == counts.max())
+            a = int(np.random.choice(best))
+            probs = [0] * nat.NUM_ACTIONS
+            probs[a] = 1
+            _, q = self._arena.policy(1.0)
+            return probs, [float(x) for x in q[0].cpu().numpy()], is_full_search
+        probs, q = self._arena.policy(float(temp))
+        return [float(x) for x in probs[0].cpu().numpy()], [float(x) for x in q[0].cpu().numpy()], is_full_search
+
+    def search(self, canonicalBoard, dirichlet_noise=False, forced_playouts=False):
+        """one simulation (MCTS.py:99-177; called directly by SplendorPlayers.py:178) -> float32[n]"""
+        self._run(canonicalBoard, 1, bool(forced_playouts), bool(dirichlet_noise))
+        return self._arena.root_stats(want_arrays=False)["last_v"][0].cpu().numpy().astype(np.float32)
+
+    def root_stats(self):
+        st = self._arena.root_stats()
+        return {k: (v[0].cpu().numpy() if v is not None else None) for k, v in st.items()}
+
+    @staticmethod
+    def reset_all_search_trees():
+        """MCTS.py:188-192"""
+        for obj in list(MCTS._instances):
+            obj._arena.reset()
+            obj.last_cleaning = 0

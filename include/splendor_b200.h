@@ -146,6 +146,73 @@ int spl_scores(spl_ctx* ctx, const int8_t* planes, int n_lanes, int32_t* scores,
 int spl_symmetries(spl_ctx* ctx, const int8_t* aos, const float* pi, const uint8_t* valids, int n_lanes,
                    int8_t* out_states, float* out_pi, uint8_t* out_valids, int32_t* out_count, void* stream);
 
+/* ======================================================================================================
+ * MCTS tree arena  (replaces MCTS.py:16-250)
+ *
+ * One tree per game lane, one warp per tree. The reference's `nodes_data` dictionary (exact state bytes -> node; a DAG
+ * with transpositions that persists across moves until reset_all_search_trees, MCTS.py:36,119-120,188-192) is a per-tree
+ * node pool + hash table inside one caller-owned device buffer. A move is searched in waves:
+ *
+ *     spl_mcts_begin                      root lookup / creation, tree cleaning            (getActionProb :45-58)
+ *     repeat: spl_mcts_select             descend by PUCT to an unevaluated node           (search :99-166, :199-237)
+ *             <network on leaf rows>      caller-side (torch / any device code)            (nnet.predict :138)
+ *             spl_mcts_expand             store Ps, root noise, back the value up          (:141-148, :168-177)
+ *     spl_mcts_policy                     counts -> pruning -> temperature -> probs, q     (:61-97)
+ *
+ * Every tree runs exactly the reference's sequential algorithm (one leaf per tree per wave); the batch is the number
+ * of trees. Simulations that end in a terminal node are backed up inside spl_mcts_select without a network call.
+ * ====================================================================================================== */
+typedef struct spl_mcts spl_mcts;
+
+#define SPL_MCTS_MOVE_FORCED 1u   /* forced playouts + policy-target pruning for this move (:56, :69-74) */
+#define SPL_MCTS_MOVE_NOISE 2u    /* root softmax + Dirichlet noise on the first simulation (:58, :141-143, :150-154) */
+
+#define SPL_MCTS_ST_OVERFLOW_NODES 1  /* tree status bits (info[5] of spl_mcts_root_stats) */
+#define SPL_MCTS_ST_OVERFLOW_EDGES 2
+#define SPL_MCTS_ST_PROTOCOL 4        /* select called while a leaf was still waiting for spl_mcts_expand */
+
+typedef struct {
+    double   cpuct, fpu;        /* args.cpuct, args.fpu (pick_highest_UCB :199-213) */
+    double   temperature0;      /* args.temperature[0]: root softmax before the noise (:141, :244-250) */
+    double   dirichlet_alpha;   /* args.dirichletAlpha (:181); used by the on-device sampler when dir_values == NULL */
+    uint64_t seed;              /* Philox key of the on-device Dirichlet sampler, counter (game, root ply, action rank) */
+    uint32_t game_base;         /* game id of tree 0 */
+    int      edge_reserve;      /* edges budgeted per new node when deciding whether to clean before a move (default 32) */
+    int      gc_reachable;      /* 0: cleaning keeps every node with ply >= root ply - result-neutral, like the reference's
+                                   own cleaning :80-85 (default); 1: keeps only what the new root reaches (smaller pools) */
+} spl_mcts_params;
+
+/* bytes of device memory an arena needs; node_cap / edge_cap are per tree */
+size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_cap, int edge_cap);
+/* MCTS.__init__ (:21-43): `arena` is caller-owned device memory of at least spl_mcts_arena_bytes, 256-byte aligned */
+int  spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void* arena, size_t arena_bytes, spl_mcts** out);
+void spl_mcts_destroy(spl_mcts* m);
+int  spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p);
+/* reset_all_search_trees (:188-192); tree_select (may be NULL) restricts it to trees with a non-zero byte */
+int  spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream);
+/* start of getActionProb for every (selected) tree: roots int8[T][R*7] canonical boards, sims int32[T] simulation budget
+ * (numMCTSSims or numMCTSSims // ratio_fullMCTS, :55), move_flags uint8[T] of SPL_MCTS_MOVE_* */
+int  spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const uint8_t* move_flags, const uint8_t* tree_select,
+                    void* stream);
+/* one selection wave. Outputs per tree: leaf_states int8[T][R*7], leaf_valids uint8[T][406] (getValidMoves of the leaf),
+ * leaf_flags uint8[T] (1: this row needs the network). dir_values (may be NULL): double[T][406], the vector
+ * rng.dirichlet would return for the tree's root, one value per legal action in action order.
+ * counters (may be NULL): int32[2], [0] += rows that need the network, [1] += trees whose budget is not yet spent. */
+int  spl_mcts_select(spl_mcts* m, const double* dir_values, int8_t* leaf_states, uint8_t* leaf_valids, uint8_t* leaf_flags,
+                     int32_t* counters, void* stream);
+/* pi float[T][406] = the network's probabilities (exp of the masked log-softmax, GenericNNetWrapper.py:166), v float[T][n] */
+int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double* dir_values, void* stream);
+/* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */
+int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* stream);
+/* raw root statistics, any pointer may be NULL: nsa int32[T][406], qsa double[T][406] (-42 = unvisited), ps float[T][406],
+ * info int32[T][12] = nodes, edges, root Ns, simulations done, network calls since reset, status bits,
+ *                     lossy resets * 65536 + cleanings, root Qs (float bits), then 4 floats (bits): the value vector the last
+ *                     finished simulation returned at the root (what MCTS.search returns, :99-177) */
+int  spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info, void* stream);
+/* deterministic stand-in network ("fixed NN outputs"): a pure function of the state bytes with exact dyadic outputs; the
+ * golden MCTS fixtures were produced by the reference's own MCTS.py with this function as its network */
+int  spl_mcts_fixed_net(spl_ctx* ctx, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,218 @@
+"""GPU parity tests of the MCTS tree arena, through the C ABI (include/splendor_b200.h, spl_mcts_*).
+
+Bar (BASELINE.json north_star): MCTS visit counts identical, Q within 1e-6 (we hold 1e-12) for fixed NN outputs.
+  * golden: tests/golden/mcts_*.npz - outputs of the reference's own MCTS.py (cross-move tree reuse, transpositions,
+    forced playouts, Dirichlet noise, playout cap, 2/3/4 players), network = the fixed dyadic function
+  * live: random mid-game roots vs the C search oracle, many trees per launch, ragged budgets
+  * the drop-in `MCTS` class driven like Coach/Arena with a host `predict`
+  * the leaf evaluator on the device vs the reference network's recorded outputs
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SCEN = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mcts_*.npz")))
+
+
+def _azg():
+    import azg_b200
+    return azg_b200
+
+
+def _np(x):
+    return x.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", SCEN)
+def test_arena_reproduces_reference_mcts(golden_dir, name):
+    az = _azg()
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
+    cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
+    T = 3   # the same search in three trees at once: they must not disturb each other
+    ar = az.MCTSArena(n, T, node_cap=4096, cpuct=cpuct, fpu=fpu)
+    dev = ar.device
+    for i in range(len(g["ns"])):
+        full = bool(g["full"][i])
+        nb = sims if full else sims // ratio
+        fl = (1 if (full and forced) else 0) | (2 if (full and noise) else 0)
+        roots = torch.from_numpy(np.repeat(g["root"][i][None], T, 0)).to(dev)
+        simt = torch.full((T,), nb, dtype=torch.int32, device=dev)
+        flt = torch.full((T,), fl, dtype=torch.uint8, device=dev)
+        dirv = torch.from_numpy(np.repeat(g["dir"][i][None], T, 0)).to(dev).contiguous() if noise else None
+        ar.search(roots, simt, lambda s, v: ar.fixed_net(s, v), flt, dirv)
+        ar.check_status()
+        st = ar.root_stats()
+        probs, q = ar.policy(1.0)
+        for t in range(T):
+            assert np.array_equal(_np(st["nsa"][t]).astype(np.int64), g["nsa"][i]), (name, i, t, "visit counts")
+            assert int(st["ns"][t]) == g["ns"][i] and int(st["nodes"][t]) == g["nodes"][i] and int(st["nn_calls"][t]) == g["nn_calls"][i]
+            assert np.allclose(_np(st["qsa"][t]), g["qsa"][i], rtol=0, atol=1e-12)
+            assert _np(st["qs"])[t] == g["qs"][i]
+            assert np.allclose(_np(probs[t]), g["probs"][i], rtol=0, atol=1e-12)
+            assert np.allclose(_np(q[t]), g["q"][i], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_arena_vs_search_oracle_many_trees(n):
+    """64 different mid-game roots per launch, ragged budgets and flags, three consecutive moves with tree reuse and
+    a pool small enough to force the ply-based cleaning"""
+    az = _azg()
+    from oracle import pyoracle as po
+    T, rng = 64, np.random.default_rng(100 + n)
+    kw = dict(cpuct=1.7, fpu=0.15)
+    ar = az.MCTSArena(n, T, node_cap=1200, **kw)
+    dev = ar.device
+    boards, oracles, budgets, flags = [], [], [], []
+    for t in range(T):
+        b = po.Board(n); b.init_philox(4242, t)
+        for _ in range(int(rng.integers(0, 40 * n))):
+            if b.check_end_game().any():
+                break
+            v = b.valid_moves(0)
+            b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, 4242, t, 0); b.swap_players(1)
+        if b.check_end_game().any():
+            b.init_philox(4242, 1000 + t)
+        boards.append(b)
+        sims = int(rng.integers(40, 260))
+        fl = int(rng.integers(0, 4))
+        budgets.append(sims); flags.append(fl)
+        oracles.append(po.MCTSOracle(n, sims, forced_playouts=bool(fl & 1), dirichlet_noise=bool(fl & 2), **kw))
+    cleaned = 0
+    for mv in range(4):
+        roots = torch.from_numpy(np.stack([b.state for b in boards])).to(dev)
+        dirs = np.zeros((T, 406))
+        for t, b in enumerate(boards):
+            k = int(b.valid_moves(0).sum())
+            dirs[t, :k] = rng.dirichlet([0.3] * k)
+        ar.search(roots, torch.tensor(budgets, dtype=torch.int32, device=dev), lambda s, v: ar.fixed_net(s, v),
+                  torch.tensor(flags, dtype=torch.uint8, device=dev), torch.from_numpy(dirs).to(dev))
+        ar.check_status()
+        st = ar.root_stats()
+        probs, q = ar.policy(1.0)
+        nsa, qsa, ns, qs, nnc = _np(st["nsa"]), _np(st["qsa"]), _np(st["ns"]), _np(st["qs"]), _np(st["nn_calls"])
+        assert int(st["resets"].max()) == 0
+        cleaned = int(st["cleanings"].max())
+        for t, b in enumerate(boards):
+            if b.check_end_game().any():
+                continue
+            o = oracles[t].get_action_prob(b.state, temp=1.0, full_search=True, dir_values=dirs[t])
+            assert np.array_equal(o["nsa"], nsa[t].astype(np.int64)), (mv, t, "visit counts")
+            assert o["ns"] == ns[t] and oracles[t].nn_calls == nnc[t]
+            assert np.allclose(o["qsa"], qsa[t], rtol=0, atol=1e-12) and o["qs"] == qs[t]
+            assert np.allclose(o["probs"], _np(probs[t]), rtol=0, atol=1e-12) and np.allclose(o["q"], _np(q[t]), rtol=0, atol=1e-12)
+            a = int(np.argmax(o["nsa"]))
+            b.make_move(a, 0, -2 if (t + mv) % 3 == 0 else -1, 4242, t, 0); b.swap_players(1)
+    assert cleaned > 0
+
+
+def test_fixed_net_kernel_matches_oracle():
+    az = _azg()
+    from oracle import pyoracle as po
+    for n in (2, 3, 4):
+        ar = az.MCTSArena(n, 1, node_cap=64)
+        states, valids = [], []
+        b = po.Board(n); b.init_philox(5, n)
+        rng = np.random.default_rng(n)
+        for _ in range(50):
+            v = b.valid_moves(0)
+            states.append(b.state.copy()); valids.append(v.astype(np.uint8))
+            b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -1); b.swap_players(1)
+        s = torch.from_numpy(np.stack(states)).to(ar.device); va = torch.from_numpy(np.stack(valids)).to(ar.device)
+        pi, v = ar.fixed_net(s, va)
+        for i in range(len(states)):
+            p0, v0 = po.fake_predict(states[i], valids[i], n)
+            assert np.array_equal(_np(pi[i]), p0) and np.array_equal(_np(v[i]), v0)
+
+
+class _FakeRng:
+    def __init__(self, coin, seed):
+        self.coin, self.seed, self.last_dir = coin, seed, None
+
+    def random(self):
+        return self.coin
+
+    def dirichlet(self, alphas):
+        from oracle import fakenn
+        self.seed += 1
+        self.last_dir = fakenn.dirichlet(self.seed, len(alphas))
+        return self.last_dir
+
+
+class _DotDict(dict):
+    def __getattr__(self, name):
+        return self[name]
+
+
+@pytest.mark.parametrize("name", ["b_n2_forced_noise", "e_n2_cap", "g_n3_late"])
+def test_mcts_class_is_a_drop_in(golden_dir, name):
+    """the reference-surface class driven exactly as oracle/refgen/gen_mcts_golden.py drove the reference's MCTS:
+    same args object, a host `predict` network, an injected rng - same returned probs / q / flags"""
+    az = _azg()
+    from oracle import fakenn
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
+    cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
+    game = az.SplendorGame(n)
+    args = _DotDict(numMCTSSims=sims, prob_fullMCTS=prob_full, ratio_fullMCTS=ratio, forced_playouts=bool(forced), cpuct=cpuct, fpu=fpu,
+                    no_mem_optim=True, temperature=[1.0, 1.0], dirichletAlpha=0.3)
+    nnet = fakenn.FakeNNet(n)
+    mcts = az.MCTS(game, nnet, args, dirichlet_noise=bool(noise))
+    mcts.rng = _FakeRng(0.5, seed=sum(map(ord, name)))
+    for i in range(len(g["ns"])):
+        probs, q, full = mcts.getActionProb(g["root"][i], temp=1, force_full_search=bool(force))
+        assert isinstance(probs, list) and len(probs) == 406 and isinstance(q, list) and len(q) == n and isinstance(full, bool)
+        assert full == bool(g["full"][i])
+        assert np.allclose(probs, g["probs"][i], rtol=0, atol=1e-12) and np.allclose(q, g["q"][i], rtol=0, atol=1e-12)
+        assert nnet.calls == g["nn_calls"][i]
+        st = mcts.root_stats()
+        assert np.array_equal(st["nsa"].astype(np.int64), g["nsa"][i])
+    probs, q, full = mcts.getActionProb(g["root"][0], temp=0, force_full_search=True)
+    assert sum(probs) == 1 and max(probs) == 1
+    v = mcts.search(g["root"][1])
+    assert v.shape == (n,) and v.dtype == np.float32
+    az.MCTS.reset_all_search_trees()
+    assert len(mcts.nodes_data) == 0
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_device_network_matches_reference_network(golden_dir, n):
+    az = _azg()
+    g = np.load(os.path.join(golden_dir, f"nnet_n{n}.npz"))
+    net = az.SplendorNNetB200(n, state_dict=az.nnet.random_state_dict(n, int(g["seed"])), dtype=torch.float32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pi, v = net(torch.from_numpy(g["state"]).to(net.device), torch.from_numpy(g["valids"]).to(net.device))
+    assert np.abs(_np(pi) - g["pi"]).max() < 2e-5 and np.abs(_np(v) - g["v"]).max() < 2e-5     # float32 tolerance
+    p1, v1 = net.predict(g["state"][3], g["valids"][3])
+    assert np.abs(p1 - g["pi"][3]).max() < 2e-5 and np.abs(v1 - g["v"][3]).max() < 2e-5
+    net16 = az.SplendorNNetB200(n, state_dict=az.nnet.random_state_dict(n, int(g["seed"])), dtype=torch.bfloat16)
+    pi16, v16 = net16(torch.from_numpy(g["state"]).to(net.device), torch.from_numpy(g["valids"]).to(net.device))
+    assert np.abs(_np(pi16) - g["pi"]).max() < 0.08 and np.abs(_np(v16) - g["v"]).max() < 0.08   # bf16 fast mode: loose
+
+
+def test_search_with_the_real_network_and_dirichlet_sampler():
+    """4096-tree search with the torch network and the on-device Dirichlet sampler: budgets are spent exactly, visit
+    counts add up, the noise has the right first moment"""
+    az = _azg()
+    n, T, sims = 2, 512, 64
+    env = az.SplendorEnv(n, T, seed=9)
+    env.reset(); env.rollout(30, rotate=True)
+    roots = env.states()
+    net = az.SplendorNNetB200(n, seed=3)
+    ar = az.MCTSArena(n, T, node_cap=256, cpuct=1.25, fpu=0.2, dirichlet_alpha=0.3, seed=77)
+    simt = torch.full((T,), sims, dtype=torch.int32, device=ar.device)
+    flt = torch.full((T,), 3, dtype=torch.uint8, device=ar.device)
+    ar.search(roots, simt, net, flt, None)
+    ar.check_status()
+    st = ar.root_stats()
+    ns, nsa = _np(st["ns"]), _np(st["nsa"])
+    assert (ns == sims - 1).all() and (nsa.sum(1) == ns).all() and (_np(st["sims_done"]) == sims).all()
+    ps = _np(st["ps"])
+    assert np.allclose(ps.sum(1), 1.0, atol=1e-5) and (ps >= 0).all()
+    probs, q = ar.policy(1.0)
+    assert np.allclose(_np(probs).sum(1), 1.0, atol=1e-9)
