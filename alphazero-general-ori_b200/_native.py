@@ -31,7 +31,7 @@ EXPORTS = [
     "spl_mcts_select", "spl_mcts_expand", "spl_mcts_policy", "spl_mcts_root_stats", "spl_mcts_fixed_net",
 ]
 MCTS_MOVE_FORCED, MCTS_MOVE_NOISE = 1, 2
-MCTS_INFO_WORDS = 12
+MCTS_INFO_WORDS = 16
 
 
 class StepArgs(C.Structure):

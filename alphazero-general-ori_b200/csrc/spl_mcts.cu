@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(MW * 32) mcts_stats_kernel(MctsArena A, int32_
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
     mcts_root_stats_tree(w, A, t, nsa ? nsa + (size_t)t * SPL_ACTIONS : nullptr, qsa ? qsa + (size_t)t * SPL_ACTIONS : nullptr,
-                         ps ? ps + (size_t)t * SPL_ACTIONS : nullptr, info ? info + (size_t)t * 12 : nullptr);
+                         ps ? ps + (size_t)t * SPL_ACTIONS : nullptr, info ? info + (size_t)t * 16 : nullptr);
 }
 
 __global__ void __launch_bounds__(MW * 32) mcts_reset_kernel(MctsArena A, const uint8_t* tree_select) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(MW * 32) mcts_reset_kernel(MctsArena A, const 
     if (tree_select && !tree_select[t]) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
     mcts_clear_tree(w, A, t);
-    if (w.lane == 0) { A.trees[t].nn_calls = 0; A.trees[t].resets = 0; A.trees[t].compactions = 0; }
+    if (w.lane == 0 && !tree_select) { A.trees[t].nn_calls = 0; A.trees[t].resets = 0; A.trees[t].compactions = 0; A.trees[t].truncated = 0; }   // a full reset also clears the statistics
 }
 
 template <int N>
@@ -156,7 +156,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     if (((uintptr_t)arena & 255u) != 0) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena must be 256-byte aligned");
     const ArenaPlan p = plan_arena(ctx->n, n_trees, node_cap, edge_cap);
     if (arena_bytes < p.total) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena smaller than spl_mcts_arena_bytes");
-    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsEdge) == 24 && sizeof(MctsTree) == 64, "arena record sizes");
+    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsEdge) == 24 && sizeof(MctsTree) == 80, "arena record sizes");
     spl_mcts* m = new spl_mcts;
     m->ctx = ctx;
     char* base = (char*)arena;

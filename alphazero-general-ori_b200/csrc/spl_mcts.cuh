@@ -114,12 +114,15 @@ struct MctsEdge {   // 24 B
     uint32_t child;  // node index + 1 (0 = not linked yet)
     uint16_t action, pad;
 };
-struct MctsTree {   // 64 B
+struct MctsTree {   // 80 B
     int32_t n_nodes, n_edges, root, leaf;
     int32_t sims_done, sims_target, path_len;
     uint32_t flags, status;
     int32_t nn_calls, resets, compactions;
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
+    int32_t truncated; // searches cut short because a pool filled up mid-move (the next begin makes room again)
+    int32_t depth_sum; // sum of path lengths of this move's simulations (diagnostics)
+    int32_t pad[2];
 };
 struct MctsArena {
     int n_trees, cap, ecap, hcap, sp, max_depth;
@@ -405,6 +408,7 @@ SPL_D void mcts_backup(const MctsArena& A, int t, int depth, float* v) {
     MctsTree* T = A.trees + t;
 #pragma unroll
     for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? v[i] : 0.f;
+    T->depth_sum += depth;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -657,7 +661,7 @@ SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_a
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
         T->n_nodes = 0; T->n_edges = 0; T->root = -1; T->leaf = -1; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
-        T->flags = 0u; T->status = 0u;
+        T->flags = 0u; T->status = 0u; T->depth_sum = 0;
     }
     w.sync();
 }
@@ -675,8 +679,13 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     w.sync();
     const int root_ply = (int)(uint8_t)st[6];
     const uint64_t h = mcts_hash(w, st, A.sp);
-    const int need_nodes = sims_target + 2, need_edges = (sims_target + 2) * edge_reserve;
-    if (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
+    // room for this move: one node per simulation and, per node, the larger of the configured reserve and 1.5 x this
+    // tree's own average number of legal moves
+    const int avg = T->n_nodes > 16 ? (T->n_edges + T->n_nodes - 1) / T->n_nodes : 0;
+    const int per_node = edge_reserve > avg + avg / 2 ? edge_reserve : avg + avg / 2;
+    const int need_nodes = sims_target + 2, need_edges = (sims_target + 2) * per_node;
+    const uint32_t overflowed = T->status & (MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_EDGES);
+    if (overflowed || T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
         bool cleared = false;
         if (gc_reachable) {
             const int old_root = mcts_lookup(w, A, t, st, h);
@@ -699,12 +708,17 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
             if (w.lane == 0) T->resets = resets + 1;
             w.sync();
         }
+        if (w.lane == 0) {
+            if (overflowed) T->truncated += 1;
+            T->status &= ~(uint32_t)(MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_EDGES);
+        }
+        w.sync();
     }
     int idx = mcts_lookup(w, A, t, st, h);
     if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
     if (w.lane == 0) {
         T->root = idx; T->leaf = -1; T->sims_done = 0; T->sims_target = idx < 0 ? 0 : sims_target; T->path_len = 0;
-        T->flags = flags;
+        T->flags = flags; T->depth_sum = 0;
     }
     w.sync();
 }
@@ -755,7 +769,7 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
     w.sync();
 }
 
-// raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[12]
+// raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[16]
 template <class W>
 SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* nsa, double* qsa, float* ps, int32_t* info) {
     const MctsTree* T = A.trees + t;
@@ -781,9 +795,10 @@ SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* 
     }
     if (info && w.lane == 0) {
         info[0] = T->n_nodes; info[1] = T->n_edges; info[2] = ns; info[3] = T->sims_done; info[4] = T->nn_calls;
-        info[5] = (int32_t)T->status; info[6] = T->resets * 65536 + T->compactions;
+        info[5] = (int32_t)(T->status | ((uint32_t)T->truncated << 8)); info[6] = T->resets * 65536 + T->compactions;
         memcpy(&info[7], &qs, 4);
         memcpy(&info[8], T->last_v, 16);
+        info[12] = T->depth_sum;
     }
     w.sync();
 }

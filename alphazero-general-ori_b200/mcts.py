@@ -132,6 +132,32 @@ class MCTSArena:
             self.expand(pi, v, dir_values)
         self.select(dir_values)   # drains simulations that end in terminal nodes; emits no leaf once the budgets are spent
 
+    def get_action_prob_batch(self, boards, sims, evaluator, temp=1.0, move_flags=None, out=None):
+        """MCTS.getActionProb for T games with HOST buffers: boards int8[T,R,7] (numpy / pinned tensor) in,
+        (probs float64[T,406], q float64[T,n]) pinned host tensors out. `sims`: int or int32[T] device tensor."""
+        if not hasattr(self, "_h_roots"):
+            self._h_roots = torch.empty((self.T, self.R, 7), dtype=torch.int8).pin_memory()
+            self._d_roots = torch.empty((self.T, self.R, 7), dtype=torch.int8, device=self.device)
+            self._d_sims = torch.empty(self.T, dtype=torch.int32, device=self.device)
+            self._h_probs = torch.empty((self.T, nat.NUM_ACTIONS), dtype=torch.float64).pin_memory()
+            self._h_q = torch.empty((self.T, self.n), dtype=torch.float64).pin_memory()
+        b = boards if torch.is_tensor(boards) else torch.from_numpy(np.ascontiguousarray(boards, dtype=np.int8))
+        if b.data_ptr() != self._h_roots.data_ptr():
+            self._h_roots.copy_(b.view(self.T, self.R, 7))
+        self._d_roots.copy_(self._h_roots, non_blocking=True)
+        if torch.is_tensor(sims):
+            self._d_sims.copy_(sims)
+            waves = None
+        else:
+            self._d_sims.fill_(int(sims))
+            waves = int(sims)
+        self.search(self._d_roots, self._d_sims, evaluator, move_flags, None, None, waves)
+        probs, q = self.policy(temp)
+        self._h_probs.copy_(probs, non_blocking=True)
+        self._h_q.copy_(q, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_probs, self._h_q
+
     def policy(self, temp=1.0):
         """getActionProb's tail (MCTS.py:61-97) -> (probs float64[T,406], q float64[T,n])"""
         probs = torch.empty((self.T, nat.NUM_ACTIONS), dtype=torch.float64, device=self.device)
@@ -150,8 +176,8 @@ class MCTSArena:
         nat.check(self._lib.spl_mcts_root_stats(self._m, _ptr(nsa), _ptr(qsa), _ptr(ps), _ptr(info), self._stream()))
         self.launches += 1
         return dict(nsa=nsa, qsa=qsa, ps=ps, nodes=info[:, 0], edges=info[:, 1], ns=info[:, 2], sims_done=info[:, 3],
-                    nn_calls=info[:, 4], status=info[:, 5], resets=info[:, 6] >> 16, cleanings=info[:, 6] & 0xFFFF,
-                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32))
+                    nn_calls=info[:, 4], status=info[:, 5] & 0xFF, truncated=info[:, 5] >> 8, resets=info[:, 6] >> 16, cleanings=info[:, 6] & 0xFFFF,
+                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32), depth_sum=info[:, 12])
 
     def check_status(self):
         st = self.root_stats(want_arrays=False)["status"]

@@ -1,0 +1,108 @@
+"""Batched self-play on one GPU: T game lanes, one MCTS tree per lane, everything resident on the device.
+
+This is the loop `Coach.executeEpisode` runs one game at a time (Coach.py:67-100):
+
+    canonical = getCanonicalForm(board, cur)                    -> the env keeps every lane canonical (rotate=True)
+    pi, q, is_full = mcts.getActionProb(canonical, temp=1)      -> MCTSArena.search + policy for all lanes at once
+    action = pick from pi                                       -> torch.multinomial on the device
+    board, cur = getNextState(board, cur, action)               -> SplendorEnv.step (Philox deck reveals)
+    r = getGameEnded(board, cur)                                -> same launch; finished lanes restart (auto reset)
+
+Playout-cap randomisation (MCTS.py:54-56): each lane flips its own coin per move (full search with probability
+prob_fullMCTS, else numMCTSSims // ratio_fullMCTS simulations without noise or forced playouts).
+Games shard over GPUs by global game id (`game_base`); there is no collective on this path.
+"""
+import torch
+
+from . import _native as nat
+from .engine import SplendorEnv
+from .mcts import MCTSArena
+
+
+class SelfPlayEngine:
+    def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
+                 prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
+                 temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0):
+        self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
+        self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
+        self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
+        self.evaluator = evaluator
+        self.env = SplendorEnv(n_players, n_games, device=device, seed=seed, game_base=game_base)
+        self.device = self.env.device
+        node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
+        self.arena = MCTSArena(n_players, n_games, node_cap, edge_cap, device=device, cpuct=cpuct, fpu=fpu, temperature0=temperature0,
+                               dirichlet_alpha=dirichlet_alpha, seed=seed, game_base=game_base, edge_reserve=edge_reserve,
+                               gc_reachable=gc_reachable)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed) * 1000003 + int(game_base))
+        self.sims = torch.empty(n_games, dtype=torch.int32, device=self.device)
+        self.flags = torch.empty(n_games, dtype=torch.uint8, device=self.device)
+        self.roots = torch.empty((n_games, self.env.R, 7), dtype=torch.int8, device=self.device)
+        self.actions = torch.empty(n_games, dtype=torch.int16, device=self.device)
+        self.graph_waves = int(graph_waves)
+        self._graph = None
+        self.env.reset()
+        self.moves = 0
+        self.sims_total = torch.zeros((), dtype=torch.int64, device=self.device)   # simulations requested so far
+
+    # ------------------------------------------------------------------
+    def _wave(self):
+        ar = self.arena
+        ar.select(None)
+        pi, v = self.evaluator(ar.leaf_states, ar.leaf_valids)
+        ar.expand(pi, v, None)
+
+    def _run_waves(self, waves):
+        if self.graph_waves <= 0:
+            for _ in range(waves):
+                self._wave()
+            return
+        if self._graph is None:   # capture `graph_waves` waves once; replays reuse the arena's static leaf buffers
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._wave()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                for _ in range(self.graph_waves):
+                    self._wave()
+        for _ in range((waves + self.graph_waves - 1) // self.graph_waves):
+            self._graph.replay()
+
+    def search(self, temp=1.0):
+        """one getActionProb for every lane -> (probs float64[T,406], q float64[T,n], is_full bool[T])"""
+        T = self.T
+        if self.prob_full >= 1.0:
+            is_full = torch.ones(T, dtype=torch.bool, device=self.device)
+            max_sims = self.num_sims
+        else:
+            is_full = torch.rand(T, device=self.device, generator=self.gen) < self.prob_full
+            max_sims = self.num_sims
+        self.sims.copy_(torch.where(is_full, self.num_sims, self.num_sims // self.ratio_full).to(torch.int32))
+        fl = (nat.MCTS_MOVE_FORCED if self.forced else 0) | (nat.MCTS_MOVE_NOISE if self.noise else 0)
+        self.flags.copy_(torch.where(is_full, fl, 0).to(torch.uint8))
+        self.sims_total += self.sims.sum()
+        self.env.states(out=self.roots)
+        self.arena.begin(self.roots, self.sims, self.flags)
+        if self.graph_waves > 0 and self._graph is None:
+            # the warm-up waves of the capture must not eat into this move's budget: capture on a scratch move first
+            self._run_waves(0)
+            self.arena.begin(self.roots, self.sims, self.flags)
+        self._run_waves(max_sims)
+        self.arena.select(None)   # drain simulations ending in terminal nodes
+        probs, q = self.arena.policy(temp)
+        return probs, q, is_full
+
+    def play_move(self, temp=1.0):
+        """search, sample an action per lane from the visit distribution, advance every game (finished lanes restart and
+        their trees are cleared). Returns (probs, q, is_full, ended float32[T,n])."""
+        probs, q, is_full = self.search(temp)
+        a = torch.multinomial(probs.to(torch.float32), 1, generator=self.gen).view(-1)
+        self.actions.copy_(a.to(torch.int16))
+        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=True, want_mask=False, want_status=False, count=True)
+        done = (self.env.ended != 0).any(dim=1).to(torch.uint8)
+        self.arena.reset(done)
+        self.moves += 1
+        return probs, q, is_full, self.env.ended

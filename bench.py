@@ -1,20 +1,23 @@
 #!/usr/bin/env python3
-"""bench.py - Splendor env steps/s on N B200s (BASELINE.json metric), one JSON line on rank 0.
+"""bench.py - the BASELINE.json metric "Splendor env steps/s & MCTS sims/s" on N B200s, one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--lanes L] [--plies P] [--mode rollout|step]
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # headline: MCTS sims/s on configs[1] + env steps/s nested
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the CPU arm: oracle port of the reference rules on all host cores
+    python bench.py --impl reference ...                            # the CPU arm (oracle port of MCTS.py + torch-CPU network)
+    python bench.py --workload env ...                              # env-step throughput only (configs[4])
 
-A "step" of the bench is one pass of the hot path over the whole batch of game lanes: one launch of the
-persistent ply kernel (`--mode rollout`, P plies per lane per launch: legality mask -> uniform random legal
-action -> move + Philox deck reveal -> ply++ -> canonical rotation -> end-game check -> auto reset), or of the
-single-ply kernel (`--mode step`, P = 1, state read from and written back to HBM every ply).
-value = env steps (lane-plies) per second over all ranks. Games shard over GPUs with no collective on the path
-(weak scaling: lanes per GPU fixed).
+Headline workload = BASELINE.json configs[1]: 2-player self-play, 1600 MCTS simulations per move with SplendorNNet
+(random-init weights), 4096 parallel games per GPU. A "step" = one move of every game: getActionProb for all lanes
+(tree-arena begin + 1600 waves of select -> network -> expand/backup + policy), an action sampled from the visit
+distribution and the real move with its Philox deck reveal. value = simulations per second over all ranks.
+The env-step half of the metric (configs[4], one step = one launch of the persistent ply kernel over 1 Mi lanes) is
+measured in the same run and reported under "env_steps", with its own roofline, e2e and CPU baseline.
+Games shard over GPUs with no collective on the path (weak scaling: games per GPU fixed).
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -23,45 +26,58 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "splendor_env_steps_per_s"
-UNIT = "steps/s"
-B_STEP = {2: 846, 3: 1060, 4: 1302}   # algorithmic bytes per env step: 2S + 52 + 2 + 4n
+METRIC_MCTS, UNIT_MCTS = "splendor_mcts_sims_per_s", "sims/s"
+METRIC_ENV, UNIT_ENV = "splendor_env_steps_per_s", "steps/s"
+B_STEP = {2: 846, 3: 1060, 4: 1302}     # algorithmic bytes per env step: 2S + 52 + 2 + 4n
+B_SIM = {2: 4500, 3: 5300, 4: 6300}     # algorithmic bytes per simulation (d=4.83, m=20)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "mcts", "env"])
     ap.add_argument("--players", type=int, default=2)
+    # MCTS (configs[1])
+    ap.add_argument("--trees", type=int, default=4096, help="parallel games (trees) per GPU")
+    ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
+    ap.add_argument("--nn-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--graph-waves", type=int, default=16, help="waves per CUDA-graph replay (0: plain launches)")
+    ap.add_argument("--gc", default="ply", choices=["ply", "reachable"])
+    ap.add_argument("--node-cap", type=int, default=0)
+    ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
+    ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
+    # env (configs[4])
     ap.add_argument("--lanes", type=int, default=1 << 20, help="game lanes per GPU")
     ap.add_argument("--plies", type=int, default=16, help="plies per lane per launch (rollout mode)")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "step"])
+    ap.add_argument("--env-steps", type=int, default=20)
     ap.add_argument("--e2e-lanes", type=int, default=65536)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=300, help="untimed plies per lane before warm-up (de-synchronises the games)")
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--burn-in", type=int, default=300, help="untimed plies per lane before warm-up (de-synchronises the games)")
+    # CPU legs
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--cpu-mcts-worker", type=str, default="", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference rules (oracle/), all host cores
+# CPU arms: the oracle port of the reference (oracle/), all host cores
 # ----------------------------------------------------------------------------------------------
 def cpu_rollouts(n_players, seed, seconds, threads=None):
     """plays whole random games (same Philox policy as the GPU path) on `threads` host threads for about
-    `seconds`; returns (steps/s, threads, games, plies)"""
+    `seconds`; returns (steps/s, threads, games, plies, seconds)"""
     from oracle import pyoracle as po
     po.lib()
     threads = threads or len(os.sched_getaffinity(0))
-    # calibrate one thread
     t0 = time.perf_counter()
-    tot, _, _ = po.rollout(n_players, seed, 0, 200)
-    dt = time.perf_counter() - t0
-    per_game = dt / 200
+    po.rollout(n_players, seed, 0, 200)
+    per_game = (time.perf_counter() - t0) / 200
     games = max(200, int(seconds / per_game))
     results = [0] * threads
 
@@ -79,35 +95,103 @@ def cpu_rollouts(n_players, seed, seconds, threads=None):
     return plies / dt, threads, games * threads, plies, dt
 
 
+def cpu_mcts_worker(spec):
+    """one process = one core: the C port of MCTS.py (oracle/mcts_oracle.c) driving the network on the CPU through a
+    per-leaf `predict` (torch float32, batch 1, one thread - GenericNNetWrapper.py:7,20,141-168), like the reference"""
+    n, sims, moves, seed, idx, fixed = [int(x) for x in spec.split(",")]
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import pyoracle as po
+    import azg_b200
+    from azg_b200 import nnet
+    predict = None
+    if not fixed:
+        W = nnet.fold(nnet.random_state_dict(n, seed), "cpu", torch.float32)
+
+        def predict(board, valids):
+            with torch.no_grad():
+                pi, v = nnet.forward_folded(W, torch.from_numpy(board.copy()).view(1, -1, 7), torch.from_numpy(valids.astype(np.uint8)).view(1, -1))
+            return pi[0].numpy(), v[0].numpy()
+    m = po.MCTSOracle(n, sims, cpuct=1.0, fpu=0.0, predict=predict)
+    b = po.Board(n); b.init_philox(seed, 100000 + idx)
+    rng = np.random.default_rng(seed + idx)
+    for _ in range(24):
+        v = b.valid_moves(0)
+        b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, seed, 100000 + idx, 0); b.swap_players(1)
+    m.get_action_prob(b.state, full_search=True)     # warm-up move (allocations, caches)
+    done = 0
+    t0 = time.perf_counter()
+    for _ in range(moves):
+        if b.check_end_game().any():
+            b.init_philox(seed, 200000 + idx + done); m.reset()
+        o = m.get_action_prob(b.state, full_search=True)
+        done += sims
+        a = int(rng.choice(406, p=o["probs"]))
+        b.make_move(a, 0, -2, seed, 100000 + idx, 0); b.swap_players(1)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"sims": done, "seconds": dt}), flush=True)
+
+
+def cpu_mcts(n, sims, moves, seed, fixed, procs=None):
+    """-> (sims/s aggregate, cores, total sims, wall seconds) with one worker process per host core"""
+    procs = procs or len(os.sched_getaffinity(0))
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-mcts-worker", f"{n},{sims},{moves},{seed},{i},{int(fixed)}"],
+                           stdout=subprocess.PIPE, env=env, text=True) for i in range(procs)]
+    tot, rate, worst = 0, 0.0, 0.0
+    for p in ps:
+        out, _ = p.communicate()
+        r = json.loads(out.strip().splitlines()[-1])
+        tot += r["sims"]; rate += r["sims"] / r["seconds"]; worst = max(worst, r["seconds"])
+    return rate, procs, tot, worst
+
+
+def workload_mcts(args):
+    net = "fixed stand-in network" if args.fixed_net else "SplendorNNet (random-init)"
+    return (f"configs[1]: {args.players}p self-play, {args.sims} MCTS sims/move with {net}, {args.trees} parallel games per GPU")
+
+
+def workload_env(args):
+    return f"configs[4]: {args.players}p env-step throughput, random legal moves, {args.lanes} game lanes per GPU"
+
+
 def run_reference(args):
+    """the reference's own CPU implementation of the path on this box's host cores (oracle port; the reference is
+    Python + Numba and cannot travel to the GPU box)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.players
-    per_step = max(0.5, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_rollouts(n, args.seed, min(per_step, 1.0))
-    tot_plies, tot_dt, cores, games = 0, 0.0, 0, 0
-    for _ in range(args.steps):
-        v, cores, g, plies, dt = cpu_rollouts(n, args.seed, per_step)
-        tot_plies += plies; tot_dt += dt; games += g
-    value = tot_plies / tot_dt
-    sample = f"{games} whole random {n}p games (oracle port of SplendorLogicNumba rules, C, -O2), {cores} threads"
+    cores = len(os.sched_getaffinity(0))
+    if args.workload == "env":
+        per_step = max(0.5, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+        for _ in range(args.warmup):
+            cpu_rollouts(n, args.seed, min(per_step, 1.0))
+        tot, tdt, games = 0, 0.0, 0
+        for _ in range(args.steps):
+            v, cores, g, plies, dt = cpu_rollouts(n, args.seed, per_step)
+            tot += plies; tdt += dt; games += g
+        value, metric, unit, wl = tot / tdt, METRIC_ENV, UNIT_ENV, workload_env(args)
+        sample = f"{games} whole random {n}p games (oracle port of the SplendorLogicNumba rules, C -O2), {cores} threads"
+    else:
+        # step = one move (getActionProb) per worker; bounded: sims per move scaled so that K+W moves stay within minutes
+        sims = min(args.sims, 400)
+        moves = max(1, args.steps)
+        rate, cores, tot, tdt = cpu_mcts(n, sims, moves, args.seed, args.fixed_net)
+        value, metric, unit, wl = rate, METRIC_MCTS, UNIT_MCTS, workload_mcts(args)
+        sample = (f"{cores} processes x {moves} moves x {sims} sims/move = {tot} simulations (C port of MCTS.py + per-leaf torch-CPU "
+                  f"float32 SplendorNNet predict, 1 thread each; {sims} instead of {args.sims} sims/move to bound the run)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "players": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tdt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64/f32 tree statistics, f32 network" if metric == METRIC_MCTS else "int8", "data": "synthetic",
+        "config": {"workload": wl, "players": n},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_name(args):
-    return (f"config5: {args.players}p env-step throughput, random legal moves, {args.lanes} game lanes per GPU "
-            f"(64k-lane point of the BASELINE metric reported in `sweep`)")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -159,31 +243,140 @@ class Clocks:
                 "samples": len(s)}
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 # ----------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+# MCTS leg (configs[1])
+# ----------------------------------------------------------------------------------------------
+def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
+    n, T, sims = args.players, args.trees, args.sims
+    torch.backends.cuda.matmul.allow_tf32 = False      # the float32 network is evaluated in float32
+    torch.backends.cudnn.allow_tf32 = False
+    dtype = torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16
+    net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=dtype)
+    reach = args.gc == "reachable"
+    cap = args.node_cap or (3 if reach else 8) * sims
+    eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
+                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves)
+    if args.fixed_net:
+        pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
+        eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
+        nn_launches = 1
+    else:
+        eng.evaluator = net
+        nn_launches = None
+    eng.env.rollout(args.opening_plies, rotate=True)    # mid-game positions, lanes de-synchronised by the random openings
 
-    import torch
-    import torch.distributed as dist
-    import azg_b200
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        eng.play_move()
+    barrier()
+    eng.env.counters.zero_()
+    sims0 = int(eng.sims_total.item())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with Clocks(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            eng.play_move()
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n, L, P = args.players, args.lanes, (args.plies if args.mode == "rollout" else 1)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    sims_done = int(eng.sims_total.item()) - sims0
+    assert sims_done == T * sims * args.steps
+    st = eng.arena.root_stats(want_arrays=False)
+    truncated_now = int((st["sims_done"] < sims).sum())
+    value = world * sims_done / (ms_total * 1e-3)
+    waves_per_step = -(-sims // args.graph_waves) * args.graph_waves if args.graph_waves > 0 else sims
+    own_launches_total = args.steps * (waves_per_step * 2 + 8)
 
-    # games shard over ranks by global game id: lane l of rank r is game r*L + l (results independent of N)
-    env = azg_b200.SplendorEnv(n, L, device=local, seed=args.seed, game_base=rank * L, use_tma=not args.no_tma)
+    # ---- kernel breakdown of one wave, measured live with CUDA events on plain (non-graph) launches
+    ar = eng.arena
+    eng.env.states(out=eng.roots)
+    ar.begin(eng.roots, eng.sims, eng.flags)
+    nb = 200
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nb)]
+    for i in range(nb):
+        evs[i][0].record(); ar.select(None)
+        evs[i][1].record(); pi, v = eng.evaluator(ar.leaf_states, ar.leaf_valids)
+        evs[i][2].record(); ar.expand(pi, v, None)
+        evs[i][3].record()
+    torch.cuda.synchronize()
+    sel = sum(e[0].elapsed_time(e[1]) for e in evs[20:]) / (nb - 20)
+    nnt = sum(e[1].elapsed_time(e[2]) for e in evs[20:]) / (nb - 20)
+    exp = sum(e[2].elapsed_time(e[3]) for e in evs[20:]) / (nb - 20)
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "mcts_select_kernel", "avg_launch_ms": sel,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_sim": B_SIM[n],
+                "note": "one launch = one simulation of every tree; the search is bound by the latency of sequential waves, not bytes",
+                "wave_breakdown_ms": {"mcts_select_kernel": sel, "network_forward": nnt, "mcts_expand_kernel": exp}}
+
+    line = {
+        "metric": METRIC_MCTS, "value": value, "unit": UNIT_MCTS, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
+        "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
+                   "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
+                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "opening_plies": args.opening_plies,
+                   "parallelism": f"games sharded dp{world}, no collective on the path",
+                   "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
+        "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
+        "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
+                       "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(st["sims_done"].sum())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
+                       "games_finished": int(eng.env.counters[0].item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, int(eng.sims_total.item()))},
+    }
+    if rank == 0:
+        line["clocks"] = clk.summary()
+
+    # ---- e2e: the Coach-style loop through the public API with HOST buffers (boards in, probs out, boards out)
+    game = azg.SplendorGame(n, seed=args.seed, device=local)
+    import numpy as np
+    boards = eng.env.states().cpu().numpy()
+    ar.reset()
+    ke = 3
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        probs, q = ar.get_action_prob_batch(boards, sims, eng.evaluator)
+        acts = probs.numpy().argmax(1).astype(np.int16)
+        boards, valids, ended = game.getNextStateBatch(boards, 0, acts)
+        boards = boards.copy()
+        h2d += T * (eng.env.S + eng.env.S + 2); d2h += T * (406 * 8 + n * 8 + eng.env.S + 406 + 4 * n)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    line["e2e"] = {"value": world * T * sims * ke / float(t.item()), "unit": UNIT_MCTS, "h2d_bytes_per_step": h2d // ke, "d2h_bytes_per_step": d2h // ke,
+                   "call": "MCTSArena.get_action_prob_batch(host boards) -> host probs/q, then SplendorGame.getNextStateBatch(host boards, actions)",
+                   "steps": ke}
+    return line, eng
+
+
+# ----------------------------------------------------------------------------------------------
+# env leg (configs[4])
+# ----------------------------------------------------------------------------------------------
+def bench_env(args, torch, dist, azg, world, rank, local, dev, barrier):
+    n, L, P = args.players, args.lanes, (args.plies if args.mode == "rollout" else 1)
+    steps = args.env_steps
+    env = azg.SplendorEnv(n, L, device=local, seed=args.seed, game_base=rank * L, use_tma=not args.no_tma)
     env.reset()
-    # burn-in: games start in lock-step; play until the lanes are spread over all game phases (steady state)
     env.rollout(args.burn_in, rotate=True)
     if args.mode == "step":
         env.step(None, want_next=True, want_ended=False, want_status=False)
@@ -195,83 +388,53 @@ def main():
             env.step(env.next_actions, player=0, chance="philox", rotate=True, auto_reset=True, want_next=True,
                      want_status=False, count=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(3):
         one_step()
     barrier()
     env.counters.zero_()
     launches0 = env.launches
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     with Clocks(local) as clk:
         barrier()
-        t0 = time.perf_counter()
         evs[0].record()
-        for i in range(args.steps):
+        for i in range(steps):
             one_step()
             evs[i + 1].record()
         barrier()
-        wall = time.perf_counter() - t0
     ms_total = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    launches = env.launches - launches0
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     cnt = env.counters.cpu().tolist()
-    assert cnt[1] == L * P * args.steps, f"ply accounting {cnt[1]} != {L * P * args.steps}"
-    steps_all = world * L * P * args.steps
-    value = steps_all / (ms_total * 1e-3)
-
-    # ---- roofline of the dominant kernel (the ply kernel itself; events bracket exactly one launch each)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    assert cnt[1] == L * P * steps, f"ply accounting {cnt[1]} != {L * P * steps}"
+    value = world * L * P * steps / (ms_total * 1e-3)
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_ms = sum(per_launch_ms) / len(per_launch_ms)
     achieved = B_STEP[n] * L * P / (avg_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(f"{args.mode}_n{n}_bytes_per_lane_ply")
-        if traffic is not None:
-            traffic = traffic * L * P
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "spl_rollout_kernel" if args.mode == "rollout" else "spl_step_kernel",
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_step": B_STEP[n], "avg_launch_ms": avg_ms}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "players": n, "lanes_per_gpu": L, "plies_per_launch": P, "mode": args.mode, "burn_in_plies": args.burn_in,
-                   "tma": not args.no_tma, "parallelism": f"games sharded dp{world}, no collective on the path",
-                   "l2": f"inputs larger than L2: {L * env.S / 1e6:.0f} MB of lane tiles per GPU vs 126 MB L2"},
-        "roofline": roofline, "gpu_launches": launches, "wall_s": wall, "games_finished": cnt[0] * world,
+    out = {
+        "metric": METRIC_ENV, "value": value, "unit": UNIT_ENV, "steps": steps, "ms_per_step": ms_total / steps, "dtype": "int8",
+        "config": {"workload": workload_env(args), "lanes_per_gpu": L, "plies_per_launch": P, "mode": args.mode, "burn_in_plies": args.burn_in,
+                   "tma": not args.no_tma, "l2": f"inputs larger than L2: {L * env.S / 1e6:.0f} MB of lane tiles per GPU vs 126 MB L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "spl_rollout_kernel" if args.mode == "rollout" else "spl_step_kernel",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "algorithmic_bytes_per_step": B_STEP[n], "avg_launch_ms": avg_ms},
+        "gpu_launches": env.launches - launches0, "games_finished": cnt[0] * world, "clocks": clk.summary(),
     }
-    if rank == 0:
-        line["clocks"] = clk.summary()
-
-    # ---- e2e through the reference-facing call with HOST buffers (rank-local, all ranks in parallel)
-    game = azg_b200.SplendorGame(n, seed=args.seed, device=local)
+    # e2e through the reference-facing call with HOST buffers
+    game = azg.SplendorGame(n, seed=args.seed, device=local)
     Le = args.e2e_lanes
     eenv = game._env_for(Le)
-    src = azg_b200.SplendorEnv(n, Le, device=local, seed=args.seed, game_base=rank * Le)
+    src = azg.SplendorEnv(n, Le, device=local, seed=args.seed, game_base=rank * Le)
     src.reset(); src.rollout(20, rotate=True); src.step(None, want_next=True)
     eenv._h_in.copy_(src.states().cpu()); eenv._h_act.copy_(src.next_actions.cpu())
     for _ in range(3):
         game._step_pinned(eenv, 0, False, True)
     barrier()
-    ke = max(3, min(args.steps, 10))
+    ke = 5
     t0 = time.perf_counter()
     for _ in range(ke):
         game._step_pinned(eenv, 0, False, True)     # includes H2D of boards+actions and D2H of boards+masks+end vectors
@@ -280,37 +443,26 @@ def main():
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    line["e2e"] = {"value": world * Le * ke / float(t.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": Le * (env.S + 2), "d2h_bytes_per_step": Le * (env.S + 406 + 4 * n),
-                   "call": "SplendorGame.getNextStateBatch (pinned host int8[L,R,7] boards + actions in; next canonical boards, "
-                           "bool[L,406] masks, float32[L,n] end vectors out)", "lanes_per_call": Le}
-
-    # ---- sweep point named by the metric: 64k lanes, L2 flushed between timed launches
-    if rank == 0:
-        if not args.no_sweep:
-            line["sweep"] = sweep(azg_b200, torch, n, local, args)
-        if not args.no_cpu:
-            v, cores, games, plies, dtc = cpu_rollouts(n, args.seed, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{games} whole random {n}p games = {plies} plies in {dtc:.1f} s "
-                                              f"(oracle port of the SplendorLogicNumba rules, C -O2, one thread per core)"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    out["e2e"] = {"value": world * Le * ke / float(t.item()), "unit": UNIT_ENV,
+                  "h2d_bytes_per_step": Le * (env.S + 2), "d2h_bytes_per_step": Le * (env.S + 406 + 4 * n),
+                  "call": "SplendorGame.getNextStateBatch (pinned host int8[L,R,7] boards + actions in; next canonical boards, "
+                          "bool[L,406] masks, float32[L,n] end vectors out)", "lanes_per_call": Le}
+    del env
+    if rank == 0 and not args.no_sweep:
+        out["sweep"] = sweep(azg, torch, n, local, args)
+    return out
 
 
-def sweep(azg_b200, torch, n, local, args):
+def sweep(azg, torch, n, local, args):
     out = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     for Ls in (1 << 10, 1 << 13, 1 << 16, 1 << 18):
-        e = azg_b200.SplendorEnv(n, Ls, device=local, seed=args.seed, use_tma=not args.no_tma)
+        e = azg.SplendorEnv(n, Ls, device=local, seed=args.seed, use_tma=not args.no_tma)
         e.reset()
         e.rollout(args.burn_in, rotate=True)
         for _ in range(3):
             e.rollout(args.plies, rotate=True)
-        tot = 0.0
-        reps = 5
+        tot, reps = 0.0, 5
         for _ in range(reps):
             flush.fill_(1)   # evict L2 between timed launches
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,6 +472,73 @@ def sweep(azg_b200, torch, n, local, args):
         out.append({"lanes": Ls, "plies_per_launch": args.plies, "steps_per_s": Ls * args.plies * reps / (tot * 1e-3), "l2": "flushed"})
         del e
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.cpu_mcts_worker:
+        return cpu_mcts_worker(args.cpu_mcts_worker)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import azg_b200 as azg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.players
+    line = None
+    if args.workload in ("both", "mcts"):
+        line, eng = bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier)
+        del eng
+        torch.cuda.empty_cache()
+    if args.workload in ("both", "env"):
+        envres = bench_env(args, torch, dist, azg, world, rank, local, dev, barrier)
+        if line is None:
+            line = {"metric": METRIC_ENV, "value": envres["value"], "unit": UNIT_ENV, "n_gpus": world, "steps": envres["steps"],
+                    "warmup": 3, "ms_per_step": envres["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "int8", "data": "synthetic", "config": dict(envres["config"], players=n,
+                                                                          parallelism=f"games sharded dp{world}, no collective on the path"),
+                    "roofline": envres["roofline"], "gpu_launches": envres["gpu_launches"], "e2e": envres["e2e"],
+                    "sweep": envres.get("sweep"), "clocks": envres["clocks"]}
+        else:
+            line["env_steps"] = envres
+    if rank == 0:
+        if not args.no_cpu:
+            if line["metric"] == METRIC_MCTS:
+                sims_cpu = min(args.sims, 400)
+                rate, cores, tot, secs = cpu_mcts(n, sims_cpu, 3, args.seed, args.fixed_net)
+                line["cpu_baseline"] = {"value": rate, "unit": UNIT_MCTS, "cores": cores, "kind": "port",
+                                        "sample": f"{cores} processes x 3 moves x {sims_cpu} sims/move = {tot} simulations in {secs:.1f} s (C port of "
+                                                  f"MCTS.py + per-leaf torch-CPU float32 SplendorNNet predict, one thread per core)"}
+            if args.workload in ("both", "env"):
+                v, cores, games, plies, dtc = cpu_rollouts(n, args.seed, args.cpu_seconds)
+                cb = {"value": v, "unit": UNIT_ENV, "cores": cores, "kind": "port",
+                      "sample": f"{games} whole random {n}p games = {plies} plies in {dtc:.1f} s (oracle port of the SplendorLogicNumba "
+                                f"rules, C -O2, one thread per core)"}
+                if "env_steps" in line:
+                    line["env_steps"]["cpu_baseline"] = cb
+                else:
+                    line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -167,7 +167,10 @@ typedef struct spl_mcts spl_mcts;
 #define SPL_MCTS_MOVE_FORCED 1u   /* forced playouts + policy-target pruning for this move (:56, :69-74) */
 #define SPL_MCTS_MOVE_NOISE 2u    /* root softmax + Dirichlet noise on the first simulation (:58, :141-143, :150-154) */
 
-#define SPL_MCTS_ST_OVERFLOW_NODES 1  /* tree status bits (info[5] of spl_mcts_root_stats) */
+/* tree status bits (low byte of info[5] of spl_mcts_root_stats). A pool that fills up mid-move stops that tree's search
+ * early (the policy then reflects the simulations done so far); the next spl_mcts_begin makes room, clears the bit and
+ * counts the event as a truncated search. */
+#define SPL_MCTS_ST_OVERFLOW_NODES 1
 #define SPL_MCTS_ST_OVERFLOW_EDGES 2
 #define SPL_MCTS_ST_PROTOCOL 4        /* select called while a leaf was still waiting for spl_mcts_expand */
 
@@ -205,9 +208,10 @@ int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double*
 /* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */
 int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* stream);
 /* raw root statistics, any pointer may be NULL: nsa int32[T][406], qsa double[T][406] (-42 = unvisited), ps float[T][406],
- * info int32[T][12] = nodes, edges, root Ns, simulations done, network calls since reset, status bits,
+ * info int32[T][16] = nodes, edges, root Ns, simulations done, network calls since reset, status bits | truncated searches << 8,
  *                     lossy resets * 65536 + cleanings, root Qs (float bits), then 4 floats (bits): the value vector the last
- *                     finished simulation returned at the root (what MCTS.search returns, :99-177) */
+ *                     finished simulation returned at the root (what MCTS.search returns, :99-177), then the sum of the
+ *                     path lengths of this move's simulations; 3 spare words */
 int  spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info, void* stream);
 /* deterministic stand-in network ("fixed NN outputs"): a pure function of the state bytes with exact dyadic outputs; the
  * golden MCTS fixtures were produced by the reference's own MCTS.py with this function as its network */

@@ -137,10 +137,10 @@ class TreeSim:
         status = lib_mcts().hm_search(self._h, _p(st, C.c_int8), sims, fl, None if d is None else _p(d, C.c_double))
         probs = np.zeros(406); q = np.zeros(self.n)
         lib_mcts().hm_policy(self._h, float(temp), _p(probs, C.c_double), _p(q, C.c_double))
-        nsa = np.zeros(406, dtype=np.int32); qsa = np.zeros(406); ps = np.zeros(406, dtype=np.float32); info = np.zeros(12, dtype=np.int32)
+        nsa = np.zeros(406, dtype=np.int32); qsa = np.zeros(406); ps = np.zeros(406, dtype=np.float32); info = np.zeros(16, dtype=np.int32)
         lib_mcts().hm_root_stats(self._h, _p(nsa, C.c_int32), _p(qsa, C.c_double), _p(ps, C.c_float), _p(info, C.c_int32))
         return dict(probs=probs, q=q, nsa=nsa.astype(np.int64), qsa=qsa, ps=ps, ns=int(info[2]), qs=info[7:8].view(np.float32)[0],
-                    nodes=int(info[0]), edges=int(info[1]), nn_calls=int(info[4]), status=status, resets=int(info[6]) >> 16,
+                    nodes=int(info[0]), edges=int(info[1]), nn_calls=int(info[4]), status=status, truncated=int(info[5]) >> 8, resets=int(info[6]) >> 16,
                     compactions=int(info[6]) & 0xFFFF)
 
 
