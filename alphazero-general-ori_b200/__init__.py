@@ -8,8 +8,8 @@ from . import _native
 from .engine import SplendorEnv, rows
 from .game import Board, SplendorGame, action_size, observation_size
 from .mcts import MCTS, MCTSArena
-from .nnet import SplendorNNetB200
+from .nnet import FusedSplendorNNet, SplendorNNetB200
 from .selfplay import SelfPlayEngine
 from . import nnet
 
-__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "SelfPlayEngine", "nnet", "observation_size", "action_size", "rows", "_native"]
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "nnet", "observation_size", "action_size", "rows", "_native"]

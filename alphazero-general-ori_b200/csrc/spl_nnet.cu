@@ -1,0 +1,522 @@
+// libsplendor_b200.so - fused leaf evaluator: the whole SplendorNNet inference pass in ONE launch.
+//
+// Replaces, for the tree arena's leaf rows, GenericNNetWrapper.predict (GenericNNetWrapper.py:141-168) +
+// SplendorNNet.forward (SplendorNNet.py:127-159): int8 states + legal masks in, exp(log_softmax(masked pi)) and tanh(v)
+// out. The torch path (nnet.py) needs ~60 small kernels per wave; here one CTA carries 16 leaves through every layer
+// with the activations resident in shared memory:
+//
+//   stage A (the "2d" layers, one row per (leaf, gem column): 112 rows per CTA, warp c owns gem column c)
+//       x[56|71|88] -> Linear+BN(7)+ReLU -> Linear+ReLU -> DenseAndPartialGPool(4x8) -> Linear+ReLU
+//   FlattenAndPartialGPool(64, 5)  -> 704 features per leaf
+//   stage B (the "1d" layers, 16 rows per CTA, the 8 warps split the output columns)
+//       704 -> 128 -> pool-dense -> 128 -> 128 -> pool-dense -> {PI: 128 -> 406 masked softmax, V: 128 -> n tanh}
+//
+// Matrix products run on the tensor cores as bf16 x bf16 -> fp32 (mma.sync m16n8k16), weights are streamed from L2
+// through a double-buffered cp.async ring in [n][k] blocks laid out exactly as they sit in shared memory (padded rows,
+// conflict-free fragment loads), biases / BatchNorm terms are applied in fp32 in the epilogues. BatchNorm is folded on
+// the host in double precision (eval mode); the score-difference head is not evaluated (MCTS never reads it).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "spl_internal.h"
+
+namespace {
+
+constexpr int NN_SB = 16;        // leaves per CTA
+constexpr int NN_THREADS = 256;  // 8 warps
+constexpr int ASTR = 136;        // activation row stride in bf16 elements (128 + 8: conflict-free fragment loads)
+constexpr int FSTR = 712;        // flattened row stride (704 + 8)
+constexpr int LSTR = 416;        // logits row stride (fp32)
+constexpr int NN_ACTIONS = 406;
+constexpr int NN_MAXBLK = 48;
+
+// fp32 parameter region of the blob (offsets in floats)
+enum {
+    P_B1 = 0, P_S1 = 128, P_T1 = 136, P_B2 = 144, P_BG1 = 272, P_SG1 = 400, P_TG1 = 408, P_B3 = 416, P_B4 = 544,
+    P_BG4 = 672, P_B5A = 800, P_B5B = 928, P_BG5 = 1056, P_BP0 = 1184, P_BP1 = 1312, P_BV0 = 1760, P_BV1 = 1888,
+    P_TOTAL = 1896
+};
+
+struct NnPlan {   // byte offsets of the weight blocks inside the blob (after the fp32 parameters)
+    int nblocks;
+    int off[NN_MAXBLK];
+    int bytes[NN_MAXBLK];
+    int kb[NN_MAXBLK];   // k extent of the block (row stride = kb + 8 elements)
+    int total_bytes;
+};
+
+inline int kpad1(int n) { return (32 + 10 * n + n * n + 15) / 16 * 16; }
+
+NnPlan make_plan(int n) {
+    NnPlan p;
+    memset(&p, 0, sizeof p);
+    int o = P_TOTAL * 4, b = 0;
+    auto add = [&](int nb, int kb) {
+        p.off[b] = o; p.kb[b] = kb; p.bytes[b] = nb * (kb + 8) * 2; o += p.bytes[b]; b++;
+    };
+    add(64, kpad1(n)); add(64, kpad1(n));       // L1   dense2d_1.0
+    add(64, 128); add(64, 128);                 // L2   dense2d_1.3
+    add(64, 96); add(64, 96);                   // G1   partialgpool_1.dense_part.0
+    add(64, 128); add(64, 128);                 // L3   dense2d_3.0
+    for (int i = 0; i < 11; i++) add(128, 64);  // L4   dense1d_4.0 (704 = 11 x 64)
+    add(64, 112); add(64, 112);                 // G4
+    add(64, 128); add(64, 128);                 // L5a
+    add(64, 128); add(64, 128);                 // L5b
+    add(64, 112); add(64, 112);                 // G5
+    add(64, 128); add(64, 128);                 // PI0
+    add(64, 128); add(64, 128);                 // V0
+    for (int i = 0; i < 7; i++) add(64, 128);   // PI1 (406 -> 448 rows)
+    add(64, 128);                               // V1 (n -> 64 rows)
+    p.nblocks = b;
+    p.total_bytes = o;
+    return p;
+}
+
+constexpr int SLOT_BYTES = 128 * 72 * 2;   // largest block: [128 n][64 k]
+static_assert(SLOT_BYTES >= 64 * ASTR * 2, "slot holds a [64][128] block");
+
+struct NnSmem {
+    __nv_bfloat16 act[7 * NN_SB * ASTR];     // stage A activations; later the fp32 logits
+    __nv_bfloat16 flat[NN_SB * FSTR];
+    __nv_bfloat16 vec[3][NN_SB * ASTR];
+    unsigned char slot[2][SLOT_BYTES];
+};
+static_assert(sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR >= sizeof(float) * NN_SB * LSTR, "logits alias the activations");
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void sts_bf16x2(__nv_bfloat16* p, float x, float y) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
+}
+
+// A fragments of a 16-row strip: rows row0 + {g, g+8}, k = 16 ks + {2t, 2t+1, 2t+8, 2t+9}
+template <int KS>
+__device__ __forceinline__ void load_afrags(uint32_t (&afr)[8][4], const __nv_bfloat16* a, int stride, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        const __nv_bfloat16* p = a + ks * 16 + 2 * t;
+        afr[ks][0] = lds32(p + g * stride);
+        afr[ks][1] = lds32(p + (g + 8) * stride);
+        afr[ks][2] = lds32(p + g * stride + 8);
+        afr[ks][3] = lds32(p + (g + 8) * stride + 8);
+    }
+}
+
+// stage A: one warp = one 16-row strip, A in registers, one [64 n][KB] weight block -> 8 output tiles
+template <int KS, class Epi>
+__device__ __forceinline__ void strip_gemm(const uint32_t (&afr)[8][4], const __nv_bfloat16* w, int wstride, int g, int t, Epi epi) {
+#pragma unroll 2
+    for (int nt = 0; nt < 8; nt++) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* wr = w + (nt * 8 + g) * wstride + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) mma_bf16(c, afr[ks], lds32(wr + ks * 16), lds32(wr + ks * 16 + 8));
+        epi(nt, c);
+    }
+}
+
+// stage B: 16 rows shared by all warps (A from shared memory), this warp computes ONE output tile of the block
+template <int KS>
+__device__ __forceinline__ void tile_gemm(float (&c)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride, int g, int t) {
+    const __nv_bfloat16* wr = w + g * wstride + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        uint32_t af[4];
+        const __nv_bfloat16* p = a + ks * 16 + 2 * t;
+        af[0] = lds32(p + g * astride);
+        af[1] = lds32(p + (g + 8) * astride);
+        af[2] = lds32(p + g * astride + 8);
+        af[3] = lds32(p + (g + 8) * astride + 8);
+        mma_bf16(c, af, lds32(wr + ks * 16), lds32(wr + ks * 16 + 8));
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsigned char* __restrict__ blob, NnPlan plan, const int8_t* __restrict__ states,
+                                                                     const uint8_t* __restrict__ valids, int n_rows, float* __restrict__ pi,
+                                                                     float* __restrict__ vout) {
+    constexpr int R = 32 + 10 * NP + NP * NP, S = 7 * R, K1 = (R + 15) / 16 * 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NnSmem& sm = *reinterpret_cast<NnSmem*>(smem_raw);
+    const float* prm = reinterpret_cast<const float*>(blob);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int base = blockIdx.x * NN_SB;
+    const int live = min(NN_SB, n_rows - base);
+
+    // ---- weight-block ring: block b lives in slot b & 1
+    int next_issue = 0;
+    auto issue = [&](int b) {
+        const unsigned char* src = blob + plan.off[b];
+        unsigned char* dst = sm.slot[b & 1];
+        for (int i = tid * 16; i < plan.bytes[b]; i += NN_THREADS * 16) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue(0);
+    next_issue = 1;
+    auto acquire = [&](int b) -> const __nv_bfloat16* {   // block b ready for every thread; block b+1 in flight
+        if (next_issue == b + 1 && b + 1 < plan.nblocks) { issue(b + 1); next_issue = b + 2; cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        return reinterpret_cast<const __nv_bfloat16*>(sm.slot[b & 1]);
+    };
+    auto release = [&]() { __syncthreads(); };
+
+    // ---- input: act[c*16 + s][k] = state[s][k][c]  (int8 counts are exact in bf16), zero padding up to K1
+    for (int i = tid; i < 7 * NN_SB * K1; i += NN_THREADS) {
+        const int row = i / K1, k = i - row * K1, c = row >> 4, s = row & 15;
+        float x = 0.f;
+        if (k < R && s < live) x = (float)states[(size_t)(base + s) * S + k * 7 + c];
+        sm.act[row * ASTR + k] = __float2bfloat16(x);
+    }
+    __syncthreads();
+
+    uint32_t afr[8][4];
+    __nv_bfloat16* arow = sm.act + warp * 16 * ASTR;   // this warp's strip (stage A, warps 0..6)
+    const bool strip = warp < 7;
+    int blk = 0;
+
+    // ---- L1: Linear(R,128) + BatchNorm1d(7) + ReLU
+    {
+        const float s1 = strip ? prm[P_S1 + warp] : 0.f, t1 = strip ? prm[P_T1 + warp] : 0.f;
+        if (strip) load_afrags<K1 / 16>(afr, arow, ASTR, g, t);
+        __syncwarp();
+        for (int h = 0; h < 2; h++) {
+            const __nv_bfloat16* w = acquire(blk);
+            if (strip)
+                strip_gemm<K1 / 16>(afr, w, K1 + 8, g, t, [&](int nt, float (&c)[4]) {
+                    const int n = h * 64 + nt * 8 + 2 * t;
+                    const float b0 = prm[P_B1 + n], b1 = prm[P_B1 + n + 1];
+                    sts_bf16x2(arow + g * ASTR + n, fmaxf((c[0] + b0) * s1 + t1, 0.f), fmaxf((c[1] + b1) * s1 + t1, 0.f));
+                    sts_bf16x2(arow + (g + 8) * ASTR + n, fmaxf((c[2] + b0) * s1 + t1, 0.f), fmaxf((c[3] + b1) * s1 + t1, 0.f));
+                });
+            release(); blk++;
+        }
+    }
+    // ---- L2 and (after the pool layer) L3: Linear(128,128) + ReLU
+    auto dense_relu_strip = [&](int pbias) {
+        if (strip) load_afrags<8>(afr, arow, ASTR, g, t);
+        __syncwarp();
+        for (int h = 0; h < 2; h++) {
+            const __nv_bfloat16* w = acquire(blk);
+            if (strip)
+                strip_gemm<8>(afr, w, ASTR, g, t, [&](int nt, float (&c)[4]) {
+                    const int n = h * 64 + nt * 8 + 2 * t;
+                    const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
+                    sts_bf16x2(arow + g * ASTR + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
+                    sts_bf16x2(arow + (g + 8) * ASTR + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
+                });
+            release(); blk++;
+        }
+    };
+    dense_relu_strip(P_B2);
+    // ---- G1: DenseAndPartialGPool(128 -> 128; 4 groups of 8 max+avg, Linear(96,120)+BN(7)+ReLU)
+    {
+        const float sg = strip ? prm[P_SG1 + warp] : 0.f, tg = strip ? prm[P_TG1 + warp] : 0.f;
+        float pmx[2], pav[2];
+        if (strip) {
+            load_afrags<6>(afr, arow + 32, ASTR, g, t);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {   // 64 (row, group) pairs per strip, two per lane
+                const int pr = lane * 2 + q, row = pr >> 2, grp = pr & 3;
+                const uint4 raw = *reinterpret_cast<const uint4*>(arow + row * ASTR + grp * 8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    mx = fmaxf(mx, fmaxf(f.x, f.y)); sum += f.x + f.y;
+                }
+                pmx[q] = mx; pav[q] = sum * 0.125f;
+            }
+        }
+        __syncwarp();
+        if (strip) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int pr = lane * 2 + q, row = pr >> 2, grp = pr & 3;
+                arow[row * ASTR + grp] = __float2bfloat16(pmx[q]);
+                arow[row * ASTR + 4 + grp] = __float2bfloat16(pav[q]);
+            }
+        }
+        for (int h = 0; h < 2; h++) {
+            const __nv_bfloat16* w = acquire(blk);
+            if (strip)
+                strip_gemm<6>(afr, w, 96 + 8, g, t, [&](int nt, float (&c)[4]) {
+                    const int n = h * 64 + nt * 8 + 2 * t;
+                    if (n < 120) {
+                        const float b0 = prm[P_BG1 + n], b1 = prm[P_BG1 + n + 1];
+                        sts_bf16x2(arow + g * ASTR + 8 + n, fmaxf((c[0] + b0) * sg + tg, 0.f), fmaxf((c[1] + b1) * sg + tg, 0.f));
+                        sts_bf16x2(arow + (g + 8) * ASTR + 8 + n, fmaxf((c[2] + b0) * sg + tg, 0.f), fmaxf((c[3] + b1) * sg + tg, 0.f));
+                    }
+                });
+            release(); blk++;
+        }
+    }
+    dense_relu_strip(P_B3);
+
+    // ---- FlattenAndPartialGPool(64, 5): [max over the 5 gem colours | mean | gold, points rows | last 64 features of all 7]
+    for (int i = tid; i < NN_SB * 704; i += NN_THREADS) {
+        const int s = i / 704, f = i - s * 704;
+        float x;
+        if (f < 128) {
+            const int j = f & 63;
+            float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float a = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
+                mx = fmaxf(mx, a); sum += a;
+            }
+            x = f < 64 ? mx : sum * 0.2f;
+        } else if (f < 256) {
+            const int c = 5 + ((f - 128) >> 6), j = (f - 128) & 63;
+            x = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
+        } else {
+            const int c = (f - 256) >> 6, j = 64 + ((f - 256) & 63);
+            x = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
+        }
+        sm.flat[s * FSTR + f] = __float2bfloat16(x);
+    }
+    __syncthreads();
+
+    // ---- L4: Linear(704,128) + ReLU. 16 rows; warp w owns output tiles 2w, 2w+1; accumulate over 11 k-blocks
+    {
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kb = 0; kb < 11; kb++) {
+            const __nv_bfloat16* w = acquire(blk);
+            tile_gemm<4>(c0, sm.flat + kb * 64, FSTR, w + (2 * warp) * 8 * 72, 72, g, t);
+            tile_gemm<4>(c1, sm.flat + kb * 64, FSTR, w + (2 * warp + 1) * 8 * 72, 72, g, t);
+            release(); blk++;
+        }
+        __nv_bfloat16* o = sm.vec[0];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            float(&c)[4] = q ? c1 : c0;
+            const int n = (2 * warp + q) * 8 + 2 * t;
+            const float b0 = prm[P_B4 + n], b1 = prm[P_B4 + n + 1];
+            sts_bf16x2(o + g * ASTR + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
+            sts_bf16x2(o + (g + 8) * ASTR + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
+        }
+        __syncthreads();
+    }
+    // stage B helpers: in -> out, two [64 n][KB] blocks, warp w owns tile w of each block
+    auto dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias, bool relu) {
+        for (int h = 0; h < 2; h++) {
+            const __nv_bfloat16* w = acquire(blk);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_gemm<8>(c, in, ASTR, w + warp * 8 * ASTR, ASTR, g, t);
+            const int n = h * 64 + warp * 8 + 2 * t;
+            const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
+            float v0 = c[0] + b0, v1 = c[1] + b1, v2 = c[2] + b0, v3 = c[3] + b1;
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            sts_bf16x2(out + g * ASTR + n, v0, v1);
+            sts_bf16x2(out + (g + 8) * ASTR + n, v2, v3);
+            release(); blk++;
+        }
+    };
+    auto pool_dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias) {   // 4 groups of 4 + Linear(112,120)+BN(1)+ReLU
+        if (tid < 64) {
+            const int row = tid >> 2, grp = tid & 3;
+            const uint2 raw = *reinterpret_cast<const uint2*>(in + row * ASTR + grp * 4);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const float2 a = __bfloat1622float2(h2[0]), b = __bfloat1622float2(h2[1]);
+            out[row * ASTR + grp] = __float2bfloat16(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)));
+            out[row * ASTR + 4 + grp] = __float2bfloat16((a.x + a.y + b.x + b.y) * 0.25f);
+        }
+        for (int h = 0; h < 2; h++) {
+            const __nv_bfloat16* w = acquire(blk);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_gemm<7>(c, in + 16, ASTR, w + warp * 8 * 120, 120, g, t);
+            const int n = h * 64 + warp * 8 + 2 * t;
+            if (n < 120) {
+                const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
+                sts_bf16x2(out + g * ASTR + 8 + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
+                sts_bf16x2(out + (g + 8) * ASTR + 8 + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
+            }
+            release(); blk++;
+        }
+    };
+    pool_dense_vec(sm.vec[0], sm.vec[1], P_BG4);
+    dense_vec(sm.vec[1], sm.vec[0], P_B5A, true);
+    dense_vec(sm.vec[0], sm.vec[1], P_B5B, true);
+    pool_dense_vec(sm.vec[1], sm.vec[0], P_BG5);
+    dense_vec(sm.vec[0], sm.vec[1], P_BP0, false);   // output_layers_PI.0 (no activation)
+    dense_vec(sm.vec[0], sm.vec[2], P_BV0, false);   // output_layers_V.0
+
+    // ---- PI1: 128 -> 406 logits (fp32, in the former activation buffer), 7 blocks of 64 rows
+    float* logits = reinterpret_cast<float*>(sm.act);
+    for (int h = 0; h < 7; h++) {
+        const __nv_bfloat16* w = acquire(blk);
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        tile_gemm<8>(c, sm.vec[1], ASTR, w + warp * 8 * ASTR, ASTR, g, t);
+        const int n = h * 64 + warp * 8 + 2 * t;
+        if (n < LSTR) {
+            const float b0 = prm[P_BP1 + n], b1 = prm[P_BP1 + n + 1];
+            logits[g * LSTR + n] = c[0] + b0; logits[g * LSTR + n + 1] = c[1] + b1;
+            logits[(g + 8) * LSTR + n] = c[2] + b0; logits[(g + 8) * LSTR + n + 1] = c[3] + b1;
+        }
+        release(); blk++;
+    }
+    // ---- V1: 128 -> n, tanh
+    {
+        const __nv_bfloat16* w = acquire(blk);
+        if (warp == 0) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_gemm<8>(c, sm.vec[2], ASTR, w, ASTR, g, t);
+            const int n = 2 * t;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int row = g + (q >> 1) * 8, col = n + (q & 1);
+                if (col < NP && row < live) vout[(size_t)(base + row) * NP + col] = tanhf(c[q] + prm[P_BV1 + col]);
+            }
+        }
+        release(); blk++;
+    }
+    // ---- masked softmax: log_softmax(where(valid, pi, -1e8)) then exp (SplendorNNet.py:153-159, GenericNNetWrapper.py:166)
+    for (int s = warp * 2; s < warp * 2 + 2; s++) {
+        if (s >= live) continue;
+        const uint8_t* va = valids + (size_t)(base + s) * NN_ACTIONS;
+        float x[13], mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 13; j++) {
+            const int a = lane + 32 * j;
+            x[j] = -INFINITY;
+            if (a < NN_ACTIONS) { x[j] = va[a] ? logits[s * LSTR + a] : -1e8f; mx = fmaxf(mx, x[j]); }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 13; j++) {
+            x[j] = (lane + 32 * j) < NN_ACTIONS ? expf(x[j] - mx) : 0.f;
+            sum += x[j];
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 13; j++) {
+            const int a = lane + 32 * j;
+            if (a < NN_ACTIONS) pi[(size_t)(base + s) * NN_ACTIONS + a] = x[j] * inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host: BatchNorm folding + blob packing
+struct BnFold { double s[8], t[8]; };
+BnFold fold_bn(const float* w, const float* b, const float* mean, const float* var, int c) {
+    BnFold f;
+    for (int i = 0; i < c; i++) {
+        f.s[i] = (double)w[i] / sqrt((double)var[i] + 1e-5);
+        f.t[i] = (double)b[i] - (double)mean[i] * f.s[i];
+    }
+    return f;
+}
+uint16_t to_bf16(double x) {
+    float f = (float)x;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);   // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+// writes rows [n0, n0+nb) x cols [k0, k0+kb) of W[N][K] (scaled by `scale`) as a padded [nb][kb+8] bf16 block
+void pack_block(unsigned char* dst, const float* W, int N, int K, int n0, int nb, int k0, int kb, double scale) {
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    for (int r = 0; r < nb; r++)
+        for (int c = 0; c < kb + 8; c++) {
+            const int n = n0 + r, k = k0 + c;
+            d[r * (kb + 8) + c] = (n < N && c < kb && k < K) ? to_bf16((double)W[(size_t)n * K + k] * scale) : (uint16_t)0;
+        }
+}
+
+}   // namespace
+
+extern "C" {
+
+size_t spl_nnet_blob_bytes(int n_players) {
+    if (n_players < 2 || n_players > 4) return 0;
+    return (size_t)make_plan(n_players).total_bytes;
+}
+
+int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_bytes) {
+    if (n_players < 2 || n_players > 4 || !T || !blob) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: bad argument");
+    const NnPlan p = make_plan(n_players);
+    if (blob_bytes < (size_t)p.total_bytes) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: blob smaller than spl_nnet_blob_bytes");
+    for (int i = 0; i < 46; i++)
+        if (!T[i]) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: null tensor");
+    const int R = 32 + 10 * n_players + n_players * n_players, K1 = kpad1(n_players);
+    unsigned char* B = (unsigned char*)blob;
+    memset(B, 0, p.total_bytes);
+    float* prm = reinterpret_cast<float*>(B);
+    const BnFold bn1 = fold_bn(T[2], T[3], T[4], T[5], 7), bng1 = fold_bn(T[10], T[11], T[12], T[13], 7);
+    const BnFold bn4 = fold_bn(T[20], T[21], T[22], T[23], 1), bn5 = fold_bn(T[26], T[27], T[28], T[29], 1), bng5 = fold_bn(T[34], T[35], T[36], T[37], 1);
+    for (int i = 0; i < 128; i++) {
+        prm[P_B1 + i] = T[1][i]; prm[P_B2 + i] = T[7][i]; prm[P_B3 + i] = T[15][i]; prm[P_B4 + i] = T[17][i];
+        prm[P_B5A + i] = (float)((double)T[25][i] * bn5.s[0] + bn5.t[0]);
+        prm[P_B5B + i] = T[31][i]; prm[P_BP0 + i] = T[39][i]; prm[P_BV0 + i] = T[43][i];
+    }
+    for (int i = 0; i < 120; i++) {
+        prm[P_BG1 + i] = T[9][i];
+        prm[P_BG4 + i] = (float)((double)T[19][i] * bn4.s[0] + bn4.t[0]);
+        prm[P_BG5 + i] = (float)((double)T[33][i] * bng5.s[0] + bng5.t[0]);
+    }
+    for (int i = 0; i < 7; i++) {
+        prm[P_S1 + i] = (float)bn1.s[i]; prm[P_T1 + i] = (float)bn1.t[i];
+        prm[P_SG1 + i] = (float)bng1.s[i]; prm[P_TG1 + i] = (float)bng1.t[i];
+    }
+    for (int i = 0; i < NN_ACTIONS; i++) prm[P_BP1 + i] = T[41][i];
+    for (int i = 0; i < n_players; i++) prm[P_BV1 + i] = T[45][i];
+    int b = 0;
+    auto two = [&](const float* W, int N, int K, int kb, double scale) {   // two [64][kb] blocks: n halves
+        pack_block(B + p.off[b], W, N, K, 0, 64, 0, kb, scale); b++;
+        pack_block(B + p.off[b], W, N, K, 64, 64, 0, kb, scale); b++;
+    };
+    two(T[0], 128, R, K1, 1.0);
+    two(T[6], 128, 128, 128, 1.0);
+    two(T[8], 120, 96, 96, 1.0);
+    two(T[14], 128, 128, 128, 1.0);
+    for (int kbk = 0; kbk < 11; kbk++) { pack_block(B + p.off[b], T[16], 128, 704, 0, 128, kbk * 64, 64, 1.0); b++; }
+    two(T[18], 120, 112, 112, bn4.s[0]);
+    two(T[24], 128, 128, 128, bn5.s[0]);
+    two(T[30], 128, 128, 128, 1.0);
+    two(T[32], 120, 112, 112, bng5.s[0]);
+    two(T[38], 128, 128, 128, 1.0);
+    two(T[42], 128, 128, 128, 1.0);
+    for (int h = 0; h < 7; h++) { pack_block(B + p.off[b], T[40], NN_ACTIONS, 128, h * 64, 64, 0, 128, 1.0); b++; }
+    pack_block(B + p.off[b], T[44], n_players, 128, 0, 64, 0, 128, 1.0); b++;
+    if (b != p.nblocks) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: internal block count mismatch");
+    return SPL_OK;
+}
+
+int spl_nnet_forward(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream) {
+    if (!c) return spl_fail_(SPL_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!blob || !states || !valids || !pi || !v || n_rows <= 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: bad argument");
+    if (((uintptr_t)blob & 15u) != 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: blob must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const NnPlan p = make_plan(c->n);
+    const int grid = (n_rows + NN_SB - 1) / NN_SB;
+    const int smem = (int)sizeof(NnSmem);
+    DISPATCH_N(c->n, {
+        auto k = nnet_forward_kernel<N>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, NN_THREADS, smem, st>>>((const unsigned char*)blob, p, states, valids, n_rows, pi, v);
+    });
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+}   // extern "C"

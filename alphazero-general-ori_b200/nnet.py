@@ -152,6 +152,89 @@ def forward_folded(W, states, valids):
     return torch.softmax(logits, dim=1), v
 
 
+PACK_ORDER = (
+    [f"dense2d_1.0.{k}" for k in ("weight", "bias")] + [f"dense2d_1.1.{k}" for k in ("weight", "bias", "running_mean", "running_var")]
+    + [f"dense2d_1.3.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_1.dense_part.0.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_1.dense_part.1.{k}" for k in ("weight", "bias", "running_mean", "running_var")]
+    + [f"dense2d_3.0.{k}" for k in ("weight", "bias")] + [f"dense1d_4.0.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_4.dense_part.0.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_4.dense_part.1.{k}" for k in ("weight", "bias", "running_mean", "running_var")]
+    + [f"dense1d_5.0.{k}" for k in ("weight", "bias")] + [f"dense1d_5.1.{k}" for k in ("weight", "bias", "running_mean", "running_var")]
+    + [f"dense1d_5.3.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_5.dense_part.0.{k}" for k in ("weight", "bias")]
+    + [f"partialgpool_5.dense_part.1.{k}" for k in ("weight", "bias", "running_mean", "running_var")]
+    + [f"output_layers_PI.0.{k}" for k in ("weight", "bias")] + [f"output_layers_PI.1.{k}" for k in ("weight", "bias")]
+    + [f"output_layers_V.0.{k}" for k in ("weight", "bias")] + [f"output_layers_V.1.{k}" for k in ("weight", "bias")]
+)   # the 46 tensors spl_nnet_pack takes, in order (include/splendor_b200.h)
+
+
+def pack_blob(n_players, sd):
+    """state_dict -> packed weight blob (host uint8 tensor) through the library's own packer (pure host code)"""
+    import ctypes as C
+    from . import _native as nat
+    lib = nat.lib()
+    arrs = [np.ascontiguousarray(sd[k].detach().cpu().numpy(), dtype=np.float32) for k in PACK_ORDER]
+    ptrs = (C.POINTER(C.c_float) * len(arrs))(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+    nbytes = lib.spl_nnet_blob_bytes(int(n_players))
+    blob = np.zeros(nbytes, dtype=np.uint8)
+    nat.check(lib.spl_nnet_pack(int(n_players), ptrs, C.c_void_p(blob.ctypes.data), nbytes))
+    return torch.from_numpy(blob)
+
+
+class FusedSplendorNNet:
+    """The same evaluator as SplendorNNetB200 in ONE kernel launch (csrc/spl_nnet.cu): bf16 tensor-core products with
+    fp32 accumulation, activations resident in shared memory. Output buffers are static per batch size (CUDA-graph safe)."""
+
+    def __init__(self, n_players, state_dict=None, seed=0, device=0):
+        import ctypes as C
+        from . import _native as nat
+        if not torch.cuda.is_available():
+            raise RuntimeError("FusedSplendorNNet needs a CUDA device; there is no CPU fallback")
+        self.n, self.R = int(n_players), _rows(int(n_players))
+        self.device = torch.device("cuda", device)
+        self._lib, self._nat, self._C = nat.lib(), nat, C
+        h = C.c_void_p()
+        nat.check(self._lib.spl_ctx_create(self.n, 10, nat.RULES_DEFAULT, device, C.byref(h)))
+        self._ctx = h
+        self._out = {}
+        self.load_state_dict(state_dict if state_dict is not None else random_state_dict(self.n, seed))
+        self.launch_estimate = 1
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                self._lib.spl_ctx_destroy(self._ctx); self._ctx = None
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd):
+        blob = pack_blob(self.n, sd)
+        self.blob = torch.empty(blob.numel() + 16, dtype=torch.uint8, device=self.device)
+        off = (-self.blob.data_ptr()) % 16
+        self._blob_view = self.blob[off:off + blob.numel()]
+        self._blob_view.copy_(blob)
+
+    def __call__(self, states, valids):
+        B = states.shape[0]
+        out = self._out.get(B)
+        if out is None:
+            out = (torch.empty((B, NUM_ACTIONS), dtype=torch.float32, device=self.device),
+                   torch.empty((B, self.n), dtype=torch.float32, device=self.device))
+            self._out[B] = out
+        C = self._C
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._nat.check(self._lib.spl_nnet_forward(self._ctx, C.c_void_p(self._blob_view.data_ptr()), C.c_void_p(states.data_ptr()),
+                                                   C.c_void_p(valids.data_ptr()), B, C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), st))
+        return out
+
+    def predict(self, board, valid_actions):
+        st = torch.from_numpy(np.ascontiguousarray(board, dtype=np.int8)).view(1, self.R, 7).to(self.device)
+        va = torch.from_numpy(np.ascontiguousarray(valid_actions).astype(np.uint8)).view(1, NUM_ACTIONS).to(self.device)
+        pi, v = self(st, va)
+        return pi[0].cpu().numpy(), v[0].cpu().numpy()
+
+
 class SplendorNNetB200:
     """`predict`-compatible evaluator (NeuralNet.py:33-46) plus the batched device call the tree arena uses."""
 

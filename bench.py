@@ -43,7 +43,8 @@ def parse():
     # MCTS (configs[1])
     ap.add_argument("--trees", type=int, default=4096, help="parallel games (trees) per GPU")
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
-    ap.add_argument("--nn-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--nn-dtype", default="fp32", choices=["fp32", "bf16", "fused"],
+                    help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
     ap.add_argument("--graph-waves", type=int, default=16, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="ply", choices=["ply", "reachable"])
     ap.add_argument("--node-cap", type=int, default=0)
@@ -257,8 +258,10 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     n, T, sims = args.players, args.trees, args.sims
     torch.backends.cuda.matmul.allow_tf32 = False      # the float32 network is evaluated in float32
     torch.backends.cudnn.allow_tf32 = False
-    dtype = torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16
-    net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=dtype)
+    if args.nn_dtype == "fused":
+        net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
+    else:
+        net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16)
     reach = args.gc == "reachable"
     cap = args.node_cap or (3 if reach else 8) * sims
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,

@@ -217,6 +217,25 @@ int  spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int3
  * golden MCTS fixtures were produced by the reference's own MCTS.py with this function as its network */
 int  spl_mcts_fixed_net(spl_ctx* ctx, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream);
 
+/* ======================================================================================================
+ * Fused leaf evaluator  (replaces GenericNNetWrapper.predict :141-168 + SplendorNNet.forward, SplendorNNet.py:127-159,
+ * for inference on device rows; one launch per batch, bf16 tensor-core products with fp32 accumulation)
+ * ====================================================================================================== */
+/* bytes of the packed weight blob for an n-player network */
+size_t spl_nnet_blob_bytes(int n_players);
+/* HOST-side packing (no GPU involved): folds the BatchNorm layers (eval mode) and lays the weights out as the kernel
+ * streams them. `tensors`: 46 host float arrays in the reference's state_dict order (SplendorNNet.py:75-114), BatchNorm
+ * entries as (weight, bias, running_mean, running_var):
+ *   dense2d_1.0.{weight,bias}, dense2d_1.1.{4}, dense2d_1.3.{w,b}, partialgpool_1.dense_part.0.{w,b}, partialgpool_1.dense_part.1.{4},
+ *   dense2d_3.0.{w,b}, dense1d_4.0.{w,b}, partialgpool_4.dense_part.0.{w,b}, partialgpool_4.dense_part.1.{4}, dense1d_5.0.{w,b},
+ *   dense1d_5.1.{4}, dense1d_5.3.{w,b}, partialgpool_5.dense_part.0.{w,b}, partialgpool_5.dense_part.1.{4},
+ *   output_layers_PI.0.{w,b}, output_layers_PI.1.{w,b}, output_layers_V.0.{w,b}, output_layers_V.1.{w,b} */
+int spl_nnet_pack(int n_players, const float* const* tensors, void* blob_host, size_t blob_bytes);
+/* states int8[B][R*7], valids uint8[B][406] -> pi float[B][406] (probabilities), v float[B][n]; blob = device copy of the
+ * packed weights (16-byte aligned) */
+int spl_nnet_forward(spl_ctx* ctx, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

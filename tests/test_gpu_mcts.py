@@ -216,3 +216,28 @@ def test_search_with_the_real_network_and_dirichlet_sampler():
     assert np.allclose(ps.sum(1), 1.0, atol=1e-5) and (ps >= 0).all()
     probs, q = ar.policy(1.0)
     assert np.allclose(_np(probs).sum(1), 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_fused_network_kernel(golden_dir, n):
+    """one-launch evaluator (csrc/spl_nnet.cu, bf16 products / fp32 accumulation) vs the reference network's recorded
+    float32 outputs and vs the torch bf16 path; ragged batch sizes. Tolerance: bf16 inference, 0.05 absolute."""
+    az = _azg()
+    g = np.load(os.path.join(golden_dir, f"nnet_n{n}.npz"))
+    sd = az.nnet.random_state_dict(n, int(g["seed"]))
+    net = az.FusedSplendorNNet(n, state_dict=sd)
+    st = torch.from_numpy(g["state"]).to(net.device); va = torch.from_numpy(g["valids"].astype(np.uint8)).to(net.device)
+    pi, v = net(st, va)
+    torch.cuda.synchronize()
+    pi, v = _np(pi).copy(), _np(v).copy()
+    assert np.isfinite(pi).all() and np.isfinite(v).all()
+    assert np.allclose(pi.sum(1), 1.0, atol=1e-4) and (pi[~g["valids"]] == 0).all()
+    e_pi, e_v = np.abs(pi - g["pi"]).max(), np.abs(v - g["v"]).max()
+    assert e_pi < 0.05 and e_v < 0.05, (e_pi, e_v)
+    assert np.abs(pi - g["pi"]).mean() < 2e-4          # a layout slip would be far above this
+    for B in (1, 15, 17, 33):                          # ragged tails of the 16-leaf tiles
+        p2, v2 = net(st[:B].contiguous(), va[:B].contiguous())
+        torch.cuda.synchronize()
+        assert np.array_equal(_np(p2), pi[:B]) and np.array_equal(_np(v2), v[:B])
+    p1, v1 = net.predict(g["state"][5], g["valids"][5])
+    assert np.array_equal(p1, pi[5]) and np.array_equal(v1, v[5])

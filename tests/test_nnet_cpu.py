@@ -26,3 +26,25 @@ def test_state_dict_shapes_are_the_checkpoint_format():
     assert sh["dense2d_1.0.weight"] == (128, 56) and sh["output_layers_PI.1.weight"] == (406, 128)
     # (the generator script loads random_state_dict into the reference module with strict=True: names and shapes are the reference's)
     assert set(nnet.random_state_dict(3, 1).keys()) == set(nnet.state_dict_shapes(3).keys())
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_blob_packer_folds_batchnorm_like_the_torch_path(n):
+    """spl_nnet_pack is pure host code: its fp32 parameter region must agree with nnet.fold (BatchNorm folded in float64)"""
+    import azg_b200
+    sd = nnet.random_state_dict(n, 5)
+    blob = nnet.pack_blob(n, sd).numpy()
+    assert blob.size == azg_b200._native.lib().spl_nnet_blob_bytes(n) and blob.size % 16 == 0
+    prm = blob[: 1896 * 4].view(np.float32)
+    W = nnet.fold(sd, "cpu", torch.float32)
+    assert np.allclose(prm[0:128], W["l1_b"].numpy()) and np.allclose(prm[128:135], W["bn1_s"].numpy().ravel(), rtol=1e-6)
+    assert np.allclose(prm[136:143], W["bn1_t"].numpy().ravel(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(prm[672:792], W["g4_b"].numpy(), rtol=1e-6, atol=1e-7)          # BatchNorm1d(1) folded into the bias
+    assert np.allclose(prm[800:928], W["l5a_b"].numpy(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(prm[1312:1312 + 406], W["PI1_b"].numpy()) and np.allclose(prm[1888:1888 + n], W["V1_b"].numpy())
+    # first weight block: rows 0..63 of dense2d_1.0.weight as bf16, row stride K1 + 8, zero padded
+    R = 32 + 10 * n + n * n
+    K1 = (R + 15) // 16 * 16
+    blk = blob[1896 * 4: 1896 * 4 + 64 * (K1 + 8) * 2].view(np.uint16).reshape(64, K1 + 8)
+    want = sd["dense2d_1.0.weight"][:64].to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(blk[:, :R], want) and (blk[:, R:] == 0).all()
