@@ -56,7 +56,7 @@ class RolloutArgs(C.Structure):
 class MctsParams(C.Structure):
     _fields_ = [
         ("cpuct", C.c_double), ("fpu", C.c_double), ("temperature0", C.c_double), ("dirichlet_alpha", C.c_double),
-        ("seed", C.c_uint64), ("game_base", C.c_uint32), ("edge_reserve", C.c_int), ("gc_reachable", C.c_int),
+        ("seed", C.c_uint64), ("game_base", C.c_uint32), ("edge_reserve", C.c_int), ("gc_reachable", C.c_int), ("rounds", C.c_int),
     ]
 
 
@@ -128,8 +128,8 @@ def lib():
         L.spl_mcts_destroy.restype = None
         L.spl_mcts_set_params.argtypes = [vp, C.POINTER(MctsParams)]
         L.spl_mcts_reset.argtypes = [vp, vp, vp]
-        L.spl_mcts_begin.argtypes = [vp, vp, vp, vp, vp, vp]
-        L.spl_mcts_select.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.spl_mcts_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.spl_mcts_select.argtypes = [vp, vp, vp, vp, vp, vp]
         L.spl_mcts_expand.argtypes = [vp, vp, vp, vp, vp]
         L.spl_mcts_policy.argtypes = [vp, C.c_double, vp, vp, vp]
         L.spl_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]

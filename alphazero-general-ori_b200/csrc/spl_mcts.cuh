@@ -2,8 +2,10 @@
 // for the test-only host simulator in tests/hostsim/, never by the product's host path).
 //
 // What it replaces in the reference (MCTS.py):
-//   mcts_select_tree   <- MCTS.search :99-177 down to the first unevaluated node, incl. pick_highest_UCB :199-219 and
-//                         get_next_best_action_and_canonical_state :222-237 (make_move deterministic + swap_players)
+//   mcts_descend_tree  <- MCTS.search :99-177 down to the first edge that was never taken, incl. pick_highest_UCB :199-219
+//   mcts_rules_core    <- get_next_best_action_and_canonical_state :222-237 (make_move deterministic + swap_players) and
+//                         the new node's getGameEnded :124 / getValidMoves :136 - run one LANE per tree (32 trees per warp)
+//   mcts_attach_tree   <- the dictionary lookup / insertion of the child (nodes_data.get :120, :146) and leaf hand-over
 //   mcts_expand_tree   <- the "first time that we explore state s" branch :134-148 (Ps from the network, normalise,
 //                         root softmax + Dirichlet noise :141-144,180-186) followed by the backup :168-177
 //   mcts_begin_tree    <- the dictionary lookup of the root (nodes_data.get :119-120) + tree cleaning :80-85
@@ -114,7 +116,7 @@ struct MctsEdge {   // 24 B
     uint32_t child;  // node index + 1 (0 = not linked yet)
     uint16_t action, pad;
 };
-struct MctsTree {   // 80 B
+struct MctsTree {   // 96 B
     int32_t n_nodes, n_edges, root, leaf;
     int32_t sims_done, sims_target, path_len;
     uint32_t flags, status;
@@ -122,7 +124,11 @@ struct MctsTree {   // 80 B
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
     int32_t truncated; // searches cut short because a pool filled up mid-move (the next begin makes room again)
     int32_t depth_sum; // sum of path lengths of this move's simulations (diagnostics)
-    int32_t pad[2];
+    // state of the simulation in flight (it survives between the kernels of a wave):
+    int32_t cur;         // >= 0: continue the descent at this node with path_len edges already recorded; -1: start at the root
+    int32_t pend_edge;   // >= 0: the descent stopped at this (absolute) edge, whose child state is being computed / attached
+    int32_t pend_parent; // node index of that edge's parent
+    int32_t pad[3];
 };
 struct MctsArena {
     int n_trees, cap, ecap, hcap, sp, max_depth;
@@ -132,6 +138,11 @@ struct MctsArena {
     uint32_t* htab;    // [T][hcap]      node index + 1, linear probing
     MctsTree* trees;   // [T]
     uint32_t* path;    // [T][max_depth][2]  (node, absolute edge index) of the current simulation
+    // staging between the rules kernel and the attach kernel (the child state of every tree's pending edge)
+    int8_t* stage_state;   // [T][sp]
+    uint32_t* stage_mask;  // [13][T]
+    float* stage_es;       // [T][4]
+    uint8_t* stage_ended;  // [T]
 };
 struct MctsSearchParams {
     double cpuct, fpu, temperature0, dirichlet_alpha;
@@ -217,11 +228,12 @@ SPL_D void mcts_table_insert(const W& w, const MctsArena& A, int t, int idx, uin
     w.sync();
 }
 
-// New node for the state in `st` (sp bytes, zero padded): stores the bytes, computes getGameEnded (:124) and, for a
-// live position, getValidMoves (:136) -> one edge per legal action. Returns the node index or -1 on pool overflow.
-// `scratch` = 16 uint32 of per-warp scratch.
+// New node for the state `st` (sp bytes, zero padded) whose end-of-game vector / legal mask are already known:
+// stores the bytes, allocates one edge per legal action (in action order), links it into the hash table.
+// m: the 13 mask words at m[i * mstride]; es: N floats (used when ended). Returns the node index or -1 on pool overflow.
 template <int N, class W>
-SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
+SPL_D int mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h, bool ended, const float* es,
+                          const uint32_t* m, int mstride) {
     MctsTree* T = A.trees + t;
     const int idx = T->n_nodes;
     if (idx >= A.cap) {
@@ -229,23 +241,21 @@ SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSear
         w.sync();
         return -1;
     }
+    int k = 0;
+    if (!ended)
+        for (int i = 0; i < SPL_MASK_WORDS; i++) k += SPL_POPC(m[i * mstride]);
+    const int e0 = T->n_edges;
+    if (!ended && e0 + k > A.ecap) {
+        if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_EDGES;
+        w.sync();
+        return -1;
+    }
     MctsNode* nd = A.nodes + (size_t)t * A.cap + idx;
     if (w.lane == 0) {
-        AosAcc s{st};
-        float es[N];
-        const bool ended = spl_game_ended<N>(s, P.rules, es);
-        uint32_t* m = scratch;
-        int k = 0;
-        if (!ended) {
-            spl_valid_mask<N>(s, 0, P.rules, m);
-            for (int i = 0; i < SPL_MASK_WORDS; i++) k += SPL_POPC(m[i]);
-        }
-        scratch[13] = ended ? 1u : 0u;
-        scratch[14] = (uint32_t)k;
         nd->hash = h;
         nd->ply = (uint8_t)st[6];
         nd->n_edges = (uint16_t)k;
-        nd->edge_off = (uint32_t)T->n_edges;
+        nd->edge_off = (uint32_t)e0;
         if (ended) {
             nd->kind = MCTS_NODE_TERMINAL;
             for (int i = 0; i < 4; i++) nd->u.es[i] = i < N ? es[i] : 0.f;
@@ -254,22 +264,13 @@ SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSear
             nd->u.x.Ns = 0; nd->u.x.Qs = 0.f; nd->u.x.pad[0] = nd->u.x.pad[1] = 0u;
         }
     }
-    w.sync();
-    const bool ended = scratch[13] != 0u;
-    const int k = (int)scratch[14];
-    const int e0 = T->n_edges;
-    if (!ended && e0 + k > A.ecap) {
-        if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_EDGES;
-        w.sync();
-        return -1;
-    }
     mcts_copy16(w, A.states + ((size_t)t * A.cap + idx) * A.sp, st, A.sp);
     if (!ended) {   // edges in action order: word i of the mask owns a contiguous run
         MctsEdge* ed = A.edges + (size_t)t * A.ecap + e0;
         for (int i = w.lane; i < SPL_MASK_WORDS; i += W::W) {
             int off = 0;
-            for (int j = 0; j < i; j++) off += SPL_POPC(scratch[j]);
-            uint32_t bits = scratch[i];
+            for (int j = 0; j < i; j++) off += SPL_POPC(m[j * mstride]);
+            uint32_t bits = m[i * mstride];
             while (bits) {
                 const int b = SPL_FFS(bits) - 1;
                 bits &= bits - 1u;
@@ -285,6 +286,46 @@ SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSear
         if (!ended) T->n_edges = e0 + k;
     }
     mcts_table_insert(w, A, t, idx, h);
+    return idx;
+}
+
+// getGameEnded (:124) and, for a live position, getValidMoves (:136) of a canonical state, as one thread's work
+template <int N, class S>
+SPL_D bool mcts_eval_state(const S& s, SplRules rules, float* es, uint32_t* m) {
+    const bool ended = spl_game_ended<N>(s, rules, es);
+    if (!ended) spl_valid_mask<N>(s, 0, rules, m);
+    else
+        for (int i = 0; i < SPL_MASK_WORDS; i++) m[i] = 0u;
+    return ended;
+}
+
+// in-tree step of one thread: make_move(a, 0, deterministic=True) + swap_players(next_player) (:226-235), then the
+// evaluation of the new state. One LANE per tree on the device (32 trees per warp on shared-memory tiles).
+template <int N, class S>
+SPL_D bool mcts_rules_core(S& s, int action, SplRules rules, float* es, uint32_t* m) {
+    SplChance ch;
+    ch.mode = 0; ch.code = 0; ch.seed = 0; ch.game = 0; ch.episode = 0; ch.ply = 0;
+    const int nxt = spl_apply_move<N>(s, action, 0, ch);
+    if (nxt > 0) spl_rotate<N>(s, nxt, rules);
+    return mcts_eval_state<N>(s, rules, es, m);
+}
+
+// root creation at the start of a move (one per move per tree: lane 0 evaluates the state, the warp stores it)
+// `scratch` = 24 uint32 of per-warp scratch.
+template <int N, class W>
+SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
+    if (w.lane == 0) {
+        AosAcc s{st};
+        float es[N];
+        const bool ended = mcts_eval_state<N>(s, P.rules, es, scratch);
+        scratch[13] = ended ? 1u : 0u;
+        for (int i = 0; i < N; i++) memcpy(&scratch[16 + i], &es[i], 4);
+    }
+    w.sync();
+    float es[N];
+    for (int i = 0; i < N; i++) memcpy(&es[i], &scratch[16 + i], 4);
+    const int idx = mcts_store_node<N>(w, A, t, st, h, scratch[13] != 0u, es, scratch, 1);
+    w.sync();
     return idx;
 }
 
@@ -385,114 +426,160 @@ SPL_D int mcts_pick(const W& w, const MctsEdge* ed, int k, int Ns, float Qs, con
     return best_i;
 }
 
-// backup along the recorded path (:168-177). v = value vector in the frame of the node below the last edge;
-// executed by lane 0 only. np.roll(v, next_player) with next_player = 1 after every in-tree move.
+// backup along the recorded path (:168-177). v = value vector in the frame of the node below the last edge (the same in
+// every lane). np.roll(v, next_player) with next_player = 1 after every in-tree move, so the edge at depth d sees the
+// vector rolled (depth - d) times and uses its component 0 = v[(d - depth) mod N]. A path never holds a node or an edge
+// twice (the ply grows along it), so the levels are independent: one lane per level.
 template <int N>
-SPL_D void mcts_backup(const MctsArena& A, int t, int depth, float* v) {
+SPL_D float mcts_vsel(const float* v, int i) {
+    float r = v[0];
+#pragma unroll
+    for (int j = 1; j < N; j++) r = i == j ? v[j] : r;
+    return r;
+}
+template <int N, class W>
+SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const float* v) {
     MctsNode* nodes = A.nodes + (size_t)t * A.cap;
     MctsEdge* edges = A.edges + (size_t)t * A.ecap;
     const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-    for (int d = depth - 1; d >= 0; d--) {
-        float r[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) r[(i + 1) % N] = v[i];
-#pragma unroll
-        for (int i = 0; i < N; i++) v[i] = r[i];
+    for (int d = w.lane; d < depth; d += W::W) {
+        const float v0 = mcts_vsel<N>(v, ((d - depth) % N + N) % N);
         MctsNode* nd = nodes + path[2 * d];
         MctsEdge* e = edges + path[2 * d + 1];
-        e->Q = MC_DDIV(MC_DADD(MC_DMUL((double)e->N, e->Q), (double)v[0]), (double)(e->N + 1));                               // :171
-        nd->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nd->u.x.Ns + 1), nd->u.x.Qs), v[0]), (float)(nd->u.x.Ns + 2));          // :172
+        e->Q = MC_DDIV(MC_DADD(MC_DMUL((double)e->N, e->Q), (double)v0), (double)(e->N + 1));                               // :171
+        nd->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nd->u.x.Ns + 1), nd->u.x.Qs), v0), (float)(nd->u.x.Ns + 2));          // :172
         e->N += 1;
         nd->u.x.Ns += 1;
     }
-    MctsTree* T = A.trees + t;
+    if (w.lane == 0) {
+        MctsTree* T = A.trees + t;
 #pragma unroll
-    for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? v[i] : 0.f;
-    T->depth_sum += depth;
+        for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? mcts_vsel<N>(v, ((i - depth) % N + N) % N) : 0.f;
+        T->depth_sum += depth;
+    }
+}
+
+// hands a node that waits for the network to the leaf row of its tree (:136-138)
+template <int N, class W>
+SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid) {
+    typedef MctsLay<N> ML;
+    MctsTree* T = A.trees + t;
+    const MctsNode* nd = A.nodes + (size_t)t * A.cap + node;
+    const int8_t* src = A.states + ((size_t)t * A.cap + node) * A.sp;
+    for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
+    for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
+    w.sync();
+    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+    for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
+    if (w.lane == 0) { T->leaf = node; T->path_len = depth; T->sims_done = sims_done; T->cur = -1; T->pend_edge = -1; }
+    w.sync();
 }
 
 // ------------------------------------------------------------------------------------------
-// selection: runs simulations of tree t until one reaches a node that needs the network (its state and legal
-// mask are written to the leaf row and 1 is returned) or the move's budget is spent (returns 0).
-// Simulations that end in a terminal node are backed up on the spot.
-// st: per-warp scratch of MctsLay<N>::SP bytes (16-aligned); scratch: 16 uint32; dscratch: 4 doubles
+// descent (light: no rules code): runs simulations of tree t until one
+//   * reaches a node that waits for the network  -> leaf row written, returns 1
+//   * reaches an edge that was never taken       -> records it as pending (the rules kernel computes the child state,
+//                                                    mcts_attach_tree links it), returns 2
+//   * or the move's budget is spent              -> returns 0
+// Simulations that end in a terminal node are backed up on the spot, at most `max_terminal` of them per call (then 3 is
+// returned and the next call carries on): near the end of a game almost every simulation is such a one, and a single
+// tree working through its whole budget would hold up the wave. Trees with a leaf or a pending edge are skipped.
 // ------------------------------------------------------------------------------------------
 template <int N, class W>
-SPL_D int mcts_select_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint32_t* scratch, double* dscratch,
-                           const double* dir, int8_t* leaf_state, uint8_t* leaf_valid) {
-    typedef MctsLay<N> ML;
+SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int max_terminal, int8_t* leaf_state,
+                            uint8_t* leaf_valid) {
     MctsTree* T = A.trees + t;
+    if (T->leaf >= 0) return 1;
+    if (T->pend_edge >= 0) return 2;
+    if (T->status != 0u) return 0;
     MctsNode* nodes = A.nodes + (size_t)t * A.cap;
     MctsEdge* edges = A.edges + (size_t)t * A.ecap;
     uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-    if (T->leaf >= 0) {   // the previous leaf was never expanded
-        if (w.lane == 0) T->status |= MCTS_S_PROTOCOL;
-        w.sync();
-        return 0;
-    }
     int sims_done = T->sims_done;
     const int target = T->sims_target;
     const uint32_t flags = T->flags;
     const int root = T->root;
-    while (sims_done < target && T->status == 0u) {
-        int cur = root, depth = 0;
-        bool aborted = false;
+    int cur = T->cur, depth = cur >= 0 ? T->path_len : 0;
+    if (cur < 0) cur = root;
+    while (sims_done < target) {
         for (;;) {
-            MctsNode* nd = nodes + cur;
+            const MctsNode* nd = nodes + cur;
             const int kind = nd->kind;
-            if (kind == MCTS_NODE_NEEDS_NN) {   // hand the position to the network (:136-138)
-                const int8_t* src = A.states + ((size_t)t * A.cap + cur) * A.sp;
-                for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
-                for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
-                w.sync();
-                const MctsEdge* ed = edges + nd->edge_off;
-                for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
-                if (w.lane == 0) { T->leaf = cur; T->path_len = depth; T->sims_done = sims_done; }
-                w.sync();
+            if (kind == MCTS_NODE_NEEDS_NN) {
+                mcts_emit_leaf<N>(w, A, t, cur, depth, sims_done, leaf_state, leaf_valid);
                 return 1;
             }
             if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
-            MctsEdge* ed = edges + nd->edge_off;
-            const int k = nd->n_edges;
-            if (depth == 0 && sims_done == 0 && (flags & MCTS_F_NOISE))   // revisited root, first simulation of a full search :150-154
-                mcts_root_noise(w, ed, k, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
-            const int ei = mcts_pick(w, ed, k, nd->u.x.Ns, nd->u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
+            const MctsEdge* ed = edges + nd->edge_off;
+            const int ei = mcts_pick(w, ed, (int)nd->n_edges, nd->u.x.Ns, nd->u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
             if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd->edge_off + (uint32_t)ei; }
             depth++;
-            MctsEdge* e = ed + ei;
-            uint32_t child = e->child;
-            if (child == 0u) {   // first traversal of this edge: make_move(a, 0, deterministic) + swap_players (:226-235)
-                mcts_copy16(w, st, A.states + ((size_t)t * A.cap + cur) * A.sp, A.sp);
-                w.sync();
+            const uint32_t child = ed[ei].child;
+            if (child == 0u) {   // first traversal of this edge
                 if (w.lane == 0) {
-                    AosAcc s{st};
-                    SplChance ch;
-                    ch.mode = 0; ch.code = 0; ch.seed = 0; ch.game = 0; ch.episode = 0; ch.ply = 0;
-                    const int nxt = spl_apply_move<N>(s, (int)e->action, 0, ch);
-                    if (nxt > 0) spl_rotate<N>(s, nxt, P.rules);
+                    T->pend_edge = (int32_t)(nd->edge_off + (uint32_t)ei); T->pend_parent = cur;
+                    T->path_len = depth; T->sims_done = sims_done; T->cur = -1;
                 }
                 w.sync();
-                const uint64_t h = mcts_hash(w, st, A.sp);
-                int idx = mcts_lookup(w, A, t, st, h);   // transposition: the dictionary may already hold this state
-                if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
-                if (idx < 0) { aborted = true; break; }
-                child = (uint32_t)idx + 1u;
-                if (w.lane == 0) e->child = child;
-                w.sync();
+                return 2;
             }
             cur = (int)child - 1;
         }
-        if (aborted) break;
-        if (w.lane == 0) {   // terminal: return Es up the path
+        {   // terminal: return Es up the path
             float v[N];
 #pragma unroll
             for (int i = 0; i < N; i++) v[i] = nodes[cur].u.es[i];
-            mcts_backup<N>(A, t, depth, v);
+            mcts_backup<N>(w, A, t, depth, v);
         }
         w.sync();
         sims_done++;
+        cur = root; depth = 0;
+        if (--max_terminal <= 0 && sims_done < target) {
+            if (w.lane == 0) { T->sims_done = sims_done; T->cur = -1; T->path_len = 0; }
+            w.sync();
+            return 3;
+        }
     }
-    if (w.lane == 0) T->sims_done = sims_done;
+    if (w.lane == 0) { T->sims_done = sims_done; T->cur = -1; T->path_len = 0; }
+    w.sync();
+    return 0;
+}
+
+// attaches the child state computed for the pending edge: st = its bytes (sp, zero padded, 16-aligned), ended / es /
+// mask from mcts_rules_core. The dictionary may already hold the state (transposition, :120): then the descent goes on
+// from that node in the next mcts_descend_tree call. Returns 1 if a leaf row was written, 0 otherwise.
+template <int N, class W>
+SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* st, bool ended, const float* es,
+                           const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid) {
+    MctsTree* T = A.trees + t;
+    const int pe = T->pend_edge;
+    if (pe < 0) return T->leaf >= 0 ? 1 : 0;
+    const uint64_t h = mcts_hash(w, st, A.sp);
+    int idx = mcts_lookup(w, A, t, st, h);
+    if (idx < 0) idx = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
+    if (idx < 0) {   // pool overflow: the search of this tree stops here (status bit set)
+        if (w.lane == 0) { T->pend_edge = -1; T->cur = -1; T->path_len = 0; }
+        w.sync();
+        return 0;
+    }
+    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    if (w.lane == 0) A.edges[(size_t)t * A.ecap + pe].child = (uint32_t)idx + 1u;
+    w.sync();
+    const int kind = nodes[idx].kind;
+    const int depth = T->path_len, sims_done = T->sims_done;
+    if (kind == MCTS_NODE_NEEDS_NN) {
+        mcts_emit_leaf<N>(w, A, t, idx, depth, sims_done, leaf_state, leaf_valid);
+        return 1;
+    }
+    if (kind == MCTS_NODE_TERMINAL) {
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = nodes[idx].u.es[i];
+        mcts_backup<N>(w, A, t, depth, v);
+        if (w.lane == 0) { T->sims_done = sims_done + 1; T->pend_edge = -1; T->cur = -1; T->path_len = 0; }
+    } else {   // an expanded node reached through a new edge: keep descending from it
+        if (w.lane == 0) { T->pend_edge = -1; T->cur = idx; }
+    }
     w.sync();
     return 0;
 }
@@ -522,16 +609,20 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
         for (int i = w.lane; i < k; i += W::W) ed[i].P = MC_FDIV(ed[i].P, s);
         w.sync();
     }
-    if (w.lane == 0) {
-        float v[N];
+    float v[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = vin[i];
+    for (int i = 0; i < N; i++) v[i] = vin[i];
+    if (w.lane == 0) {
         nd->u.x.Ns = 0;
         nd->u.x.Qs = v[0];   // :147
         nd->kind = MCTS_NODE_EXPANDED;
-        mcts_backup<N>(A, t, T->path_len, v);
+    }
+    w.sync();
+    mcts_backup<N>(w, A, t, T->path_len, v);
+    w.sync();
+    if (w.lane == 0) {
         T->sims_done += 1;
-        T->leaf = -1;
+        T->leaf = -1; T->cur = -1; T->pend_edge = -1; T->path_len = 0;
         T->nn_calls += 1;
     }
     w.sync();
@@ -661,7 +752,7 @@ SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_a
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
         T->n_nodes = 0; T->n_edges = 0; T->root = -1; T->leaf = -1; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
-        T->flags = 0u; T->status = 0u; T->depth_sum = 0;
+        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
     }
     w.sync();
 }
@@ -672,7 +763,7 @@ SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_a
 // not-yet-linked edge transposes into is re-created instead of found, which the reference's dictionary would not do).
 template <int N, class W>
 SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* root_state, int sims_target,
-                           uint32_t flags, int edge_reserve, int gc_reachable, int8_t* st, uint32_t* scratch) {
+                           uint32_t flags, int edge_reserve, int gc_reachable, const double* dir, int8_t* st, uint32_t* scratch, double* dscratch) {
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
     for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
@@ -718,9 +809,16 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
     if (w.lane == 0) {
         T->root = idx; T->leaf = -1; T->sims_done = 0; T->sims_target = idx < 0 ? 0 : sims_target; T->path_len = 0;
-        T->flags = flags; T->depth_sum = 0;
+        T->flags = flags; T->depth_sum = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
     }
     w.sync();
+    // a root the tree already expanded gets the noise on its stored Ps before the first simulation picks (:150-154);
+    // a new root gets it when its network row arrives (mcts_expand_tree)
+    if (idx >= 0 && sims_target > 0 && (flags & MCTS_F_NOISE)) {
+        MctsNode* nd = A.nodes + (size_t)t * A.cap + idx;
+        if (nd->kind == MCTS_NODE_EXPANDED)
+            mcts_root_noise(w, A.edges + (size_t)t * A.ecap + nd->edge_off, (int)nd->n_edges, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

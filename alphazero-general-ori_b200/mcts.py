@@ -29,7 +29,7 @@ def _ptr(t):
 
 class MCTSArena:
     def __init__(self, n_players, n_trees, node_cap, edge_cap=None, device=0, cpuct=1.0, fpu=0.0, temperature0=1.0,
-                 dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, token_limit=10,
+                 dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, rounds=1, token_limit=10,
                  rule_flags=nat.RULES_DEFAULT):
         if not torch.cuda.is_available():
             raise RuntimeError("MCTSArena needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -56,7 +56,7 @@ class MCTSArena:
         self._m = m
         self.arena_bytes = nbytes
         self.params = dict(cpuct=cpuct, fpu=fpu, temperature0=temperature0, dirichlet_alpha=dirichlet_alpha, seed=seed,
-                           game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)))
+                           game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds))
         self.set_params()
         self.launches = 0
         self.reset()
@@ -87,24 +87,33 @@ class MCTSArena:
         nat.check(self._lib.spl_mcts_reset(self._m, _ptr(tree_select), self._stream()))
         self.launches += 1
 
-    def begin(self, roots, sims, move_flags=None, tree_select=None):
-        """roots int8[T,R,7] canonical boards (device), sims int32[T], move_flags uint8[T] (MCTS_MOVE_FORCED | MCTS_MOVE_NOISE)"""
+    def begin(self, roots, sims, move_flags=None, tree_select=None, dir_values=None):
+        """roots int8[T,R,7] canonical boards (device), sims int32[T], move_flags uint8[T] (MCTS_MOVE_FORCED | MCTS_MOVE_NOISE),
+        dir_values float64[T,406] (the Dirichlet vector per root, parity runs) or None (on-device Philox sampler)"""
         assert roots.dtype == torch.int8 and roots.is_cuda and roots.is_contiguous() and roots.numel() == self.T * self.S
         assert sims.dtype == torch.int32 and sims.numel() == self.T
-        self._hold = (roots, sims, move_flags, tree_select)
-        nat.check(self._lib.spl_mcts_begin(self._m, _ptr(roots), _ptr(sims), _ptr(move_flags), _ptr(tree_select), self._stream()))
+        self._hold = (roots, sims, move_flags, tree_select, dir_values)
+        nat.check(self._lib.spl_mcts_begin(self._m, _ptr(roots), _ptr(sims), _ptr(move_flags), _ptr(tree_select), _ptr(dir_values),
+                                           self._stream()))
         self.launches += 1
 
-    def select(self, dir_values=None, count=False):
-        nat.check(self._lib.spl_mcts_select(self._m, _ptr(dir_values), _ptr(self.leaf_states), _ptr(self.leaf_valids),
-                                            _ptr(self.leaf_flags), _ptr(self.counters) if count else None, self._stream()))
-        self.launches += 1
+    def select(self, count=False):
+        """one selection wave (`rounds` x (descend, rules, attach) kernels)"""
+        nat.check(self._lib.spl_mcts_select(self._m, _ptr(self.leaf_states), _ptr(self.leaf_valids), _ptr(self.leaf_flags),
+                                            _ptr(self.counters) if count else None, self._stream()))
+        self.launches += 3 * self.params["rounds"]
 
     def expand(self, pi, v, dir_values=None):
         assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.numel() == self.T * nat.NUM_ACTIONS
         assert v.dtype == torch.float32 and v.is_contiguous() and v.numel() == self.T * self.n
         nat.check(self._lib.spl_mcts_expand(self._m, _ptr(pi), _ptr(v), _ptr(dir_values), self._stream()))
         self.launches += 1
+
+    def remaining(self):
+        """one (leaf-less) selection wave that counts the trees whose budget is not spent yet -> int (host sync)"""
+        self.counters.zero_()
+        self.select(count=True)
+        return int(self.counters[1].item())
 
     def fixed_net(self, states=None, valids=None, pi=None, v=None):
         """the deterministic stand-in network (exact dyadic outputs) on device rows"""
@@ -121,16 +130,42 @@ class MCTSArena:
 
     def search(self, roots, sims, evaluator, move_flags=None, dir_values=None, tree_select=None, waves=None):
         """one getActionProb for every tree: `evaluator(leaf_states, leaf_valids) -> (pi float32[T,406], v float32[T,n])`
-        on the device. Runs max(sims) waves (every wave finishes at least one simulation of every unfinished tree), with
-        no host synchronisation inside."""
-        self.begin(roots, sims, move_flags, tree_select)
+        on the device. Runs max(sims) waves without host synchronisation (every wave finishes one simulation of nearly
+        every unfinished tree), then keeps going until no tree has budget left (descents that crossed several
+        transpositions or terminal nodes need an extra wave)."""
+        self.begin(roots, sims, move_flags, tree_select, dir_values)
         if waves is None:
             waves = int(sims.max().item())
         for _ in range(waves):
-            self.select(dir_values)
+            self.wave(evaluator, dir_values)
+        self.finish(evaluator, dir_values)
+
+    def wave(self, evaluator, dir_values=None):
+        self.select()
+        pi, v = evaluator(self.leaf_states, self.leaf_valids)
+        self.expand(pi, v, dir_values)
+
+    def finish(self, evaluator, dir_values=None, chunk=None, max_extra=100000):
+        """waves until every tree has spent its budget. One host synchronisation per `chunk()` call (default: 8 waves);
+        returns the number of extra waves."""
+        extra = 0
+        while True:
+            self.counters.zero_()
+            self.select(count=True)
+            left = int(self.counters[1].item())
+            if left == 0:
+                return extra
             pi, v = evaluator(self.leaf_states, self.leaf_valids)
             self.expand(pi, v, dir_values)
-        self.select(dir_values)   # drains simulations that end in terminal nodes; emits no leaf once the budgets are spent
+            extra += 1
+            if chunk is not None:
+                extra += chunk()
+            else:
+                for _ in range(7):
+                    self.wave(evaluator, dir_values)
+                extra += 7
+            if extra > max_extra:
+                raise nat.NativeError("MCTS arena: search does not terminate")
 
     def get_action_prob_batch(self, boards, sims, evaluator, temp=1.0, move_flags=None, out=None):
         """MCTS.getActionProb for T games with HOST buffers: boards int8[T,R,7] (numpy / pinned tensor) in,
@@ -251,11 +286,15 @@ class MCTS:
             d[:k] = self.rng.dirichlet([self.args.dirichletAlpha] * k)
             self._dir.copy_(torch.from_numpy(d).view(1, -1))
             dirv = self._dir
-        ar.begin(self._root, self._sims, self._flags)
+        ar.begin(self._root, self._sims, self._flags, None, dirv)
         while True:
-            ar.select(dirv)
-            if int(ar.leaf_flags[0].item()) == 0:
+            ar.counters.zero_()
+            ar.select(count=True)
+            has_leaf, left = [int(x) for x in ar.counters.cpu()]
+            if left == 0:
                 break
+            if not has_leaf:
+                continue
             board = ar.leaf_states[0].cpu().numpy()
             valids = ar.leaf_valids[0].cpu().numpy().astype(np.bool_)
             if self.batch_info is None:

@@ -22,7 +22,7 @@ from .mcts import MCTSArena
 class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
-                 temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0):
+                 temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -32,7 +32,7 @@ class SelfPlayEngine:
         node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
         self.arena = MCTSArena(n_players, n_games, node_cap, edge_cap, device=device, cpuct=cpuct, fpu=fpu, temperature0=temperature0,
                                dirichlet_alpha=dirichlet_alpha, seed=seed, game_base=game_base, edge_reserve=edge_reserve,
-                               gc_reachable=gc_reachable)
+                               gc_reachable=gc_reachable, rounds=rounds)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed) * 1000003 + int(game_base))
         self.sims = torch.empty(n_games, dtype=torch.int32, device=self.device)
@@ -43,14 +43,12 @@ class SelfPlayEngine:
         self._graph = None
         self.env.reset()
         self.moves = 0
+        self.extra_waves = 0
         self.sims_total = torch.zeros((), dtype=torch.int64, device=self.device)   # simulations requested so far
 
     # ------------------------------------------------------------------
     def _wave(self):
-        ar = self.arena
-        ar.select(None)
-        pi, v = self.evaluator(ar.leaf_states, ar.leaf_valids)
-        ar.expand(pi, v, None)
+        self.arena.wave(self.evaluator)
 
     def _run_waves(self, waves):
         if self.graph_waves <= 0:
@@ -91,7 +89,12 @@ class SelfPlayEngine:
             self._run_waves(0)
             self.arena.begin(self.roots, self.sims, self.flags)
         self._run_waves(max_sims)
-        self.arena.select(None)   # drain simulations ending in terminal nodes
+        chunk = None
+        if self.graph_waves > 0:
+            def chunk():
+                self._graph.replay()
+                return self.graph_waves
+        self.extra_waves += self.arena.finish(self.evaluator, chunk=chunk)   # stragglers (descents that crossed transpositions / terminal nodes)
         probs, q = self.arena.policy(temp)
         return probs, q, is_full
 

@@ -43,10 +43,11 @@ def parse():
     # MCTS (configs[1])
     ap.add_argument("--trees", type=int, default=4096, help="parallel games (trees) per GPU")
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
-    ap.add_argument("--nn-dtype", default="fp32", choices=["fp32", "bf16", "fused"],
+    ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
     ap.add_argument("--graph-waves", type=int, default=16, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="ply", choices=["ply", "reachable"])
+    ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
@@ -265,7 +266,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     reach = args.gc == "reachable"
     cap = args.node_cap or (3 if reach else 8) * sims
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
-                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves)
+                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
         eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
@@ -302,7 +303,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     truncated_now = int((st["sims_done"] < sims).sum())
     value = world * sims_done / (ms_total * 1e-3)
     waves_per_step = -(-sims // args.graph_waves) * args.graph_waves if args.graph_waves > 0 else sims
-    own_launches_total = args.steps * (waves_per_step * 2 + 8)
+    own_launches_total = args.steps * (waves_per_step * (3 * args.rounds + 1 + (0 if nn_launches is None and args.nn_dtype != "fused" else 1)) + 16)
 
     # ---- kernel breakdown of one wave, measured live with CUDA events on plain (non-graph) launches
     ar = eng.arena
@@ -311,7 +312,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     nb = 200
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nb)]
     for i in range(nb):
-        evs[i][0].record(); ar.select(None)
+        evs[i][0].record(); ar.select()
         evs[i][1].record(); pi, v = eng.evaluator(ar.leaf_states, ar.leaf_valids)
         evs[i][2].record(); ar.expand(pi, v, None)
         evs[i][3].record()
@@ -323,11 +324,11 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "mcts_select_kernel", "avg_launch_ms": sel,
+                "kernel": "selection wave (mcts_descend_kernel + mcts_rules_kernel + mcts_attach_kernel)", "avg_launch_ms": sel,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_sim": B_SIM[n],
                 "note": "one launch = one simulation of every tree; the search is bound by the latency of sequential waves, not bytes",
-                "wave_breakdown_ms": {"mcts_select_kernel": sel, "network_forward": nnt, "mcts_expand_kernel": exp}}
+                "wave_breakdown_ms": {"selection (descend+rules+attach kernels x rounds)": sel, "network_forward": nnt, "mcts_expand_kernel": exp}}
 
     line = {
         "metric": METRIC_MCTS, "value": value, "unit": UNIT_MCTS, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -335,7 +336,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
-                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "opening_plies": args.opening_plies,
+                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,

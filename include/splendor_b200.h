@@ -183,6 +183,8 @@ typedef struct {
     int      edge_reserve;      /* edges budgeted per new node when deciding whether to clean before a move (default 32) */
     int      gc_reachable;      /* 0: cleaning keeps every node with ply >= root ply - result-neutral, like the reference's
                                    own cleaning :80-85 (default); 1: keeps only what the new root reaches (smaller pools) */
+    int      rounds;            /* (descend, rules, attach) passes per selection wave (default 1): a descent that runs into
+                                   a transposition or a terminal node continues in the next pass / wave; result-neutral */
 } spl_mcts_params;
 
 /* bytes of device memory an arena needs; node_cap / edge_cap are per tree */
@@ -196,13 +198,16 @@ int  spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream);
 /* start of getActionProb for every (selected) tree: roots int8[T][R*7] canonical boards, sims int32[T] simulation budget
  * (numMCTSSims or numMCTSSims // ratio_fullMCTS, :55), move_flags uint8[T] of SPL_MCTS_MOVE_* */
 int  spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const uint8_t* move_flags, const uint8_t* tree_select,
-                    void* stream);
-/* one selection wave. Outputs per tree: leaf_states int8[T][R*7], leaf_valids uint8[T][406] (getValidMoves of the leaf),
- * leaf_flags uint8[T] (1: this row needs the network). dir_values (may be NULL): double[T][406], the vector
- * rng.dirichlet would return for the tree's root, one value per legal action in action order.
+                    const double* dir_values, void* stream);
+/* dir_values of spl_mcts_begin / spl_mcts_expand (may be NULL): double[T][406], the vector rng.dirichlet would return for
+ * the tree's root, one value per legal action in action order (parity runs); NULL = the on-device Philox sampler.
+ *
+ * one selection wave = `rounds` x (descend, rules, attach) kernels. Outputs per tree: leaf_states int8[T][R*7],
+ * leaf_valids uint8[T][406] (getValidMoves of the leaf), leaf_flags uint8[T] (1: this row needs the network).
+ * A tree finishes at most one simulation per wave and may need an extra wave when a descent crosses several
+ * transpositions / terminal nodes: run waves until counters[1] stays 0.
  * counters (may be NULL): int32[2], [0] += rows that need the network, [1] += trees whose budget is not yet spent. */
-int  spl_mcts_select(spl_mcts* m, const double* dir_values, int8_t* leaf_states, uint8_t* leaf_valids, uint8_t* leaf_flags,
-                     int32_t* counters, void* stream);
+int  spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
 /* pi float[T][406] = the network's probabilities (exp of the masked log-softmax, GenericNNetWrapper.py:166), v float[T][n] */
 int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double* dir_values, void* stream);
 /* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */

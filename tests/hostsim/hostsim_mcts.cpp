@@ -18,6 +18,14 @@ struct HsMcts {
     float *pi, *v;
 };
 
+template <int N>
+static void hm_step_rules(HsMcts* m, int8_t* st, bool* ended, float* es, uint32_t* mask) {
+    const MctsTree& T = m->A.trees[0];
+    memcpy(st, m->A.states + (size_t)T.pend_parent * m->A.sp, m->A.sp);
+    AosAcc s{st};
+    *ended = mcts_rules_core<N>(s, (int)m->A.edges[T.pend_edge].action, m->P.rules, es, mask);
+}
+
 extern "C" {
 HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, double cpuct, double fpu, double temperature0, int edge_reserve, int gc_reachable) {
     HsMcts* m = (HsMcts*)calloc(1, sizeof *m);
@@ -52,17 +60,26 @@ void hm_reset(HsMcts* m) {
     mcts_clear_tree(w, m->A, 0);
     m->A.trees[0].nn_calls = 0;
 }
-// one getActionProb: begin + (select, fixed network, expand) until the budget is spent. Returns the tree status bits.
+// one getActionProb: begin + (descend, [rules, attach], fixed network, expand) until the budget is spent - the same
+// sequence of steps the wave kernels run. Returns the tree status bits.
 int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const double* dir) {
     MctsWarp w{0};
     alignas(16) int8_t st[640];
-    uint32_t scratch[16];
+    uint32_t scratch[24];
     double dscratch[4];
-    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->edge_reserve, m->gc_reachable, st, scratch));
+    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->edge_reserve, m->gc_reachable, dir, st, scratch, dscratch));
     for (;;) {
-        int leaf = 0;
-        DISPATCH(m->n, leaf = mcts_select_tree<N>(w, m->A, 0, m->P, st, scratch, dscratch, dir, m->leaf_state, m->leaf_valid));
-        if (!leaf) break;
+        int r = 0;
+        DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, m->leaf_state, m->leaf_valid));
+        if (r == 0) break;
+        if (r == 3) continue;
+        if (r == 2) {
+            bool ended = false; float es[4] = {0, 0, 0, 0}; uint32_t mask[13];
+            memset(st, 0, sizeof st);
+            DISPATCH(m->n, hm_step_rules<N>(m, st, &ended, es, mask));
+            DISPATCH(m->n, r = mcts_attach_tree<N>(w, m->A, 0, m->P, st, ended, es, mask, 1, m->leaf_state, m->leaf_valid));
+            if (r == 0) continue;
+        }
         DISPATCH(m->n, mcts_fixed_net_row<N>(w, m->leaf_state, m->leaf_valid, m->pi, m->v, scratch));
         DISPATCH(m->n, mcts_expand_tree<N>(w, m->A, 0, m->P, m->pi, m->v, dir, dscratch));
     }
