@@ -16,13 +16,15 @@ import torch
 
 from . import _native as nat
 from .engine import SplendorEnv
+from .examples import ExampleBuffer, expand_symmetries
 from .mcts import MCTSArena
 
 
 class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
-                 temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1):
+                 temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
+                 record_examples=False):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -42,8 +44,10 @@ class SelfPlayEngine:
         self.graph_waves = int(graph_waves)
         self._graph = None
         self.env.reset()
+        self.examples = ExampleBuffer(n_players, n_games, self.env.R, self.device) if record_examples else None
         self.moves = 0
         self.extra_waves = 0
+        self.games_finished = torch.zeros((), dtype=torch.int64, device=self.device)
         self.sims_total = torch.zeros((), dtype=torch.int64, device=self.device)   # simulations requested so far
 
     # ------------------------------------------------------------------
@@ -104,8 +108,24 @@ class SelfPlayEngine:
         probs, q, is_full = self.search(temp)
         a = torch.multinomial(probs.to(torch.float32), 1, generator=self.gen).view(-1)
         self.actions.copy_(a.to(torch.int16))
-        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=True, want_mask=False, want_status=False, count=True)
-        done = (self.env.ended != 0).any(dim=1).to(torch.uint8)
-        self.arena.reset(done)
+        if self.examples is not None:   # Coach.py:76-80: the position, its policy target and legal mask, before the move
+            self.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
+            self.examples.record(self.roots, probs, self.env.valids(), q, is_full)
+        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+        ended = self.env.ended
+        done = (ended != 0).any(dim=1)
+        if self.examples is not None:
+            scores, _ = self.env.scores()
+            self.examples.advance(ended, scores)
+        done8 = done.to(torch.uint8)
+        self.env.episodes += done.to(torch.int32)      # finished lanes start their next game (Philox key: game id, episode)
+        self.env.reset(done8)
+        self.arena.reset(done8)                        # MCTS.reset_all_search_trees after every episode (Coach.py:122)
+        self.games_finished += done.sum()
         self.moves += 1
-        return probs, q, is_full, self.env.ended
+        return probs, q, is_full, ended
+
+    def drain_examples(self, symmetries=True):
+        """finished-game examples so far as device tensors (examples.FIELDS); with their symmetric variants (Coach.py:77-80)"""
+        ex = self.examples.drain()
+        return expand_symmetries(self.env, ex) if symmetries else ex

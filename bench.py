@@ -342,7 +342,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
                        "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(st["sims_done"].sum())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
-                       "games_finished": int(eng.env.counters[0].item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, int(eng.sims_total.item()))},
+                       "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, int(eng.sims_total.item()))},
     }
     if rank == 0:
         line["clocks"] = clk.summary()

@@ -241,3 +241,39 @@ def test_fused_network_kernel(golden_dir, n):
         assert np.array_equal(_np(p2), pi[:B]) and np.array_equal(_np(v2), v[:B])
     p1, v1 = net.predict(g["state"][5], g["valids"][5])
     assert np.array_equal(p1, pi[5]) and np.array_equal(v1, v[5])
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_selfplay_examples_like_coach(n):
+    """batched self-play with example recording, driven until games finish; every recorded example is checked against the
+    rules oracle (legal mask of its board, policy on legal moves only) and against Coach's end-of-game bookkeeping:
+    the winner / score-difference vectors are the final result seen from the example's mover."""
+    az = _azg()
+    from oracle import pyoracle as po
+    T, sims = 96, 12
+    eng = az.SelfPlayEngine(n, T, None, sims, seed=5, cpuct=1.0, node_cap=512, prob_full=0.6, ratio_full=3, record_examples=True)
+    eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v)
+    eng.env.rollout(50 * n - 20, rotate=True)                 # late positions: games end within a few dozen moves
+    eng.arena.reset(); eng.examples.cur_player.zero_()        # (seat labels restart here; only relative seats matter)
+    finished = 0
+    for mv in range(60):
+        probs, q, is_full, ended = eng.play_move()
+        finished = int(eng.games_finished.item())
+        if finished >= 20 and mv >= 25:
+            break
+    assert finished >= 5
+    ex = eng.drain_examples(symmetries=False)
+    E = ex["board"].shape[0]
+    assert E > 0
+    boards, pi, winner, scdiff, valids = [_np(ex[k]) for k in ("board", "pi", "winner", "scdiff", "valids")]
+    for e in range(E):
+        b = po.Board(n).set_state(boards[e])
+        assert np.array_equal(b.valid_moves(0), valids[e].astype(bool))
+        assert abs(pi[e].sum() - 1.0) < 1e-5 and (pi[e][~valids[e].astype(bool)] == 0).all()
+        assert scdiff[e][0] == 0 and set(np.unique(winner[e])) <= {1.0, -1.0, np.float32(0.01)}
+        assert (winner[e] == 1.0).sum() + (winner[e] == np.float32(0.01)).sum() >= 1
+    exs = eng.examples   # symmetric variants: identity first, counts per example in 10..1+9+2n
+    ex2 = az.examples.expand_symmetries(eng.env, ex)
+    assert ex2["board"].shape[0] >= 10 * E and ex2["board"].shape[0] <= (10 + 2 * n) * E
+    lst = az.examples.to_coach_format(ex, compress=True)
+    assert len(lst) == E
