@@ -792,6 +792,17 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
             }
         } else {
             mcts_compact(w, A, t, root_ply, false);
+            if (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
+                // the exact cleaning did not free enough: fall back to the reachable set of the new root (counted as lossy:
+                // nodes that only a not-yet-linked edge could transpose into are dropped)
+                const int old_root = mcts_lookup(w, A, t, st, h);
+                if (old_root >= 0) {
+                    mcts_mark_reachable(w, A, t, old_root);
+                    mcts_compact(w, A, t, 0, true);
+                    if (w.lane == 0) T->resets += 1;
+                    w.sync();
+                }
+            }
         }
         if (!cleared && (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap)) {   // still no room: forget the tree (counted)
             const int resets = T->resets;

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
+    ap.add_argument("--wide-trees", type=int, default=65536, help="second MCTS point: this many games per GPU (0: skip)")
+    ap.add_argument("--wide-sims", type=int, default=64, help="simulations per move of the second MCTS point")
     # env (configs[4])
     ap.add_argument("--lanes", type=int, default=1 << 20, help="game lanes per GPU")
     ap.add_argument("--plies", type=int, default=16, help="plies per lane per launch (rollout mode)")
@@ -179,10 +181,10 @@ def run_reference(args):
     else:
         # step = one move (getActionProb) per worker; bounded: sims per move scaled so that K+W moves stay within minutes
         sims = min(args.sims, 400)
-        moves = max(1, args.steps)
+        moves = max(1, args.steps) * 10            # a step of this arm = 10 moves per worker (about 1 s of CPU work)
         rate, cores, tot, tdt = cpu_mcts(n, sims, moves, args.seed, args.fixed_net)
         value, metric, unit, wl = rate, METRIC_MCTS, UNIT_MCTS, workload_mcts(args)
-        sample = (f"{cores} processes x {moves} moves x {sims} sims/move = {tot} simulations (C port of MCTS.py + per-leaf torch-CPU "
+        sample = (f"{cores} processes x {moves} moves ({args.steps} steps of 10 moves) x {sims} sims/move = {tot} simulations (C port of MCTS.py + per-leaf torch-CPU "
                   f"float32 SplendorNNet predict, 1 thread each; {sims} instead of {args.sims} sims/move to bound the run)")
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
@@ -373,6 +375,37 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     return line, eng
 
 
+def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """the "64k games" point of the BASELINE metric: many more trees than configs[1], a short budget per move so that the
+    arena fits (tree pools scale with the budget), same kernels, same network"""
+    n, T, sims = args.players, args.wide_trees, args.wide_sims
+    net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
+    cap = 8 * sims
+    eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
+                             graph_waves=args.graph_waves, rounds=args.rounds)
+    eng.env.rollout(args.opening_plies, rotate=True)
+    for _ in range(3):
+        eng.play_move()
+    barrier()
+    s0 = int(eng.sims_total.item())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        eng.play_move()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    done = int(eng.sims_total.item()) - s0
+    st = eng.arena.root_stats(want_arrays=False)
+    return {"value": world * done / (ms * 1e-3), "unit": UNIT_MCTS, "trees_per_gpu": T, "sims_per_move": sims, "steps": steps, "ms_per_step": ms / steps,
+            "arena_gb_per_gpu": eng.arena.arena_bytes / 1e9, "truncated_searches": int(st["truncated"].sum()), "lossy_resets": int(st["resets"].sum())}
+
+
 # ----------------------------------------------------------------------------------------------
 # env leg (configs[4])
 # ----------------------------------------------------------------------------------------------
@@ -511,6 +544,9 @@ def main():
         line, eng = bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier)
         del eng
         torch.cuda.empty_cache()
+        if args.wide_trees > 0:
+            line["mcts_wide"] = bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier)
+            torch.cuda.empty_cache()
     if args.workload in ("both", "env"):
         envres = bench_env(args, torch, dist, azg, world, rank, local, dev, barrier)
         if line is None:
@@ -526,9 +562,10 @@ def main():
         if not args.no_cpu:
             if line["metric"] == METRIC_MCTS:
                 sims_cpu = min(args.sims, 400)
-                rate, cores, tot, secs = cpu_mcts(n, sims_cpu, 3, args.seed, args.fixed_net)
+                cpu_moves = max(3, int(args.cpu_seconds * 4000 / sims_cpu))     # ~cpu_seconds of work per core at ~4k sims/s
+                rate, cores, tot, secs = cpu_mcts(n, sims_cpu, cpu_moves, args.seed, args.fixed_net)
                 line["cpu_baseline"] = {"value": rate, "unit": UNIT_MCTS, "cores": cores, "kind": "port",
-                                        "sample": f"{cores} processes x 3 moves x {sims_cpu} sims/move = {tot} simulations in {secs:.1f} s (C port of "
+                                        "sample": f"{cores} processes x {cpu_moves} moves x {sims_cpu} sims/move = {tot} simulations in {secs:.1f} s (C port of "
                                                   f"MCTS.py + per-leaf torch-CPU float32 SplendorNNet predict, one thread per core)"}
             if args.workload in ("both", "env"):
                 v, cores, games, plies, dtc = cpu_rollouts(n, args.seed, args.cpu_seconds)
