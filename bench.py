@@ -247,6 +247,13 @@ class Clocks:
                 "samples": len(s)}
 
 
+def load_traffic(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -325,7 +332,8 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    tr = load_traffic(f"mcts_wave_n{n}_bytes_per_sim")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None if tr is None else tr * T,
                 "kernel": "selection wave (mcts_descend_kernel + mcts_rules_kernel + mcts_attach_kernel)", "avg_launch_ms": sel,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_sim": B_SIM[n],
@@ -455,7 +463,8 @@ def bench_env(args, torch, dist, azg, world, rank, local, dev, barrier):
         "metric": METRIC_ENV, "value": value, "unit": UNIT_ENV, "steps": steps, "ms_per_step": ms_total / steps, "dtype": "int8",
         "config": {"workload": workload_env(args), "lanes_per_gpu": L, "plies_per_launch": P, "mode": args.mode, "burn_in_plies": args.burn_in,
                    "tma": not args.no_tma, "l2": f"inputs larger than L2: {L * env.S / 1e6:.0f} MB of lane tiles per GPU vs 126 MB L2"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (lambda tr: None if tr is None else tr * L * P)(load_traffic(f"{args.mode}_n{n}_bytes_per_lane_ply")),
                      "kernel": "spl_rollout_kernel" if args.mode == "rollout" else "spl_step_kernel",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                      "algorithmic_bytes_per_step": B_STEP[n], "avg_launch_ms": avg_ms},
