@@ -10,6 +10,7 @@ from .game import Board, SplendorGame, action_size, observation_size
 from .mcts import MCTS, MCTSArena
 from .nnet import FusedSplendorNNet, SplendorNNetB200
 from .selfplay import SelfPlayEngine
+from .arena import BatchedArena
 from . import examples, nnet
 
-__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "nnet", "examples", "observation_size", "action_size", "rows", "_native"]
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "BatchedArena", "nnet", "examples", "observation_size", "action_size", "rows", "_native"]

