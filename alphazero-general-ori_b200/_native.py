@@ -56,7 +56,7 @@ class RolloutArgs(C.Structure):
 class MctsParams(C.Structure):
     _fields_ = [
         ("cpuct", C.c_double), ("fpu", C.c_double), ("temperature0", C.c_double), ("dirichlet_alpha", C.c_double),
-        ("seed", C.c_uint64), ("game_base", C.c_uint32), ("edge_reserve", C.c_int), ("gc_reachable", C.c_int), ("rounds", C.c_int),
+        ("seed", C.c_uint64), ("game_base", C.c_uint32), ("edge_reserve", C.c_int), ("gc_reachable", C.c_int), ("rounds", C.c_int), ("max_levels", C.c_int),
     ]
 
 

@@ -21,7 +21,7 @@ struct spl_mcts {
     spl_ctx* ctx;
     MctsArena A;
     MctsSearchParams P;
-    int edge_reserve, gc_reachable, rounds;
+    int edge_reserve, gc_reachable, rounds, max_levels;
 };
 
 struct WarpScratch {
@@ -53,11 +53,12 @@ __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSe
 }
 
 template <int N>
-__global__ void __launch_bounds__(MW * 32, 8) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int8_t* leaf_states, uint8_t* leaf_valids) {
+__global__ void __launch_bounds__(MW * 32, 8) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int max_levels, int8_t* leaf_states,
+                                                                  uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
-    mcts_descend_tree<N>(w, A, t, P, 1, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+    mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
 }
 
 // shared-memory tile accessor of the rules kernel: cell (row, col) of this lane's tree = byte [(7 row + col) * 32 + lane]
@@ -251,7 +252,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     m->A.stage_ended = (uint8_t*)(base + p.off_sended);
     m->P.cpuct = 1.0; m->P.fpu = 0.0; m->P.temperature0 = 1.0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules = ctx->rules;
-    m->edge_reserve = 32; m->gc_reachable = 0; m->rounds = 1;
+    m->edge_reserve = 32; m->gc_reachable = 0; m->rounds = 1; m->max_levels = 1 << 20;
     *out = m;
     return SPL_OK;
 }
@@ -265,6 +266,7 @@ int spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p) {
     m->P.seed = p->seed; m->P.game_base = p->game_base;
     m->edge_reserve = p->edge_reserve; m->gc_reachable = p->gc_reachable ? 1 : 0;
     m->rounds = p->rounds < 1 ? 1 : (p->rounds > 8 ? 8 : p->rounds);
+    m->max_levels = p->max_levels < 1 ? (1 << 20) : p->max_levels;
     return SPL_OK;
 }
 
@@ -296,7 +298,7 @@ int spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint
         CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
-            mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids);
+            mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
             rk<<<(tiles + RW - 1) / RW, RW * 32, smem, st>>>(m->A, rules);
             mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt);
         }

@@ -483,11 +483,12 @@ SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int node, int d
 //   * or the move's budget is spent              -> returns 0
 // Simulations that end in a terminal node are backed up on the spot, at most `max_terminal` of them per call (then 3 is
 // returned and the next call carries on): near the end of a game almost every simulation is such a one, and a single
-// tree working through its whole budget would hold up the wave. Trees with a leaf or a pending edge are skipped.
+// tree working through its whole budget would hold up the wave. For the same reason a call walks at most `max_levels`
+// edges before it yields (3). Trees with a leaf or a pending edge are skipped.
 // ------------------------------------------------------------------------------------------
 template <int N, class W>
-SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int max_terminal, int8_t* leaf_state,
-                            uint8_t* leaf_valid) {
+SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int max_terminal, int max_levels,
+                            int8_t* leaf_state, uint8_t* leaf_valid) {
     MctsTree* T = A.trees + t;
     if (T->leaf >= 0) return 1;
     if (T->pend_edge >= 0) return 2;
@@ -515,6 +516,11 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd->edge_off + (uint32_t)ei; }
             depth++;
             const uint32_t child = ed[ei].child;
+            if (child != 0u && --max_levels <= 0) {   // yield: a very deep path finishes in the next call instead of holding up the wave
+                if (w.lane == 0) { T->cur = (int)child - 1; T->path_len = depth; T->sims_done = sims_done; }
+                w.sync();
+                return 3;
+            }
             if (child == 0u) {   // first traversal of this edge
                 if (w.lane == 0) {
                     T->pend_edge = (int32_t)(nd->edge_off + (uint32_t)ei); T->pend_parent = cur;

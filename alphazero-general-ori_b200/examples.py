@@ -64,12 +64,17 @@ class ExampleBuffer:
         self.player[lanes, slot] = self.cur_player[sel]
         self.count += sel.to(torch.int64)
 
-    def advance(self, ended, scores):
+    def advance(self, ended, scores, moved=None):
         """after the move: ended float32[T,n] (getGameEnded in the new canonical frame), scores int32[T,n] (getScore of
-        the stored state, same frame). Finished lanes hand their examples over and start a new game at seat 0."""
+        the stored state, same frame). Finished lanes hand their examples over and start a new game at seat 0.
+        moved bool[T] (None = all): the lanes that actually made a move in this call."""
         n = self.n
-        self.cur_player = (self.cur_player + 1) % n
-        done = (ended != 0).any(dim=1)
+        if moved is None:
+            self.cur_player = (self.cur_player + 1) % n
+            done = (ended != 0).any(dim=1)
+        else:
+            self.cur_player = torch.where(moved, (self.cur_player + 1) % n, self.cur_player)
+            done = moved & (ended != 0).any(dim=1)
         if bool(done.any()):
             lanes = self._lane[done]
             cnt = self.count[lanes]

@@ -29,7 +29,7 @@ def _ptr(t):
 
 class MCTSArena:
     def __init__(self, n_players, n_trees, node_cap, edge_cap=None, device=0, cpuct=1.0, fpu=0.0, temperature0=1.0,
-                 dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, rounds=1, token_limit=10,
+                 dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, rounds=1, max_levels=0, token_limit=10,
                  rule_flags=nat.RULES_DEFAULT):
         if not torch.cuda.is_available():
             raise RuntimeError("MCTSArena needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -56,7 +56,7 @@ class MCTSArena:
         self._m = m
         self.arena_bytes = nbytes
         self.params = dict(cpuct=cpuct, fpu=fpu, temperature0=temperature0, dirichlet_alpha=dirichlet_alpha, seed=seed,
-                           game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds))
+                           game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds), max_levels=int(max_levels))
         self.set_params()
         self.launches = 0
         self.reset()

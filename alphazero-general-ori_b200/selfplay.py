@@ -24,7 +24,7 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 record_examples=False):
+                 max_levels=0, record_examples=False):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -34,7 +34,7 @@ class SelfPlayEngine:
         node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
         self.arena = MCTSArena(n_players, n_games, node_cap, edge_cap, device=device, cpuct=cpuct, fpu=fpu, temperature0=temperature0,
                                dirichlet_alpha=dirichlet_alpha, seed=seed, game_base=game_base, edge_reserve=edge_reserve,
-                               gc_reachable=gc_reachable, rounds=rounds)
+                               gc_reachable=gc_reachable, rounds=rounds, max_levels=max_levels)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed) * 1000003 + int(game_base))
         self.sims = torch.empty(n_games, dtype=torch.int32, device=self.device)
@@ -129,3 +129,67 @@ class SelfPlayEngine:
         """finished-game examples so far as device tensors (examples.FIELDS); with their symmetric variants (Coach.py:77-80)"""
         ex = self.examples.drain()
         return expand_symmetries(self.env, ex) if symmetries else ex
+
+    # ------------------------------------------------------------------ asynchronous moves
+    # In lock-step every move waits for the slowest tree (deep end-game lines need several waves per simulation and a
+    # few hundred extra waves per move). Here every lane advances on its own: after each batch of waves the trees that
+    # have spent their budget sample their action, make the real move and start the next search; the others keep going.
+    # Each tree still runs exactly the reference's sequential search on its own positions.
+    def start_async(self):
+        T = self.T
+        self._assign_budgets(torch.ones(T, dtype=torch.bool, device=self.device))
+        self.env.states(out=self.roots)
+        self.arena.begin(self.roots, self.sims, self.flags)
+        self.sims_completed = torch.zeros((), dtype=torch.int64, device=self.device)
+        self.moves_completed = torch.zeros((), dtype=torch.int64, device=self.device)
+        self._async = True
+
+    def _assign_budgets(self, lanes):
+        T = self.T
+        if self.prob_full >= 1.0:
+            is_full = torch.ones(T, dtype=torch.bool, device=self.device)
+        else:
+            is_full = torch.rand(T, device=self.device, generator=self.gen) < self.prob_full
+        new_sims = torch.where(is_full, self.num_sims, max(1, self.num_sims // self.ratio_full)).to(torch.int32)
+        fl = (nat.MCTS_MOVE_FORCED if self.forced else 0) | (nat.MCTS_MOVE_NOISE if self.noise else 0)
+        new_flags = torch.where(is_full, fl, 0).to(torch.uint8)
+        self.sims.copy_(torch.where(lanes, new_sims, self.sims))
+        self.flags.copy_(torch.where(lanes, new_flags, self.flags))
+        self._is_full = torch.where(lanes, is_full, getattr(self, "_is_full", is_full))
+
+    def tick(self, waves=None, temp=1.0):
+        """`waves` selection waves (default: one graph replay) for every tree, then the lanes whose search is complete move on"""
+        if self.graph_waves > 0:
+            self._run_waves(waves or self.graph_waves)
+        else:
+            for _ in range(waves or 16):
+                self._wave()
+        st = self.arena.root_stats(want_arrays=False)
+        fin = (st["sims_done"] >= self.sims) | (st["status"] != 0)
+        probs, q = self.arena.policy(temp)
+        p = probs.to(torch.float32)
+        p = torch.where(fin.view(-1, 1) & (p.sum(dim=1, keepdim=True) > 0), p, torch.ones_like(p))
+        a = torch.multinomial(p, 1, generator=self.gen).view(-1).to(torch.int16)
+        self.actions.copy_(torch.where(fin, a, torch.full_like(a, -1)))
+        if self.examples is not None:
+            self.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
+            self.examples.record(self.roots, probs, self.env.valids(), q, self._is_full & fin)
+        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+        ended = self.env.ended
+        done = fin & (ended != 0).any(dim=1)
+        if self.examples is not None:
+            scores, _ = self.env.scores()
+            self.examples.advance(ended, scores, moved=fin)
+        done8 = done.to(torch.uint8)
+        self.env.episodes += done.to(torch.int32)
+        self.env.reset(done8)
+        self.arena.reset(done8)
+        self.games_finished += done.sum()
+        self.sims_completed += torch.where(fin, st["sims_done"], torch.zeros_like(st["sims_done"])).sum()
+        self.moves_completed += fin.sum()
+        self._assign_budgets(fin)
+        self.env.states(out=self.roots)
+        self.arena.begin(self.roots, self.sims, self.flags, fin.to(torch.uint8))
+
+    def sims_in_flight(self):
+        return self.arena.root_stats(want_arrays=False)["sims_done"].sum()

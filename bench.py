@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--graph-waves", type=int, default=16, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="ply", choices=["ply", "reachable"])
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
+    ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
+    ap.add_argument("--max-levels", type=int, default=16, help="edges a descend call walks before it yields to the next wave (0: no limit)")
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
@@ -275,7 +277,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     reach = args.gc == "reachable"
     cap = args.node_cap or (3 if reach else 8) * sims
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
-                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds)
+                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
         eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
@@ -286,18 +288,35 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     eng.env.rollout(args.opening_plies, rotate=True)    # mid-game positions, lanes de-synchronised by the random openings
 
     W = max(args.warmup, 3)
+    G = args.graph_waves if args.graph_waves > 0 else 16
+    ticks_per_step = -(-sims // G)
+    if args.async_moves:
+        eng.start_async()
+
+        def one_step():                      # a step = as many waves as a move has simulations, lanes advancing on their own
+            for _ in range(ticks_per_step):
+                eng.tick(G)
+
+        def sims_now():
+            return int(eng.sims_completed.item()) + int(eng.sims_in_flight().item())
+    else:
+        def one_step():
+            eng.play_move()
+
+        def sims_now():
+            return int(eng.sims_total.item())
     for _ in range(W):
-        eng.play_move()
+        one_step()
     barrier()
     eng.env.counters.zero_()
-    sims0 = int(eng.sims_total.item())
+    sims0 = sims_now()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with Clocks(local) as clk:
         barrier()
         t0 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
-            eng.play_move()
+            one_step()
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -306,16 +325,19 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    sims_done = int(eng.sims_total.item()) - sims0
-    assert sims_done == T * sims * args.steps
+    sims_done = sims_now() - sims0
+    if not args.async_moves:
+        assert sims_done == T * sims * args.steps
     st = eng.arena.root_stats(want_arrays=False)
-    truncated_now = int((st["sims_done"] < sims).sum())
+    truncated_now = 0 if args.async_moves else int((st["sims_done"] < sims).sum())
     value = world * sims_done / (ms_total * 1e-3)
     waves_per_step = -(-sims // args.graph_waves) * args.graph_waves if args.graph_waves > 0 else sims
     own_launches_total = args.steps * (waves_per_step * (3 * args.rounds + 1 + (0 if nn_launches is None and args.nn_dtype != "fused" else 1)) + 16)
 
     # ---- kernel breakdown of one wave, measured live with CUDA events on plain (non-graph) launches
     ar = eng.arena
+    if args.async_moves:
+        ar.finish(eng.evaluator)
     eng.env.states(out=eng.roots)
     ar.begin(eng.roots, eng.sims, eng.flags)
     nb = 200
@@ -346,13 +368,14 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
-                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
+                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves),
+                   "moves_completed": int(eng.moves_completed.item()) if args.async_moves else args.steps * T, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
                        "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(st["sims_done"].sum())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
-                       "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, int(eng.sims_total.item()))},
+                       "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, sims_now())},
     }
     if rank == 0:
         line["clocks"] = clk.summary()
@@ -390,25 +413,39 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
     cap = 8 * sims
     eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
-                             graph_waves=args.graph_waves, rounds=args.rounds)
+                             graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels)
     eng.env.rollout(args.opening_plies, rotate=True)
+    G = args.graph_waves if args.graph_waves > 0 else 16
+    ticks = -(-sims // G)
+    if args.async_moves:
+        eng.start_async()
+
+    def one_step():
+        if args.async_moves:
+            for _ in range(ticks):
+                eng.tick(G)
+        else:
+            eng.play_move()
+
+    def sims_now():
+        return int(eng.sims_completed.item()) + int(eng.sims_in_flight().item()) if args.async_moves else int(eng.sims_total.item())
     for _ in range(3):
-        eng.play_move()
+        one_step()
     barrier()
-    s0 = int(eng.sims_total.item())
+    s0 = sims_now()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     steps = 5
     barrier()
     ev0.record()
     for _ in range(steps):
-        eng.play_move()
+        one_step()
     ev1.record()
     barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    done = int(eng.sims_total.item()) - s0
+    done = sims_now() - s0
     st = eng.arena.root_stats(want_arrays=False)
     return {"value": world * done / (ms * 1e-3), "unit": UNIT_MCTS, "trees_per_gpu": T, "sims_per_move": sims, "steps": steps, "ms_per_step": ms / steps,
             "arena_gb_per_gpu": eng.arena.arena_bytes / 1e9, "truncated_searches": int(st["truncated"].sum()), "lossy_resets": int(st["resets"].sum())}

@@ -185,6 +185,8 @@ typedef struct {
                                    own cleaning :80-85 (default); 1: keeps only what the new root reaches (smaller pools) */
     int      rounds;            /* (descend, rules, attach) passes per selection wave (default 1): a descent that runs into
                                    a transposition or a terminal node continues in the next pass / wave; result-neutral */
+    int      max_levels;        /* edges one descend call walks before it yields to the next wave (0: no limit); bounds the
+                                   wave's latency by the typical, not the deepest, path; result-neutral */
 } spl_mcts_params;
 
 /* bytes of device memory an arena needs; node_cap / edge_cap are per tree */

@@ -70,7 +70,7 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
     DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->edge_reserve, m->gc_reachable, dir, st, scratch, dscratch));
     for (;;) {
         int r = 0;
-        DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, m->leaf_state, m->leaf_valid));
+        DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid));
         if (r == 0) break;
         if (r == 3) continue;
         if (r == 2) {

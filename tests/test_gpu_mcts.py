@@ -66,7 +66,8 @@ def test_arena_vs_search_oracle_many_trees(n):
     from oracle import pyoracle as po
     T, rng = 64, np.random.default_rng(100 + n)
     kw = dict(cpuct=1.7, fpu=0.15)
-    ar = az.MCTSArena(n, T, node_cap=900 if n == 2 else 1600, **kw)
+    # n = 3 also exercises a descend call that yields after 4 edges, n = 4 two (descend, rules, attach) passes per wave
+    ar = az.MCTSArena(n, T, node_cap=900 if n == 2 else 1600, max_levels=4 if n == 3 else 0, rounds=2 if n == 4 else 1, **kw)
     dev = ar.device
     boards, oracles, budgets, flags = [], [], [], []
     for t in range(T):
@@ -297,3 +298,32 @@ def test_batched_arena_like_playgames(n):
     assert two == int(((r0 == -1) & ovt).sum() + ((r0 == 1) & ~ovt).sum())
     assert (_np(d["moves"]) >= 20).all() and (_np(d["moves"]) <= 62 * n + n).all()
     assert d["total_sims"] > 0
+
+
+def test_selfplay_async_moves():
+    """lanes advancing on their own (SelfPlayEngine.tick): every completed move spent exactly its budget, games finish and
+    restart, recorded examples stay consistent with the rules oracle; a descend call that yields after 3 edges is
+    result-neutral for the search itself (covered by the arena tests) and must not break the bookkeeping here"""
+    az = _azg()
+    from oracle import pyoracle as po
+    n, T, sims = 2, 128, 24
+    eng = az.SelfPlayEngine(n, T, None, sims, seed=11, cpuct=1.0, node_cap=512, record_examples=True, max_levels=3, graph_waves=0)
+    eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v)
+    eng.env.rollout(70, rotate=True)
+    eng.start_async()
+    for _ in range(60):
+        eng.tick(8)
+    moves, done_sims = int(eng.moves_completed.item()), int(eng.sims_completed.item())
+    assert moves > 4 * T and done_sims == moves * sims          # prob_full = 1: every search has the full budget
+    assert int(eng.games_finished.item()) >= 10
+    ex = eng.drain_examples(symmetries=False)
+    E = ex["board"].shape[0]
+    assert E > 50
+    boards, pi, winner, scdiff, valids = [_np(ex[k]) for k in ("board", "pi", "winner", "scdiff", "valids")]
+    for e in range(0, E, 7):
+        b = po.Board(n).set_state(boards[e])
+        assert np.array_equal(b.valid_moves(0), valids[e].astype(bool))
+        assert abs(pi[e].sum() - 1.0) < 1e-5 and (pi[e][~valids[e].astype(bool)] == 0).all()
+        assert scdiff[e][0] == 0 and ((winner[e] == 1.0) | (winner[e] == np.float32(0.01))).any()
+    st = eng.arena.root_stats(want_arrays=False)
+    assert int(st["status"].max()) == 0
