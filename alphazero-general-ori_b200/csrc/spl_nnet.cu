@@ -3,7 +3,7 @@
 // Replaces, for the tree arena's leaf rows, GenericNNetWrapper.predict (GenericNNetWrapper.py:141-168) +
 // SplendorNNet.forward (SplendorNNet.py:127-159): int8 states + legal masks in, exp(log_softmax(masked pi)) and tanh(v)
 // out. The torch path (nnet.py) needs ~60 small kernels per wave; here one CTA carries 16 leaves through every layer
-// with the activations resident in shared memory:
+// (two warp groups of 16 leaves each per CTA, sharing the weight stream) with the activations resident in shared memory:
 //
 //   stage A (the "2d" layers, one row per (leaf, gem column): 112 rows per CTA, warp c owns gem column c)
 //       x[56|71|88] -> Linear+BN(7)+ReLU -> Linear+ReLU -> DenseAndPartialGPool(4x8) -> Linear+ReLU
@@ -12,7 +12,7 @@
 //       704 -> 128 -> pool-dense -> 128 -> 128 -> pool-dense -> {PI: 128 -> 406 masked softmax, V: 128 -> n tanh}
 //
 // Matrix products run on the tensor cores as bf16 x bf16 -> fp32 (mma.sync m16n8k16), weights are streamed from L2
-// through a double-buffered cp.async ring in [n][k] blocks laid out exactly as they sit in shared memory (padded rows,
+// through a four-slot cp.async ring in [n][k] blocks laid out exactly as they sit in shared memory (padded rows,
 // conflict-free fragment loads), biases / BatchNorm terms are applied in fp32 in the epilogues. BatchNorm is folded on
 // the host in double precision (eval mode); the score-difference head is not evaluated (MCTS never reads it).
 #include <cuda_bf16.h>
@@ -25,8 +25,11 @@
 
 namespace {
 
-constexpr int NN_SB = 16;        // leaves per CTA
-constexpr int NN_THREADS = 256;  // 8 warps
+constexpr int NN_SB = 16;        // leaves per warp group (8 warps)
+constexpr int NN_GROUPS = 2;     // warp groups per CTA: both consume the same weight block from shared memory, so a CTA
+                                 // streams the network once for 32 leaves (the first version, one group per CTA, pulled
+                                 // 190 MB of weights through L2 per 4096-leaf wave)
+constexpr int NN_THREADS = 256 * NN_GROUPS;
 constexpr int ASTR = 136;        // activation row stride in bf16 elements (128 + 8: conflict-free fragment loads)
 constexpr int FSTR = 712;        // flattened row stride (704 + 8)
 constexpr int LSTR = 416;        // logits row stride (fp32)
@@ -76,13 +79,17 @@ NnPlan make_plan(int n) {
 }
 
 constexpr int SLOT_BYTES = 128 * 72 * 2;   // largest block: [128 n][64 k]
+constexpr int NN_SLOTS = 4;                // weight ring: blocks are requested 3 steps ahead (a step is shorter than an L2 round trip)
 static_assert(SLOT_BYTES >= 64 * ASTR * 2, "slot holds a [64][128] block");
 
-struct NnSmem {
+struct NnGroupSmem {
     __nv_bfloat16 act[7 * NN_SB * ASTR];     // stage A activations; later the fp32 logits
     __nv_bfloat16 flat[NN_SB * FSTR];
     __nv_bfloat16 vec[3][NN_SB * ASTR];
-    unsigned char slot[2][SLOT_BYTES];
+};
+struct NnSmem {
+    NnGroupSmem grp[NN_GROUPS];
+    unsigned char slot[NN_SLOTS][SLOT_BYTES];
 };
 static_assert(sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR >= sizeof(float) * NN_SB * LSTR, "logits alias the activations");
 
@@ -102,84 +109,135 @@ __device__ __forceinline__ void sts_bf16x2(__nv_bfloat16* p, float x, float y) {
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
 }
 
-// A fragments of a 16-row strip: rows row0 + {g, g+8}, k = 16 ks + {2t, 2t+1, 2t+8, 2t+9}
-template <int KS>
-__device__ __forceinline__ void load_afrags(uint32_t (&afr)[8][4], const __nv_bfloat16* a, int stride, int g, int t) {
-#pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-        const __nv_bfloat16* p = a + ks * 16 + 2 * t;
-        afr[ks][0] = lds32(p + g * stride);
-        afr[ks][1] = lds32(p + (g + 8) * stride);
-        afr[ks][2] = lds32(p + g * stride + 8);
-        afr[ks][3] = lds32(p + (g + 8) * stride + 8);
-    }
+// ldmatrix: four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3) and receives, from matrix
+// i, the two elements (row l / 4, columns 2 (l % 4), +1) in r[i]
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm2(uint32_t& r0, uint32_t& r1, const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+// lane address of an A fragment (16 rows x 16 k, row-major): matrices = (rows 0-7 | 8-15) x (k 0-7 | 8-15) -> a0..a3
+__device__ __forceinline__ const __nv_bfloat16* a_lane_ptr(const __nv_bfloat16* a, int stride, int lane) {
+    return a + ((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 8;
+}
+// lane address of the B fragments of TWO adjacent output tiles (16 n x 16 k of an [n][k] block): matrices = b0, b1 of the
+// first tile, b0, b1 of the second
+__device__ __forceinline__ const __nv_bfloat16* b2_lane_ptr(const __nv_bfloat16* w, int stride, int lane) {
+    return w + ((lane & 7) + (lane >> 4) * 8) * stride + ((lane >> 3) & 1) * 8;
+}
+// lane address of the B fragments of ONE output tile over TWO k-steps (8 n x 32 k): matrices = b0, b1 of k-step 0, b0, b1 of k-step 1
+__device__ __forceinline__ const __nv_bfloat16* b1_lane_ptr(const __nv_bfloat16* w, int stride, int lane) {
+    return w + (lane & 7) * stride + (lane >> 3) * 8;
 }
 
-// stage A: one warp = one 16-row strip, A in registers, one [64 n][KB] weight block -> 8 output tiles
+// A fragments of a 16-row strip
+template <int KS>
+__device__ __forceinline__ void load_afrags(uint32_t (&afr)[8][4], const __nv_bfloat16* a, int stride, int lane) {
+    const __nv_bfloat16* p = a_lane_ptr(a, stride, lane);
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) ldsm4(afr[ks], p + ks * 16);
+}
+
+// stage A: one warp = one 16-row strip, A in registers, one [64 n][KB] weight block -> 8 output tiles, two at a time
 template <int KS, class Epi>
-__device__ __forceinline__ void strip_gemm(const uint32_t (&afr)[8][4], const __nv_bfloat16* w, int wstride, int g, int t, Epi epi) {
+__device__ __forceinline__ void strip_gemm(const uint32_t (&afr)[8][4], const __nv_bfloat16* w, int wstride, int lane, Epi epi) {
+    const __nv_bfloat16* wl = b2_lane_ptr(w, wstride, lane);
 #pragma unroll 2
-    for (int nt = 0; nt < 8; nt++) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const __nv_bfloat16* wr = w + (nt * 8 + g) * wstride + 2 * t;
+    for (int np = 0; np < 4; np++) {
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* wr = wl + np * 16 * wstride;
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) mma_bf16(c, afr[ks], lds32(wr + ks * 16), lds32(wr + ks * 16 + 8));
-        epi(nt, c);
+        for (int ks = 0; ks < KS; ks++) {
+            uint32_t b[4];
+            ldsm4(b, wr + ks * 16);
+            mma_bf16(c0, afr[ks], b[0], b[1]);
+            mma_bf16(c1, afr[ks], b[2], b[3]);
+        }
+        epi(2 * np, c0);
+        epi(2 * np + 1, c1);
     }
 }
 
-// stage B: 16 rows shared by all warps (A from shared memory), this warp computes ONE output tile of the block
+// stage B: 16 rows shared by all warps (A from shared memory), this warp computes ONE output tile (8 n) of the block
 template <int KS>
-__device__ __forceinline__ void tile_gemm(float (&c)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride, int g, int t) {
-    const __nv_bfloat16* wr = w + g * wstride + 2 * t;
+__device__ __forceinline__ void tile_gemm(float (&c)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride, int lane) {
+    const __nv_bfloat16* al = a_lane_ptr(a, astride, lane);
+    const __nv_bfloat16* wl = b1_lane_ptr(w, wstride, lane);
+#pragma unroll
+    for (int ks = 0; ks + 1 < KS; ks += 2) {
+        uint32_t a0[4], a1[4], b[4];
+        ldsm4(a0, al + ks * 16);
+        ldsm4(a1, al + ks * 16 + 16);
+        ldsm4(b, wl + ks * 16);
+        mma_bf16(c, a0, b[0], b[1]);
+        mma_bf16(c, a1, b[2], b[3]);
+    }
+    if (KS & 1) {
+        uint32_t a0[4], b0, b1;
+        ldsm4(a0, al + (KS - 1) * 16);
+        ldsm2(b0, b1, w + (lane & 7) * wstride + ((lane >> 3) & 1) * 8 + (KS - 1) * 16);
+        mma_bf16(c, a0, b0, b1);
+    }
+}
+// same A, TWO adjacent output tiles (16 n) of the block
+template <int KS>
+__device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride,
+                                           int lane) {
+    const __nv_bfloat16* al = a_lane_ptr(a, astride, lane);
+    const __nv_bfloat16* wl = b2_lane_ptr(w, wstride, lane);
 #pragma unroll
     for (int ks = 0; ks < KS; ks++) {
-        uint32_t af[4];
-        const __nv_bfloat16* p = a + ks * 16 + 2 * t;
-        af[0] = lds32(p + g * astride);
-        af[1] = lds32(p + (g + 8) * astride);
-        af[2] = lds32(p + g * astride + 8);
-        af[3] = lds32(p + (g + 8) * astride + 8);
-        mma_bf16(c, af, lds32(wr + ks * 16), lds32(wr + ks * 16 + 8));
+        uint32_t af[4], b[4];
+        ldsm4(af, al + ks * 16);
+        ldsm4(b, wl + ks * 16);
+        mma_bf16(c0, af, b[0], b[1]);
+        mma_bf16(c1, af, b[2], b[3]);
     }
 }
 
 template <int NP>
-__global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsigned char* __restrict__ blob, NnPlan plan, const int8_t* __restrict__ states,
+__global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsigned char* __restrict__ blob, NnPlan plan, const int8_t* __restrict__ states,
                                                                      const uint8_t* __restrict__ valids, int n_rows, float* __restrict__ pi,
                                                                      float* __restrict__ vout) {
     constexpr int R = 32 + 10 * NP + NP * NP, S = 7 * R, K1 = (R + 15) / 16 * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NnSmem& sm = *reinterpret_cast<NnSmem*>(smem_raw);
+    NnSmem& smem_all = *reinterpret_cast<NnSmem*>(smem_raw);
     const float* prm = reinterpret_cast<const float*>(blob);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int base = blockIdx.x * NN_SB;
-    const int live = min(NN_SB, n_rows - base);
+    const int tid = threadIdx.x, group = tid >> 8, gtid = tid & 255, warp = gtid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    NnGroupSmem& sm = smem_all.grp[group];
+    const int base = (blockIdx.x * NN_GROUPS + group) * NN_SB;
+    const int live = max(0, min(NN_SB, n_rows - base));
 
-    // ---- weight-block ring: block b lives in slot b & 1
-    int next_issue = 0;
+    // ---- weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
     auto issue = [&](int b) {
         const unsigned char* src = blob + plan.off[b];
-        unsigned char* dst = sm.slot[b & 1];
+        unsigned char* dst = smem_all.slot[b % NN_SLOTS];
         for (int i = tid * 16; i < plan.bytes[b]; i += NN_THREADS * 16) cp_async16(dst + i, src + i);
         cp_async_commit();
     };
-    issue(0);
-    next_issue = 1;
-    auto acquire = [&](int b) -> const __nv_bfloat16* {   // block b ready for every thread; block b+1 in flight
-        if (next_issue == b + 1 && b + 1 < plan.nblocks) { issue(b + 1); next_issue = b + 2; cp_async_wait<1>(); }
+    for (int b = 0; b < NN_SLOTS - 1; b++) issue(b);
+    auto acquire = [&](int b) -> const __nv_bfloat16* {   // block b ready for every thread; up to NN_SLOTS - 1 blocks in flight
+        if (b + NN_SLOTS - 1 < plan.nblocks) issue(b + NN_SLOTS - 1);   // its slot was released at the end of step b - 1
+        const int ahead = min(NN_SLOTS - 1, plan.nblocks - 1 - b);
+        if (ahead >= 3) cp_async_wait<3>();
+        else if (ahead == 2) cp_async_wait<2>();
+        else if (ahead == 1) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncthreads();
-        return reinterpret_cast<const __nv_bfloat16*>(sm.slot[b & 1]);
+        return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]);
     };
     auto release = [&]() { __syncthreads(); };
 
     // ---- input: act[c*16 + s][k] = state[s][k][c]  (int8 counts are exact in bf16), zero padding up to K1
-    for (int i = tid; i < 7 * NN_SB * K1; i += NN_THREADS) {
-        const int row = i / K1, k = i - row * K1, c = row >> 4, s = row & 15;
-        float x = 0.f;
-        if (k < R && s < live) x = (float)states[(size_t)(base + s) * S + k * 7 + c];
-        sm.act[row * ASTR + k] = __float2bfloat16(x);
+    for (int i = gtid; i < NN_SB * K1; i += 256) {
+        const int s = i / K1, k = i - s * K1;
+        const bool in = k < R && s < live;
+        const int8_t* src = states + (size_t)(base + s) * S + k * 7;
+#pragma unroll
+        for (int c = 0; c < 7; c++) sm.act[(c * 16 + s) * ASTR + k] = __float2bfloat16(in ? (float)src[c] : 0.f);
     }
     __syncthreads();
 
@@ -191,12 +249,12 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
     // ---- L1: Linear(R,128) + BatchNorm1d(7) + ReLU
     {
         const float s1 = strip ? prm[P_S1 + warp] : 0.f, t1 = strip ? prm[P_T1 + warp] : 0.f;
-        if (strip) load_afrags<K1 / 16>(afr, arow, ASTR, g, t);
+        if (strip) load_afrags<K1 / 16>(afr, arow, ASTR, lane);
         __syncwarp();
         for (int h = 0; h < 2; h++) {
             const __nv_bfloat16* w = acquire(blk);
             if (strip)
-                strip_gemm<K1 / 16>(afr, w, K1 + 8, g, t, [&](int nt, float (&c)[4]) {
+                strip_gemm<K1 / 16>(afr, w, K1 + 8, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
                     const float b0 = prm[P_B1 + n], b1 = prm[P_B1 + n + 1];
                     sts_bf16x2(arow + g * ASTR + n, fmaxf((c[0] + b0) * s1 + t1, 0.f), fmaxf((c[1] + b1) * s1 + t1, 0.f));
@@ -207,12 +265,12 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
     }
     // ---- L2 and (after the pool layer) L3: Linear(128,128) + ReLU
     auto dense_relu_strip = [&](int pbias) {
-        if (strip) load_afrags<8>(afr, arow, ASTR, g, t);
+        if (strip) load_afrags<8>(afr, arow, ASTR, lane);
         __syncwarp();
         for (int h = 0; h < 2; h++) {
             const __nv_bfloat16* w = acquire(blk);
             if (strip)
-                strip_gemm<8>(afr, w, ASTR, g, t, [&](int nt, float (&c)[4]) {
+                strip_gemm<8>(afr, w, ASTR, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
                     const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
                     sts_bf16x2(arow + g * ASTR + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
@@ -227,7 +285,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         const float sg = strip ? prm[P_SG1 + warp] : 0.f, tg = strip ? prm[P_TG1 + warp] : 0.f;
         float pmx[2], pav[2];
         if (strip) {
-            load_afrags<6>(afr, arow + 32, ASTR, g, t);
+            load_afrags<6>(afr, arow + 32, ASTR, lane);
 #pragma unroll
             for (int q = 0; q < 2; q++) {   // 64 (row, group) pairs per strip, two per lane
                 const int pr = lane * 2 + q, row = pr >> 2, grp = pr & 3;
@@ -254,7 +312,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         for (int h = 0; h < 2; h++) {
             const __nv_bfloat16* w = acquire(blk);
             if (strip)
-                strip_gemm<6>(afr, w, 96 + 8, g, t, [&](int nt, float (&c)[4]) {
+                strip_gemm<6>(afr, w, 96 + 8, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
                     if (n < 120) {
                         const float b0 = prm[P_BG1 + n], b1 = prm[P_BG1 + n + 1];
@@ -268,7 +326,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
     dense_relu_strip(P_B3);
 
     // ---- FlattenAndPartialGPool(64, 5): [max over the 5 gem colours | mean | gold, points rows | last 64 features of all 7]
-    for (int i = tid; i < NN_SB * 704; i += NN_THREADS) {
+    for (int i = gtid; i < NN_SB * 704; i += 256) {
         const int s = i / 704, f = i - s * 704;
         float x;
         if (f < 128) {
@@ -296,8 +354,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
         for (int kb = 0; kb < 11; kb++) {
             const __nv_bfloat16* w = acquire(blk);
-            tile_gemm<4>(c0, sm.flat + kb * 64, FSTR, w + (2 * warp) * 8 * 72, 72, g, t);
-            tile_gemm<4>(c1, sm.flat + kb * 64, FSTR, w + (2 * warp + 1) * 8 * 72, 72, g, t);
+            tile2_gemm<4>(c0, c1, sm.flat + kb * 64, FSTR, w + (2 * warp) * 8 * 72, 72, lane);
             release(); blk++;
         }
         __nv_bfloat16* o = sm.vec[0];
@@ -316,7 +373,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         for (int h = 0; h < 2; h++) {
             const __nv_bfloat16* w = acquire(blk);
             float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<8>(c, in, ASTR, w + warp * 8 * ASTR, ASTR, g, t);
+            tile_gemm<8>(c, in, ASTR, w + warp * 8 * ASTR, ASTR, lane);
             const int n = h * 64 + warp * 8 + 2 * t;
             const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
             float v0 = c[0] + b0, v1 = c[1] + b1, v2 = c[2] + b0, v3 = c[3] + b1;
@@ -327,8 +384,8 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         }
     };
     auto pool_dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias) {   // 4 groups of 4 + Linear(112,120)+BN(1)+ReLU
-        if (tid < 64) {
-            const int row = tid >> 2, grp = tid & 3;
+        if (gtid < 64) {
+            const int row = gtid >> 2, grp = gtid & 3;
             const uint2 raw = *reinterpret_cast<const uint2*>(in + row * ASTR + grp * 4);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
             const float2 a = __bfloat1622float2(h2[0]), b = __bfloat1622float2(h2[1]);
@@ -338,7 +395,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         for (int h = 0; h < 2; h++) {
             const __nv_bfloat16* w = acquire(blk);
             float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<7>(c, in + 16, ASTR, w + warp * 8 * 120, 120, g, t);
+            tile_gemm<7>(c, in + 16, ASTR, w + warp * 8 * 120, 120, lane);
             const int n = h * 64 + warp * 8 + 2 * t;
             if (n < 120) {
                 const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
@@ -360,7 +417,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
     for (int h = 0; h < 7; h++) {
         const __nv_bfloat16* w = acquire(blk);
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_gemm<8>(c, sm.vec[1], ASTR, w + warp * 8 * ASTR, ASTR, g, t);
+        tile_gemm<8>(c, sm.vec[1], ASTR, w + warp * 8 * ASTR, ASTR, lane);
         const int n = h * 64 + warp * 8 + 2 * t;
         if (n < LSTR) {
             const float b0 = prm[P_BP1 + n], b1 = prm[P_BP1 + n + 1];
@@ -374,7 +431,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nnet_forward_kernel(const unsig
         const __nv_bfloat16* w = acquire(blk);
         if (warp == 0) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<8>(c, sm.vec[2], ASTR, w, ASTR, g, t);
+            tile_gemm<8>(c, sm.vec[2], ASTR, w, ASTR, lane);
             const int n = 2 * t;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -508,7 +565,7 @@ int spl_nnet_forward(spl_ctx* c, const void* blob, const int8_t* states, const u
     if (((uintptr_t)blob & 15u) != 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: blob must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const NnPlan p = make_plan(c->n);
-    const int grid = (n_rows + NN_SB - 1) / NN_SB;
+    const int grid = (n_rows + NN_SB * NN_GROUPS - 1) / (NN_SB * NN_GROUPS);
     const int smem = (int)sizeof(NnSmem);
     DISPATCH_N(c->n, {
         auto k = nnet_forward_kernel<N>;

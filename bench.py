@@ -331,8 +331,13 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     st = eng.arena.root_stats(want_arrays=False)
     truncated_now = 0 if args.async_moves else int((st["sims_done"] < sims).sum())
     value = world * sims_done / (ms_total * 1e-3)
-    waves_per_step = -(-sims // args.graph_waves) * args.graph_waves if args.graph_waves > 0 else sims
-    own_launches_total = args.steps * (waves_per_step * (3 * args.rounds + 1 + (0 if nn_launches is None and args.nn_dtype != "fused" else 1)) + 16)
+    # our own kernels inside the timed region (graph replays re-launch the captured ones): per wave 3 x rounds selection
+    # kernels + the evaluator + expand; per tick / move the stats, policy, env step, resets, unpack and begin kernels
+    per_wave = 3 * args.rounds + 1 + (1 if (args.fixed_net or args.nn_dtype == "fused") else 0)
+    if args.async_moves:
+        own_launches_total = args.steps * ticks_per_step * (G * per_wave + 8)
+    else:
+        own_launches_total = args.steps * ((ticks_per_step * G + eng.extra_waves // max(1, W + args.steps)) * per_wave + 10)
 
     # ---- kernel breakdown of one wave, measured live with CUDA events on plain (non-graph) launches
     ar = eng.arena
@@ -385,6 +390,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     import numpy as np
     boards = eng.env.states().cpu().numpy()
     ar.reset()
+    ar.set_params(max_levels=0)     # lock-step calls wait for the slowest tree: no yielding inside a descent
     ke = 3
     h2d = d2h = 0
     barrier()
