@@ -11,7 +11,7 @@
 //   stage B (the "1d" layers, 16 rows per CTA, the 8 warps split the output columns)
 //       704 -> 128 -> pool-dense -> 128 -> 128 -> pool-dense -> {PI: 128 -> 406 masked softmax, V: 128 -> n tanh}
 //
-// Matrix products run on the tensor cores as bf16 x bf16 -> fp32 (mma.sync m16n8k16), weights are streamed from L2
+// Matrix products run on the tensor cores as bf16 x bf16 -> fp32 (mma.sync m16n8k16, fragments by ldmatrix), weights are streamed from L2
 // through a four-slot cp.async ring in [n][k] blocks laid out exactly as they sit in shared memory (padded rows,
 // conflict-free fragment loads), biases / BatchNorm terms are applied in fp32 in the epilogues. BatchNorm is folded on
 // the host in double precision (eval mode); the score-difference head is not evaluated (MCTS never reads it).
@@ -104,7 +104,6 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ void sts_bf16x2(__nv_bfloat16* p, float x, float y) {
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
 }
