@@ -150,6 +150,19 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_expand_kernel(MctsArena A, Mc
     mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
 }
 
+// expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree)
+template <int N>
+__global__ void __launch_bounds__(MW * 32, 8) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
+                                                                         int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
+    const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
+    WarpScratch sc = warp_scratch(warp);
+    if (t >= A.n_trees) return;
+    MctsWarp w{(int)(threadIdx.x & 31)};
+    mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
+    w.sync();
+    mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+}
+
 template <int N>
 __global__ void __launch_bounds__(MW * 32) mcts_policy_kernel(MctsArena A, double temp, double* probs, double* q) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
@@ -299,6 +312,28 @@ int spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
             mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+            rk<<<(tiles + RW - 1) / RW, RW * 32, smem, st>>>(m->A, rules);
+            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt);
+        }
+    });
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const double* dir_values, int8_t* leaf_states, uint8_t* leaf_valids,
+                           uint8_t* leaf_flags, int32_t* counters, void* stream) {
+    ENTER_M(m);
+    if (!pi || !v || !leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_expand_select: bad argument");
+    const int tiles = (m->A.n_trees + 31) / 32;
+    const SplRules rules = m->ctx->rules;
+    DISPATCH_N(m->ctx->n, {
+        const int smem = RW * MctsLay<N>::S * 32;
+        auto rk = mcts_rules_kernel<N>;
+        CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int r = 0; r < m->rounds; r++) {
+            int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
+            if (r == 0) mcts_expand_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            else mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
             rk<<<(tiles + RW - 1) / RW, RW * 32, smem, st>>>(m->A, rules);
             mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt);
         }

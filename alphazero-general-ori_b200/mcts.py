@@ -109,6 +109,17 @@ class MCTSArena:
         nat.check(self._lib.spl_mcts_expand(self._m, _ptr(pi), _ptr(v), _ptr(dir_values), self._stream()))
         self.launches += 1
 
+    def expand_select(self, pi, v, dir_values=None, count=False):
+        """expand the previous wave's leaves and select the next ones (expansion + descent fused in one launch)"""
+        nat.check(self._lib.spl_mcts_expand_select(self._m, _ptr(pi), _ptr(v), _ptr(dir_values), _ptr(self.leaf_states), _ptr(self.leaf_valids),
+                                                   _ptr(self.leaf_flags), _ptr(self.counters) if count else None, self._stream()))
+        self.launches += 3 * self.params["rounds"]
+
+    def wave_steady(self, evaluator, dir_values=None):
+        """steady-state wave for leaves that are already selected: network -> expand + next selection"""
+        pi, v = evaluator(self.leaf_states, self.leaf_valids)
+        self.expand_select(pi, v, dir_values)
+
     def remaining(self):
         """one (leaf-less) selection wave that counts the trees whose budget is not spent yet -> int (host sync)"""
         self.counters.zero_()

@@ -52,7 +52,10 @@ class SelfPlayEngine:
 
     # ------------------------------------------------------------------
     def _wave(self):
-        self.arena.wave(self.evaluator)
+        if getattr(self, "_async", False):
+            self.arena.wave_steady(self.evaluator)     # leaves are always selected one wave ahead
+        else:
+            self.arena.wave(self.evaluator)
 
     def _run_waves(self, waves):
         if self.graph_waves <= 0:
@@ -140,6 +143,7 @@ class SelfPlayEngine:
         self._assign_budgets(torch.ones(T, dtype=torch.bool, device=self.device))
         self.env.states(out=self.roots)
         self.arena.begin(self.roots, self.sims, self.flags)
+        self.arena.select()
         self.sims_completed = torch.zeros((), dtype=torch.int64, device=self.device)
         self.moves_completed = torch.zeros((), dtype=torch.int64, device=self.device)
         self._async = True

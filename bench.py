@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
     ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
-    ap.add_argument("--graph-waves", type=int, default=16, help="waves per CUDA-graph replay (0: plain launches)")
+    ap.add_argument("--graph-waves", type=int, default=64, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="ply", choices=["ply", "reachable"])
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
@@ -335,7 +335,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     # kernels + the evaluator + expand; per tick / move the stats, policy, env step, resets, unpack and begin kernels
     per_wave = 3 * args.rounds + 1 + (1 if (args.fixed_net or args.nn_dtype == "fused") else 0)
     if args.async_moves:
-        own_launches_total = args.steps * ticks_per_step * (G * per_wave + 8)
+        own_launches_total = args.steps * ticks_per_step * (G * (per_wave - 1) + 8)     # expansion and descent share a launch
     else:
         own_launches_total = args.steps * ((ticks_per_step * G + eng.extra_waves // max(1, W + args.steps)) * per_wave + 10)
 
@@ -418,10 +418,10 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     n, T, sims = args.players, args.wide_trees, args.wide_sims
     net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
     cap = 8 * sims
+    G = min(16, args.graph_waves) if args.graph_waves > 0 else 16      # short budgets: look for finished lanes every 16 waves
     eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
-                             graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels)
+                             graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds, max_levels=args.max_levels)
     eng.env.rollout(args.opening_plies, rotate=True)
-    G = args.graph_waves if args.graph_waves > 0 else 16
     ticks = -(-sims // G)
     if args.async_moves:
         eng.start_async()

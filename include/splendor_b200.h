@@ -212,6 +212,10 @@ int  spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const
 int  spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
 /* pi float[T][406] = the network's probabilities (exp of the masked log-softmax, GenericNNetWrapper.py:166), v float[T][n] */
 int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double* dir_values, void* stream);
+/* spl_mcts_expand followed by spl_mcts_select with the expansion and the next descent fused into one launch (the steady state
+ * of a search: network -> expand_select -> network -> ...) */
+int  spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const double* dir_values, int8_t* leaf_states,
+                            uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
 /* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */
 int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* stream);
 /* raw root statistics, any pointer may be NULL: nsa int32[T][406], qsa double[T][406] (-42 = unvisited), ps float[T][406],
