@@ -248,7 +248,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     if (((uintptr_t)arena & 255u) != 0) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena must be 256-byte aligned");
     const ArenaPlan p = plan_arena(ctx->n, n_trees, node_cap, edge_cap);
     if (arena_bytes < p.total) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena smaller than spl_mcts_arena_bytes");
-    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsEdge) == 24 && sizeof(MctsTree) == 96, "arena record sizes");
+    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsEdge) == 32 && sizeof(MctsTree) == 96, "arena record sizes");
     spl_mcts* m = new spl_mcts;
     m->ctx = ctx;
     char* base = (char*)arena;

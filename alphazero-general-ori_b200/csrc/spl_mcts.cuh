@@ -109,12 +109,15 @@ struct MctsNode {   // 32 B
         float es[4];                                          // TERMINAL: getGameEnded vector
     } u;
 };
-struct MctsEdge {   // 24 B
+struct MctsEdge {   // 32 B
     double Q;        // Qsa (float64, -42 = unvisited)
     float P;         // Ps[a]
     int32_t N;       // Nsa
     uint32_t child;  // node index + 1 (0 = not linked yet)
-    uint16_t action, pad;
+    uint16_t action;
+    uint16_t child_ne;    // the child's edge count and first edge, copied here when the edge is linked: the descent then
+    uint32_t child_eoff;  // fetches the child's header and its edges in ONE round trip instead of two dependent ones
+    uint32_t pad;
 };
 struct MctsTree {   // 96 B
     int32_t n_nodes, n_edges, root, leaf;
@@ -275,7 +278,7 @@ SPL_D int mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* s
                 const int b = SPL_FFS(bits) - 1;
                 bits &= bits - 1u;
                 MctsEdge e;
-                e.Q = MCTS_UNVISITED; e.P = 0.f; e.N = 0; e.child = 0u; e.action = (uint16_t)(32 * i + b); e.pad = 0;
+                e.Q = MCTS_UNVISITED; e.P = 0.f; e.N = 0; e.child = 0u; e.action = (uint16_t)(32 * i + b); e.child_ne = 0; e.child_eoff = 0u; e.pad = 0u;
                 ed[off++] = e;
             }
         }
@@ -399,13 +402,14 @@ SPL_D void mcts_root_noise(const W& w, MctsEdge* ed, int k, const MctsSearchPara
 // returns the edge position inside the node
 // ------------------------------------------------------------------------------------------
 template <class W>
-SPL_D int mcts_pick(const W& w, const MctsEdge* ed, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced, int n_iter) {
+SPL_D int mcts_pick(const W& w, const MctsEdge* ed, const MctsEdge& first, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced,
+                    int n_iter) {   // `first` = ed[lane], fetched by the caller together with the node header
     const double fpu_init = P.fpu > 0.0 ? MC_DADD((double)Qs, -P.fpu) : P.fpu;   // :202
     const double sq_ns = MC_DSQRT((double)Ns), sq_ns_eps = MC_DSQRT(MC_DADD((double)Ns, MCTS_EPS));
     double best_u = 0.0;
     int best_i = -1, forced_i = 0x7fffffff;
     for (int i = w.lane; i < k; i += W::W) {
-        const MctsEdge e = ed[i];
+        const MctsEdge e = i == w.lane ? first : ed[i];
         if (forced && forced_i == 0x7fffffff) {   // :207-208 - the first legal action short of its forced visits wins outright
             const long long quota = (long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)n_iter));
             if ((long long)e.N < quota) forced_i = i;
@@ -502,20 +506,28 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
     const int root = T->root;
     int cur = T->cur, depth = cur >= 0 ? T->path_len : 0;
     if (cur < 0) cur = root;
+    // where the edges of `cur` are expected: known from the parent's edge, or from the node header at the start of a walk
+    uint32_t eoff = nodes[cur].edge_off;
+    int ne = nodes[cur].kind == MCTS_NODE_TERMINAL ? 0 : (int)nodes[cur].n_edges;
     while (sims_done < target) {
         for (;;) {
-            const MctsNode* nd = nodes + cur;
-            const int kind = nd->kind;
+            const MctsNode* ndp = nodes + cur;
+            const MctsEdge* ed = edges + eoff;
+            MctsEdge first;                                  // header and first 32 edges: one round trip
+            first.Q = MCTS_UNVISITED; first.P = 0.f; first.N = 0; first.child = 0u; first.action = 0; first.child_ne = 0; first.child_eoff = 0u; first.pad = 0u;
+            if (w.lane < ne) first = ed[w.lane];
+            const MctsNode nd = *ndp;
+            const int kind = nd.kind;
             if (kind == MCTS_NODE_NEEDS_NN) {
                 mcts_emit_leaf<N>(w, A, t, cur, depth, sims_done, leaf_state, leaf_valid);
                 return 1;
             }
             if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
-            const MctsEdge* ed = edges + nd->edge_off;
-            const int ei = mcts_pick(w, ed, (int)nd->n_edges, nd->u.x.Ns, nd->u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
-            if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd->edge_off + (uint32_t)ei; }
+            const int ei = mcts_pick(w, ed, first, (int)nd.n_edges, nd.u.x.Ns, nd.u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
+            if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd.edge_off + (uint32_t)ei; }
             depth++;
-            const uint32_t child = ed[ei].child;
+            const MctsEdge sel = ed[ei];
+            const uint32_t child = sel.child;
             if (child != 0u && --max_levels <= 0) {   // yield: a very deep path finishes in the next call instead of holding up the wave
                 if (w.lane == 0) { T->cur = (int)child - 1; T->path_len = depth; T->sims_done = sims_done; }
                 w.sync();
@@ -523,13 +535,14 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             }
             if (child == 0u) {   // first traversal of this edge
                 if (w.lane == 0) {
-                    T->pend_edge = (int32_t)(nd->edge_off + (uint32_t)ei); T->pend_parent = cur;
+                    T->pend_edge = (int32_t)(nd.edge_off + (uint32_t)ei); T->pend_parent = cur;
                     T->path_len = depth; T->sims_done = sims_done; T->cur = -1;
                 }
                 w.sync();
                 return 2;
             }
             cur = (int)child - 1;
+            eoff = sel.child_eoff; ne = (int)sel.child_ne;
         }
         {   // terminal: return Es up the path
             float v[N];
@@ -540,6 +553,7 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
         w.sync();
         sims_done++;
         cur = root; depth = 0;
+        eoff = nodes[root].edge_off; ne = nodes[root].kind == MCTS_NODE_TERMINAL ? 0 : (int)nodes[root].n_edges;
         if (--max_terminal <= 0 && sims_done < target) {
             if (w.lane == 0) { T->sims_done = sims_done; T->cur = -1; T->path_len = 0; }
             w.sync();
@@ -569,7 +583,12 @@ SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSear
         return 0;
     }
     MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    if (w.lane == 0) A.edges[(size_t)t * A.ecap + pe].child = (uint32_t)idx + 1u;
+    if (w.lane == 0) {
+        MctsEdge* e = A.edges + (size_t)t * A.ecap + pe;
+        e->child = (uint32_t)idx + 1u;
+        e->child_eoff = nodes[idx].edge_off;
+        e->child_ne = nodes[idx].kind == MCTS_NODE_TERMINAL ? (uint16_t)0 : nodes[idx].n_edges;
+    }
     w.sync();
     const int kind = nodes[idx].kind;
     const int depth = T->path_len, sims_done = T->sims_done;
@@ -692,6 +711,10 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
         }
         e_new += ne;
         w.sync();
+    }
+    for (int k = w.lane; k < e_new; k += W::W) {   // the children moved too: refresh the edge ranges cached in the edges
+        MctsEdge* e = edges + k;
+        if (e->child) e->child_eoff = nodes[e->child - 1u].edge_off;
     }
     for (int i = w.lane; i < A.hcap; i += W::W) remap[i] = 0u;
     w.sync();
