@@ -27,7 +27,7 @@ EXPORTS = [
     "spl_state_rows", "spl_state_bytes", "spl_lanes_padded", "spl_planes_bytes", "spl_mask_planes_bytes",
     "spl_pack", "spl_unpack", "spl_mask_unpack", "spl_reset_philox", "spl_reset_explicit", "spl_step", "spl_rollout",
     "spl_scores", "spl_symmetries",
-    "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_begin",
+    "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
     "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_policy", "spl_mcts_root_stats", "spl_mcts_fixed_net",
     "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward",
 ]
@@ -128,6 +128,7 @@ def lib():
         L.spl_mcts_destroy.restype = None
         L.spl_mcts_set_params.argtypes = [vp, C.POINTER(MctsParams)]
         L.spl_mcts_reset.argtypes = [vp, vp, vp]
+        L.spl_mcts_clean.argtypes = [vp, ci, vp]
         L.spl_mcts_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.spl_mcts_select.argtypes = [vp, vp, vp, vp, vp, vp]
         L.spl_mcts_expand.argtypes = [vp, vp, vp, vp, vp]

@@ -180,6 +180,13 @@ __global__ void __launch_bounds__(MW * 32) mcts_stats_kernel(MctsArena A, int32_
                          ps ? ps + (size_t)t * SPL_ACTIONS : nullptr, info ? info + (size_t)t * 16 : nullptr);
 }
 
+__global__ void __launch_bounds__(MW * 32) mcts_clean_kernel(MctsArena A, int max_nodes, int max_edges, int gc_reachable) {
+    const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
+    if (t >= A.n_trees) return;
+    MctsWarp w{(int)(threadIdx.x & 31)};
+    mcts_clean_tree(w, A, t, max_nodes, max_edges, gc_reachable);
+}
+
 __global__ void __launch_bounds__(MW * 32) mcts_reset_kernel(MctsArena A, const uint8_t* tree_select) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
@@ -286,6 +293,15 @@ int spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p) {
 int spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream) {
     ENTER_M(m);
     mcts_reset_kernel<<<grid, MW * 32, 0, st>>>(m->A, tree_select);
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_clean(spl_mcts* m, int fill_percent, void* stream) {
+    ENTER_M(m);
+    if (fill_percent < 0 || fill_percent > 100) return spl_fail_(SPL_E_ARG, "spl_mcts_clean: bad argument");
+    mcts_clean_kernel<<<grid, MW * 32, 0, st>>>(m->A, (int)((long long)m->A.cap * fill_percent / 100), (int)((long long)m->A.ecap * fill_percent / 100),
+                                                m->gc_reachable);
     CU(cudaGetLastError());
     return SPL_OK;
 }

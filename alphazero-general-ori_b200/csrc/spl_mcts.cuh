@@ -676,6 +676,16 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
         n_new += SPL_POPC(b);
     }
     w.sync();
+    // a simulation may be in flight (the periodic cleaning runs between waves): its references into the pools - root,
+    // cur, leaf, the pending edge and the recorded path - are re-based with the nodes. Edge references become
+    // (node, position inside the node) while the blocks move.
+    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    const bool in_flight = T->leaf >= 0 || T->cur >= 0 || T->pend_edge >= 0;
+    const int plen = in_flight ? T->path_len : 0;
+    for (int d = w.lane; d < plen; d += W::W) path[2 * d + 1] -= nodes[path[2 * d]].edge_off;
+    int pend_rel = -1;
+    if (T->pend_edge >= 0) pend_rel = T->pend_edge - (int)nodes[T->pend_parent].edge_off;
+    w.sync();
     int e_new = 0;
     for (int i = 0; i < n_old; i++) {
         const uint32_t r = remap[i];
@@ -716,6 +726,22 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
         MctsEdge* e = edges + k;
         if (e->child) e->child_eoff = nodes[e->child - 1u].edge_off;
     }
+    w.sync();
+    for (int d = w.lane; d < plen; d += W::W) {
+        const uint32_t nn = remap[path[2 * d]] - 1u;
+        path[2 * d] = nn;
+        path[2 * d + 1] += nodes[nn].edge_off;
+    }
+    if (w.lane == 0) {
+        if (T->root >= 0) T->root = (int)remap[T->root] - 1;       // (-1 if the root itself was dropped: begin re-creates it)
+        if (T->leaf >= 0) T->leaf = (int)remap[T->leaf] - 1;
+        if (T->cur >= 0) T->cur = (int)remap[T->cur] - 1;
+        if (pend_rel >= 0) {
+            T->pend_parent = (int)remap[T->pend_parent] - 1;
+            T->pend_edge = (int)nodes[T->pend_parent].edge_off + pend_rel;
+        }
+    }
+    w.sync();
     for (int i = w.lane; i < A.hcap; i += W::W) remap[i] = 0u;
     w.sync();
     if (w.lane == 0) {
@@ -772,6 +798,21 @@ SPL_D void mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) 
         }
     }
     w.sync();
+}
+
+// periodic cleaning between waves (any state of the search): trees whose pools are filled beyond the thresholds drop
+// what can no longer be used - nodes below the root's ply (exact) or everything the root does not reach (gc_reachable).
+// Every tree that needs it cleans in the SAME launch, so the serial per-tree work is paid once for all of them.
+template <class W>
+SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes, int max_edges, int gc_reachable) {
+    MctsTree* T = A.trees + t;
+    if (T->root < 0 || (T->n_nodes <= max_nodes && T->n_edges <= max_edges)) return;
+    if (gc_reachable) {
+        mcts_mark_reachable(w, A, t, T->root);
+        mcts_compact(w, A, t, 0, true);
+    } else {
+        mcts_compact(w, A, t, (int)A.nodes[(size_t)t * A.cap + T->root].ply, false);
+    }
 }
 
 template <class W>

@@ -87,6 +87,11 @@ class MCTSArena:
         nat.check(self._lib.spl_mcts_reset(self._m, _ptr(tree_select), self._stream()))
         self.launches += 1
 
+    def clean(self, fill_percent=50):
+        """between waves: trees filled beyond fill_percent compact their pools (all in one launch)"""
+        nat.check(self._lib.spl_mcts_clean(self._m, int(fill_percent), self._stream()))
+        self.launches += 1
+
     def begin(self, roots, sims, move_flags=None, tree_select=None, dir_values=None):
         """roots int8[T,R,7] canonical boards (device), sims int32[T], move_flags uint8[T] (MCTS_MOVE_FORCED | MCTS_MOVE_NOISE),
         dir_values float64[T,406] (the Dirichlet vector per root, parity runs) or None (on-device Philox sampler)"""

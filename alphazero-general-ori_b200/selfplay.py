@@ -24,7 +24,7 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 max_levels=0, record_examples=False):
+                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -42,6 +42,7 @@ class SelfPlayEngine:
         self.roots = torch.empty((n_games, self.env.R, 7), dtype=torch.int8, device=self.device)
         self.actions = torch.empty(n_games, dtype=torch.int16, device=self.device)
         self.graph_waves = int(graph_waves)
+        self.clean_every, self.clean_percent, self._ticks = int(clean_every), int(clean_percent), 0
         self._graph = None
         self.env.reset()
         self.examples = ExampleBuffer(n_players, n_games, self.env.R, self.device) if record_examples else None
@@ -168,6 +169,9 @@ class SelfPlayEngine:
         else:
             for _ in range(waves or 16):
                 self._wave()
+        self._ticks += 1
+        if self.clean_every > 0 and self._ticks % self.clean_every == 0:
+            self.arena.clean(self.clean_percent)      # every tree that needs it, in one launch, off the path of begin
         st = self.arena.root_stats(want_arrays=False)
         fin = (st["sims_done"] >= self.sims) | (st["status"] != 0)
         probs, q = self.arena.policy(temp)

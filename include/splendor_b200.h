@@ -197,6 +197,10 @@ void spl_mcts_destroy(spl_mcts* m);
 int  spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p);
 /* reset_all_search_trees (:188-192); tree_select (may be NULL) restricts it to trees with a non-zero byte */
 int  spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream);
+/* cleaning between waves, in any state of the search: every tree whose node or edge pool is filled beyond fill_percent drops
+ * what it can no longer use (per gc_reachable) and re-bases the simulation in flight. All trees that need it clean in the
+ * same launch - the way to keep the serial per-tree compaction off the critical path of spl_mcts_begin. */
+int  spl_mcts_clean(spl_mcts* m, int fill_percent, void* stream);
 /* start of getActionProb for every (selected) tree: roots int8[T][R*7] canonical boards, sims int32[T] simulation budget
  * (numMCTSSims or numMCTSSims // ratio_fullMCTS, :55), move_flags uint8[T] of SPL_MCTS_MOVE_* */
 int  spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const uint8_t* move_flags, const uint8_t* tree_select,

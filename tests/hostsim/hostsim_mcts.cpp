@@ -13,6 +13,7 @@ struct HsMcts {
     MctsArena A;
     MctsSearchParams P;
     int edge_reserve, gc_reachable;
+    int clean_every, clean_gc, clean_counter;   // test hook: clean in the middle of a search every N driver steps
     int8_t* leaf_state;
     uint8_t* leaf_valid;
     float *pi, *v;
@@ -62,6 +63,13 @@ void hm_reset(HsMcts* m) {
 }
 // one getActionProb: begin + (descend, [rules, attach], fixed network, expand) until the budget is spent - the same
 // sequence of steps the wave kernels run. Returns the tree status bits.
+static void hm_maybe_clean(HsMcts* m) {
+    if (m->clean_every <= 0) return;
+    if (++m->clean_counter % m->clean_every) return;
+    MctsWarp w{0};
+    mcts_clean_tree(w, m->A, 0, 0, 0, m->clean_gc);      // thresholds 0: always compacts
+}
+void hm_set_clean(HsMcts* m, int every, int gc_reachable) { m->clean_every = every; m->clean_gc = gc_reachable; m->clean_counter = 0; }
 int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const double* dir) {
     MctsWarp w{0};
     alignas(16) int8_t st[640];
@@ -71,6 +79,7 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
     for (;;) {
         int r = 0;
         DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid));
+        hm_maybe_clean(m);
         if (r == 0) break;
         if (r == 3) continue;
         if (r == 2) {
@@ -78,6 +87,7 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
             memset(st, 0, sizeof st);
             DISPATCH(m->n, hm_step_rules<N>(m, st, &ended, es, mask));
             DISPATCH(m->n, r = mcts_attach_tree<N>(w, m->A, 0, m->P, st, ended, es, mask, 1, m->leaf_state, m->leaf_valid));
+            hm_maybe_clean(m);
             if (r == 0) continue;
         }
         DISPATCH(m->n, mcts_fixed_net_row<N>(w, m->leaf_state, m->leaf_valid, m->pi, m->v, scratch));

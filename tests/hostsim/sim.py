@@ -108,6 +108,7 @@ def lib_mcts():
         L.hm_search.argtypes = [C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.c_uint32, C.POINTER(C.c_double)]
         L.hm_policy.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.hm_root_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.hm_set_clean.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hm_fixed_net.argtypes = [C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _lib_mcts = L
     return _lib_mcts
@@ -128,6 +129,10 @@ class TreeSim:
 
     def reset(self):
         lib_mcts().hm_reset(self._h)
+
+    def set_clean(self, every, gc_reachable=False):
+        """test hook: run the between-waves cleaning every `every` driver steps, whatever the search is doing"""
+        lib_mcts().hm_set_clean(self._h, int(every), int(gc_reachable))
 
     def get_action_prob(self, canonical, temp=1.0, full_search=True, dir_values=None):
         st = np.ascontiguousarray(canonical, dtype=np.int8)

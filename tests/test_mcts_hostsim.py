@@ -116,3 +116,39 @@ def test_reachable_gc_keeps_a_consistent_tree(n, seed):
         prev_child_n = int(t["nsa"][a])
         b.swap_players(1)
     assert carried >= 5 and t["compactions"] >= 1
+
+
+@pytest.mark.parametrize("name,every", [("a_n2_plain", 7), ("b_n2_forced_noise", 13), ("c_n3_fpu", 5), ("d_n4_forced", 11), ("f_n2_late", 3)])
+def test_cleaning_in_the_middle_of_a_search_is_result_neutral(golden_dir, name, every):
+    """the periodic cleaning (exact mode: keep ply >= root ply) compacts the pools while a simulation is in flight - after a
+    descent stopped at a pending edge, after an attach produced a leaf, between yields - and re-bases root / cur / leaf /
+    pending edge / path. The search must still reproduce the reference's fixtures exactly."""
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
+    cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
+    m = hs.TreeSim(n, sims, cpuct=cpuct, fpu=fpu, forced_playouts=bool(forced), dirichlet_noise=bool(noise), ratio_full=ratio)
+    m.set_clean(every)
+    for i in range(len(g["ns"])):
+        d = g["dir"][i] if g["dir_len"][i] > 0 else (np.zeros(406) if noise else None)
+        out = m.get_action_prob(g["root"][i], temp=1.0, full_search=bool(g["full"][i]), dir_values=d)
+        _check(out, g, i, name, nodes_exact=False)
+    assert out["compactions"] > 50
+
+
+def test_reachable_cleaning_in_the_middle_of_a_search_keeps_the_tree_consistent():
+    n, sims = 2, 300
+    rng = np.random.default_rng(3)
+    mt = hs.TreeSim(n, sims, cap=4096, cpuct=1.5, fpu=0.2)
+    mt.set_clean(9, gc_reachable=True)
+    b = po.Board(n); b.init_philox(5, 1)
+    for _ in range(20):
+        v = b.valid_moves(0)
+        b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, 5, 1, 0); b.swap_players(1)
+    prev = None
+    for mv in range(8):
+        t = mt.get_action_prob(b.state, temp=1.0, full_search=True)
+        assert t["status"] == 0 and t["nsa"].sum() == t["ns"] and abs(t["probs"].sum() - 1.0) < 1e-12
+        if prev is not None and prev > 1:
+            assert t["ns"] >= sims + prev - 1            # the carried-over subtree kept its statistics
+        a = int(np.argmax(t["nsa"])); prev = int(t["nsa"][a])
+        b.make_move(a, 0, -1, 5, 1, 0); b.swap_players(1)
