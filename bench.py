@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--graph-waves", type=int, default=64, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="reachable", choices=["ply", "reachable"],
                     help="tree cleaning: ply = exact (keeps every node that could still be looked up), reachable = only what the root reaches")
-    ap.add_argument("--clean-moves", type=float, default=2.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")
+    ap.add_argument("--clean-moves", type=float, default=4.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
     ap.add_argument("--max-levels", type=int, default=16, help="edges a descend call walks before it yields to the next wave (0: no limit)")
@@ -277,12 +277,12 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     else:
         net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16)
     reach = args.gc == "reachable"
-    cap = args.node_cap or (6 if reach else 8) * sims
+    cap = args.node_cap or 8 * sims
     G0 = args.graph_waves if args.graph_waves > 0 else 16
     clean_every = max(1, int(args.clean_moves * sims / G0)) if args.async_moves else 0
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
                              edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels,
-                             clean_every=clean_every, clean_percent=50)
+                             clean_every=clean_every, clean_percent=45)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
         eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
@@ -366,7 +366,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
     tr = load_traffic(f"mcts_wave_n{n}_bytes_per_sim")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None if tr is None else tr * T,
-                "kernel": "selection wave (mcts_descend_kernel + mcts_rules_kernel + mcts_attach_kernel)", "avg_launch_ms": sel,
+                "kernel": "selection wave (mcts_expand_descend_kernel + mcts_rules_kernel + mcts_attach_kernel)", "avg_launch_ms": sel,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_sim": B_SIM[n],
                 "note": "one launch = one simulation of every tree; the search is bound by the latency of sequential waves, not bytes",
@@ -426,7 +426,7 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     G = min(16, args.graph_waves) if args.graph_waves > 0 else 16      # short budgets: look for finished lanes every 16 waves
     eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
                              gc_reachable=args.gc == "reachable", graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds,
-                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if args.async_moves else 0)
+                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if args.async_moves else 0, clean_percent=45)
     eng.env.rollout(args.opening_plies, rotate=True)
     ticks = -(-sims // G)
     if args.async_moves:
