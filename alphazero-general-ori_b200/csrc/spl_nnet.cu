@@ -88,6 +88,7 @@ struct NnGroupSmem {
     __nv_bfloat16 vec[3][NN_SB * ASTR];
 };
 struct NnSmem {
+    float prm[P_TOTAL];                      // biases / BatchNorm terms: read in every epilogue, so not from L2
     NnGroupSmem grp[NN_GROUPS];
     unsigned char slot[NN_SLOTS][SLOT_BYTES];
 };
@@ -197,6 +198,9 @@ __device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], const
     }
 }
 
+__device__ long long g_nn_stamps[32];   // diagnostics: phase time stamps of CTA 0 (SM clock), read by spl_nnet_debug_stamps
+#define NN_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_nn_stamps[i] = clock64(); } while (0)
+
 template <int NP>
 __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsigned char* __restrict__ blob, NnPlan plan, const int8_t* __restrict__ states,
                                                                      const uint8_t* __restrict__ valids, int n_rows, float* __restrict__ pi,
@@ -204,11 +208,13 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     constexpr int R = 32 + 10 * NP + NP * NP, S = 7 * R, K1 = (R + 15) / 16 * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NnSmem& smem_all = *reinterpret_cast<NnSmem*>(smem_raw);
-    const float* prm = reinterpret_cast<const float*>(blob);
+    const float* prm = smem_all.prm;
+    for (int i = threadIdx.x; i < P_TOTAL; i += NN_THREADS) smem_all.prm[i] = reinterpret_cast<const float*>(blob)[i];
     const int tid = threadIdx.x, group = tid >> 8, gtid = tid & 255, warp = gtid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     NnGroupSmem& sm = smem_all.grp[group];
     const int base = (blockIdx.x * NN_GROUPS + group) * NN_SB;
     const int live = max(0, min(NN_SB, n_rows - base));
+    NN_STAMP(0);
 
     // ---- weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
     auto issue = [&](int b) {
@@ -217,17 +223,20 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         for (int i = tid * 16; i < plan.bytes[b]; i += NN_THREADS * 16) cp_async16(dst + i, src + i);
         cp_async_commit();
     };
-    for (int b = 0; b < NN_SLOTS - 1; b++) issue(b);
-    auto acquire = [&](int b) -> const __nv_bfloat16* {   // block b ready for every thread; up to NN_SLOTS - 1 blocks in flight
-        if (b + NN_SLOTS - 1 < plan.nblocks) issue(b + NN_SLOTS - 1);   // its slot was released at the end of step b - 1
-        const int ahead = min(NN_SLOTS - 1, plan.nblocks - 1 - b);
-        if (ahead >= 3) cp_async_wait<3>();
-        else if (ahead == 2) cp_async_wait<2>();
-        else if (ahead == 1) cp_async_wait<1>();
+    int next_issue = 0;
+    // blocks [b, b + count) ready for every thread; the ring stays full (everything before b has been released)
+    auto acquire = [&](int b, int count) -> const __nv_bfloat16* {
+        const int upto = min(plan.nblocks, b + NN_SLOTS);
+        while (next_issue < upto) issue(next_issue++);
+        const int pending = next_issue - (b + count);      // groups that may still be in flight
+        if (pending >= 3) cp_async_wait<3>();
+        else if (pending == 2) cp_async_wait<2>();
+        else if (pending == 1) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncthreads();
         return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]);
     };
+    auto slot_of = [&](int b) -> const __nv_bfloat16* { return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]); };
     auto release = [&]() { __syncthreads(); };
 
     // ---- input: act[c*16 + s][k] = state[s][k][c]  (int8 counts are exact in bf16), zero padding up to K1
@@ -240,6 +249,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     }
     __syncthreads();
 
+    NN_STAMP(1);
     uint32_t afr[8][4];
     __nv_bfloat16* arow = sm.act + warp * 16 * ASTR;   // this warp's strip (stage A, warps 0..6)
     const bool strip = warp < 7;
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         if (strip) load_afrags<K1 / 16>(afr, arow, ASTR, lane);
         __syncwarp();
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk);
+            const __nv_bfloat16* w = acquire(blk, 1);
             if (strip)
                 strip_gemm<K1 / 16>(afr, w, K1 + 8, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         if (strip) load_afrags<8>(afr, arow, ASTR, lane);
         __syncwarp();
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk);
+            const __nv_bfloat16* w = acquire(blk, 1);
             if (strip)
                 strip_gemm<8>(afr, w, ASTR, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
@@ -278,7 +288,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             release(); blk++;
         }
     };
+    NN_STAMP(2);
     dense_relu_strip(P_B2);
+    NN_STAMP(3);
     // ---- G1: DenseAndPartialGPool(128 -> 128; 4 groups of 8 max+avg, Linear(96,120)+BN(7)+ReLU)
     {
         const float sg = strip ? prm[P_SG1 + warp] : 0.f, tg = strip ? prm[P_TG1 + warp] : 0.f;
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             }
         }
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk);
+            const __nv_bfloat16* w = acquire(blk, 1);
             if (strip)
                 strip_gemm<6>(afr, w, 96 + 8, lane, [&](int nt, float (&c)[4]) {
                     const int n = h * 64 + nt * 8 + 2 * t;
@@ -322,39 +334,39 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             release(); blk++;
         }
     }
+    NN_STAMP(4);
     dense_relu_strip(P_B3);
+    NN_STAMP(5);
 
     // ---- FlattenAndPartialGPool(64, 5): [max over the 5 gem colours | mean | gold, points rows | last 64 features of all 7]
-    for (int i = gtid; i < NN_SB * 704; i += 256) {
-        const int s = i / 704, f = i - s * 704;
-        float x;
-        if (f < 128) {
-            const int j = f & 63;
-            float mx = -INFINITY, sum = 0.f;
+    for (int i = gtid; i < NN_SB * 64; i += 256) {          // first 64 features of every row: pooled over the colour rows
+        const int s = i >> 6, j = i & 63;
+        float a[7];
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const float a = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
-                mx = fmaxf(mx, a); sum += a;
-            }
-            x = f < 64 ? mx : sum * 0.2f;
-        } else if (f < 256) {
-            const int c = 5 + ((f - 128) >> 6), j = (f - 128) & 63;
-            x = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
-        } else {
-            const int c = (f - 256) >> 6, j = 64 + ((f - 256) & 63);
-            x = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
-        }
-        sm.flat[s * FSTR + f] = __float2bfloat16(x);
+        for (int c = 0; c < 7; c++) a[c] = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
+        const float mx = fmaxf(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])), a[4]);
+        const float sum = a[0] + a[1] + a[2] + a[3] + a[4];
+        __nv_bfloat16* o = sm.flat + s * FSTR + j;
+        o[0] = __float2bfloat16(mx); o[64] = __float2bfloat16(sum * 0.2f);
+        o[128] = __float2bfloat16(a[5]); o[192] = __float2bfloat16(a[6]);
+    }
+    for (int i = gtid; i < NN_SB * 7 * 32; i += 256) {      // last 64 features of all 7 rows: copied, two at a time
+        const int s = i / 224, r = i - s * 224, c = r >> 5, jj = (r & 31) * 2;
+        *reinterpret_cast<uint32_t*>(sm.flat + s * FSTR + 256 + c * 64 + jj) =
+            *reinterpret_cast<const uint32_t*>(sm.act + (c * 16 + s) * ASTR + 64 + jj);
     }
     __syncthreads();
 
+    NN_STAMP(6);
     // ---- L4: Linear(704,128) + ReLU. 16 rows; warp w owns output tiles 2w, 2w+1; accumulate over 11 k-blocks
     {
         float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int kb = 0; kb < 11; kb++) {
-            const __nv_bfloat16* w = acquire(blk);
-            tile2_gemm<4>(c0, c1, sm.flat + kb * 64, FSTR, w + (2 * warp) * 8 * 72, 72, lane);
-            release(); blk++;
+        for (int kb = 0; kb < 11; kb += 2) {   // two k-blocks per ring step
+            const int cnt = kb + 1 < 11 ? 2 : 1;
+            acquire(blk, cnt);
+            for (int q = 0; q < cnt; q++)
+                tile2_gemm<4>(c0, c1, sm.flat + (kb + q) * 64, FSTR, slot_of(blk + q) + (2 * warp) * 8 * 72, 72, lane);
+            release(); blk += cnt;
         }
         __nv_bfloat16* o = sm.vec[0];
 #pragma unroll
@@ -367,10 +379,12 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         }
         __syncthreads();
     }
-    // stage B helpers: in -> out, two [64 n][KB] blocks, warp w owns tile w of each block
+    // stage B helpers: in -> out, the two [64 n][KB] blocks of a layer in ONE ring step, warp w owns tile w of each block
     auto dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias, bool relu) {
+        acquire(blk, 2);
+#pragma unroll
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk);
+            const __nv_bfloat16* w = slot_of(blk + h);
             float c[4] = {0.f, 0.f, 0.f, 0.f};
             tile_gemm<8>(c, in, ASTR, w + warp * 8 * ASTR, ASTR, lane);
             const int n = h * 64 + warp * 8 + 2 * t;
@@ -379,8 +393,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
             sts_bf16x2(out + g * ASTR + n, v0, v1);
             sts_bf16x2(out + (g + 8) * ASTR + n, v2, v3);
-            release(); blk++;
         }
+        release(); blk += 2;
     };
     auto pool_dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias) {   // 4 groups of 4 + Linear(112,120)+BN(1)+ReLU
         if (gtid < 64) {
@@ -391,8 +405,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             out[row * ASTR + grp] = __float2bfloat16(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)));
             out[row * ASTR + 4 + grp] = __float2bfloat16((a.x + a.y + b.x + b.y) * 0.25f);
         }
+        acquire(blk, 2);
+#pragma unroll
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk);
+            const __nv_bfloat16* w = slot_of(blk + h);
             float c[4] = {0.f, 0.f, 0.f, 0.f};
             tile_gemm<7>(c, in + 16, ASTR, w + warp * 8 * 120, 120, lane);
             const int n = h * 64 + warp * 8 + 2 * t;
@@ -401,9 +417,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
                 sts_bf16x2(out + g * ASTR + 8 + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
                 sts_bf16x2(out + (g + 8) * ASTR + 8 + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
             }
-            release(); blk++;
         }
+        release(); blk += 2;
     };
+    NN_STAMP(7);
     pool_dense_vec(sm.vec[0], sm.vec[1], P_BG4);
     dense_vec(sm.vec[1], sm.vec[0], P_B5A, true);
     dense_vec(sm.vec[0], sm.vec[1], P_B5B, true);
@@ -411,23 +428,28 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     dense_vec(sm.vec[0], sm.vec[1], P_BP0, false);   // output_layers_PI.0 (no activation)
     dense_vec(sm.vec[0], sm.vec[2], P_BV0, false);   // output_layers_V.0
 
+    NN_STAMP(8);
     // ---- PI1: 128 -> 406 logits (fp32, in the former activation buffer), 7 blocks of 64 rows
     float* logits = reinterpret_cast<float*>(sm.act);
-    for (int h = 0; h < 7; h++) {
-        const __nv_bfloat16* w = acquire(blk);
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_gemm<8>(c, sm.vec[1], ASTR, w + warp * 8 * ASTR, ASTR, lane);
-        const int n = h * 64 + warp * 8 + 2 * t;
-        if (n < LSTR) {
-            const float b0 = prm[P_BP1 + n], b1 = prm[P_BP1 + n + 1];
-            logits[g * LSTR + n] = c[0] + b0; logits[g * LSTR + n + 1] = c[1] + b1;
-            logits[(g + 8) * LSTR + n] = c[2] + b0; logits[(g + 8) * LSTR + n + 1] = c[3] + b1;
+    for (int h = 0; h < 7; h += 2) {   // two 64-row blocks per ring step
+        const int cnt = h + 1 < 7 ? 2 : 1;
+        acquire(blk, cnt);
+        for (int q = 0; q < cnt; q++) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_gemm<8>(c, sm.vec[1], ASTR, slot_of(blk + q) + warp * 8 * ASTR, ASTR, lane);
+            const int n = (h + q) * 64 + warp * 8 + 2 * t;
+            if (n < LSTR) {
+                const float b0 = prm[P_BP1 + n], b1 = prm[P_BP1 + n + 1];
+                logits[g * LSTR + n] = c[0] + b0; logits[g * LSTR + n + 1] = c[1] + b1;
+                logits[(g + 8) * LSTR + n] = c[2] + b0; logits[(g + 8) * LSTR + n + 1] = c[3] + b1;
+            }
         }
-        release(); blk++;
+        release(); blk += cnt;
     }
+    NN_STAMP(9);
     // ---- V1: 128 -> n, tanh
     {
-        const __nv_bfloat16* w = acquire(blk);
+        const __nv_bfloat16* w = acquire(blk, 1);
         if (warp == 0) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
             tile_gemm<8>(c, sm.vec[2], ASTR, w, ASTR, lane);
@@ -440,6 +462,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         }
         release(); blk++;
     }
+    NN_STAMP(10);
     // ---- masked softmax: log_softmax(where(valid, pi, -1e8)) then exp (SplendorNNet.py:153-159, GenericNNetWrapper.py:166)
     for (int s = warp * 2; s < warp * 2 + 2; s++) {
         if (s >= live) continue;
@@ -468,6 +491,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             if (a < NN_ACTIONS) pi[(size_t)(base + s) * NN_ACTIONS + a] = x[j] * inv;
         }
     }
+    NN_STAMP(11);
 }
 
 // ------------------------------------------------------------------------------------------ host: BatchNorm folding + blob packing
@@ -554,6 +578,12 @@ int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_
     for (int h = 0; h < 7; h++) { pack_block(B + p.off[b], T[40], NN_ACTIONS, 128, h * 64, 64, 0, 128, 1.0); b++; }
     pack_block(B + p.off[b], T[44], n_players, 128, 0, 64, 0, 128, 1.0); b++;
     if (b != p.nblocks) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: internal block count mismatch");
+    return SPL_OK;
+}
+
+int spl_nnet_debug_stamps(long long* out32) {   /* diagnostics only: SM-clock stamps of the last launch's CTA 0 */
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out32, g_nn_stamps, sizeof(long long) * 32));
     return SPL_OK;
 }
 

@@ -250,6 +250,8 @@ int spl_nnet_pack(int n_players, const float* const* tensors, void* blob_host, s
  * packed weights (16-byte aligned) */
 int spl_nnet_forward(spl_ctx* ctx, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v,
                      void* stream);
+/* diagnostics: SM-clock time stamps of the phases of CTA 0 in the last spl_nnet_forward launch (long long[32]) */
+int spl_nnet_debug_stamps(long long* out32);
 
 #ifdef __cplusplus
 }

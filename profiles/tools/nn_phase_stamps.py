@@ -1,0 +1,15 @@
+import ctypes as C, numpy as np, torch, sys
+sys.path.insert(0, __import__("os").path.realpath(__import__("os").path.join(__import__("os").path.dirname(__file__), "..", "..")))
+import azg_b200
+net = azg_b200.FusedSplendorNNet(2, seed=1)
+env = azg_b200.SplendorEnv(2, 4096, seed=3); env.reset(); env.rollout(30, rotate=True)
+st = env.states(); env.step(None, store_state=False, want_ended=False, want_status=False); va = env.valids()
+for _ in range(5): net(st, va)
+torch.cuda.synchronize()
+buf = (C.c_longlong * 32)()
+lib = azg_b200._native.lib(); lib.spl_nnet_debug_stamps.argtypes=[C.c_void_p]
+lib.spl_nnet_debug_stamps(buf)
+s = np.array(buf[:12], dtype=np.int64)
+names = ["start->input", "input+L1", "L2", "G1", "L3", "flatten", "L4", "G4..V0", "PI1", "V1", "softmax"]
+d = np.diff(s) / 1.965e3
+print("us per phase:", dict(zip(names, np.round(d, 2))), "total", round((s[11]-s[0])/1.965e3, 2))

@@ -307,7 +307,8 @@ def test_selfplay_async_moves():
     az = _azg()
     from oracle import pyoracle as po
     n, T, sims = 2, 128, 24
-    eng = az.SelfPlayEngine(n, T, None, sims, seed=11, cpuct=1.0, node_cap=512, record_examples=True, max_levels=3, graph_waves=0)
+    eng = az.SelfPlayEngine(n, T, None, sims, seed=11, cpuct=1.0, node_cap=512, record_examples=True, max_levels=3, graph_waves=0,
+                            gc_reachable=True, clean_every=3, clean_percent=10)    # also: the between-waves cleaning, often
     eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v)
     eng.env.rollout(70, rotate=True)
     eng.start_async()
@@ -326,4 +327,36 @@ def test_selfplay_async_moves():
         assert abs(pi[e].sum() - 1.0) < 1e-5 and (pi[e][~valids[e].astype(bool)] == 0).all()
         assert scdiff[e][0] == 0 and ((winner[e] == 1.0) | (winner[e] == np.float32(0.01))).any()
     st = eng.arena.root_stats(want_arrays=False)
-    assert int(st["status"].max()) == 0
+    assert int(st["status"].max()) == 0 and int(st["cleanings"].sum()) > T and int(st["resets"].sum()) == 0
+
+
+def test_cleaning_between_waves_is_result_neutral_on_the_device(golden_dir):
+    """spl_mcts_clean (exact mode) after every few waves of a fixture search - simulations in flight get re-based - must not
+    change a single visit count (the host-simulator test does the same with a one-lane warp)"""
+    az = _azg()
+    name = "b_n2_forced_noise"
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
+    cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
+    T = 4
+    ar = az.MCTSArena(n, T, node_cap=4096, cpuct=cpuct, fpu=fpu, max_levels=5)
+    dev = ar.device
+    for i in range(len(g["ns"])):
+        roots = torch.from_numpy(np.repeat(g["root"][i][None], T, 0)).to(dev)
+        simt = torch.full((T,), sims, dtype=torch.int32, device=dev)
+        flt = torch.full((T,), 3, dtype=torch.uint8, device=dev)
+        dirv = torch.from_numpy(np.repeat(g["dir"][i][None], T, 0)).to(dev).contiguous()
+        ar.begin(roots, simt, flt, None, dirv)
+        ar.select()
+        for w in range(sims):
+            pi, v = ar.fixed_net()
+            ar.expand_select(pi, v, dirv)
+            if w % 5 == 2:
+                ar.clean(0)                      # threshold 0: every tree compacts, whatever its search is doing
+        ar.finish(lambda s, v: ar.fixed_net(s, v), dirv)
+        ar.check_status()
+        st = ar.root_stats()
+        for t in range(T):
+            assert np.array_equal(_np(st["nsa"][t]).astype(np.int64), g["nsa"][i]), (i, t)
+            assert np.allclose(_np(st["qsa"][t]), g["qsa"][i], rtol=0, atol=1e-12)
+        assert int(st["cleanings"].min()) > 10 * (i + 1)
