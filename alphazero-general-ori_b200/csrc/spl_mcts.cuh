@@ -656,6 +656,63 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
 // ------------------------------------------------------------------------------------------
 // start of a move: find or create the root; make room first if the pools could run out
 // ------------------------------------------------------------------------------------------
+// re-bases the simulation in flight after the nodes moved: remap[old] = new index + 1, nodes[] already at their new places;
+// path edge entries were made node-relative beforehand (mcts_path_make_relative)
+template <class W>
+SPL_D int mcts_path_make_relative(const W& w, const MctsArena& A, int t, int* pend_rel) {
+    MctsTree* T = A.trees + t;
+    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    const bool in_flight = T->leaf >= 0 || T->cur >= 0 || T->pend_edge >= 0;
+    const int plen = in_flight ? T->path_len : 0;
+    for (int d = w.lane; d < plen; d += W::W) path[2 * d + 1] -= nodes[path[2 * d]].edge_off;
+    *pend_rel = T->pend_edge >= 0 ? T->pend_edge - (int)nodes[T->pend_parent].edge_off : -1;
+    w.sync();
+    return plen;
+}
+template <class W>
+SPL_D void mcts_rebase_in_flight(const W& w, const MctsArena& A, int t, const uint32_t* remap, int plen, int pend_rel) {
+    MctsTree* T = A.trees + t;
+    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    for (int d = w.lane; d < plen; d += W::W) {
+        const uint32_t nn = remap[path[2 * d]] - 1u;
+        path[2 * d] = nn;
+        path[2 * d + 1] += nodes[nn].edge_off;
+    }
+    if (w.lane == 0) {
+        if (T->root >= 0) T->root = (int)remap[T->root] - 1;       // (-1 if the root itself was dropped: begin re-creates it)
+        if (T->leaf >= 0) T->leaf = (int)remap[T->leaf] - 1;
+        if (T->cur >= 0) T->cur = (int)remap[T->cur] - 1;
+        if (pend_rel >= 0) {
+            T->pend_parent = (int)remap[T->pend_parent] - 1;
+            T->pend_edge = (int)nodes[T->pend_parent].edge_off + pend_rel;
+        }
+    }
+    w.sync();
+}
+
+// hash table from scratch for nodes [0, n): the lanes insert concurrently (compare-and-swap on the slots)
+template <class W>
+SPL_D void mcts_rebuild_table(const W& w, const MctsArena& A, int t, int n) {
+    uint32_t* tab = A.htab + (size_t)t * A.hcap;
+    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    for (int i = w.lane; i < A.hcap; i += W::W) tab[i] = 0u;
+    w.sync();
+    for (int i = w.lane; i < n; i += W::W) {
+        uint32_t slot = (uint32_t)nodes[i].hash & (uint32_t)(A.hcap - 1);
+        for (;;) {
+#ifdef __CUDACC__
+            if (atomicCAS(&tab[slot], 0u, (uint32_t)i + 1u) == 0u) break;
+#else
+            if (tab[slot] == 0u) { tab[slot] = (uint32_t)i + 1u; break; }
+#endif
+            slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
+        }
+    }
+    w.sync();
+}
+
 // In-place compaction keeping nodes with ply >= min_ply. A node below the root's ply can never be looked up again
 // (every key carries its ply), so this is result-neutral - the reference's own cleaning (:80-85) relies on the same
 // fact. Node indices and edge offsets both grow in creation order, so every block only moves towards the front.
@@ -679,13 +736,8 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
     // a simulation may be in flight (the periodic cleaning runs between waves): its references into the pools - root,
     // cur, leaf, the pending edge and the recorded path - are re-based with the nodes. Edge references become
     // (node, position inside the node) while the blocks move.
-    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-    const bool in_flight = T->leaf >= 0 || T->cur >= 0 || T->pend_edge >= 0;
-    const int plen = in_flight ? T->path_len : 0;
-    for (int d = w.lane; d < plen; d += W::W) path[2 * d + 1] -= nodes[path[2 * d]].edge_off;
-    int pend_rel = -1;
-    if (T->pend_edge >= 0) pend_rel = T->pend_edge - (int)nodes[T->pend_parent].edge_off;
-    w.sync();
+    int pend_rel;
+    const int plen = mcts_path_make_relative(w, A, t, &pend_rel);
     int e_new = 0;
     for (int i = 0; i < n_old; i++) {
         const uint32_t r = remap[i];
@@ -727,30 +779,9 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
         if (e->child) e->child_eoff = nodes[e->child - 1u].edge_off;
     }
     w.sync();
-    for (int d = w.lane; d < plen; d += W::W) {
-        const uint32_t nn = remap[path[2 * d]] - 1u;
-        path[2 * d] = nn;
-        path[2 * d + 1] += nodes[nn].edge_off;
-    }
+    mcts_rebase_in_flight(w, A, t, remap, plen, pend_rel);
+    mcts_rebuild_table(w, A, t, n_new);
     if (w.lane == 0) {
-        if (T->root >= 0) T->root = (int)remap[T->root] - 1;       // (-1 if the root itself was dropped: begin re-creates it)
-        if (T->leaf >= 0) T->leaf = (int)remap[T->leaf] - 1;
-        if (T->cur >= 0) T->cur = (int)remap[T->cur] - 1;
-        if (pend_rel >= 0) {
-            T->pend_parent = (int)remap[T->pend_parent] - 1;
-            T->pend_edge = (int)nodes[T->pend_parent].edge_off + pend_rel;
-        }
-    }
-    w.sync();
-    for (int i = w.lane; i < A.hcap; i += W::W) remap[i] = 0u;
-    w.sync();
-    if (w.lane == 0) {
-        uint32_t* tab = remap;
-        for (int i = 0; i < n_new; i++) {
-            uint32_t slot = (uint32_t)nodes[i].hash & (uint32_t)(A.hcap - 1);
-            while (tab[slot] != 0u) slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
-            tab[slot] = (uint32_t)i + 1u;
-        }
         T->n_nodes = n_new;
         T->n_edges = e_new;
         T->compactions += 1;
@@ -758,11 +789,12 @@ SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool
     w.sync();
 }
 
-// marks (in the hash-table region, which the compaction rebuilds anyway) every node reachable from `root` through
-// linked edges: breadth-first, one node per step, its edges spread over the lanes. Tighter than the ply rule, but it
-// also drops nodes that a not-yet-linked edge could still transpose into (production mode; see mcts_begin_tree).
+// numbers (in the hash-table region, which the compaction rebuilds anyway) every node reachable from `root` through
+// linked edges in breadth-first order: mark[old index] = position + 1, queue[position] = old index; returns the count.
+// Frontier nodes are expanded 32 at a time, one lane per node, edge position by edge position, so the numbering is
+// deterministic. Tighter than the ply rule, but it also drops nodes that a not-yet-linked edge could still transpose into.
 template <class W>
-SPL_D void mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) {
+SPL_D int mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) {
     MctsTree* T = A.trees + t;
     const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
     const MctsEdge* edges = A.edges + (size_t)t * A.ecap;
@@ -774,30 +806,138 @@ SPL_D void mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) 
     w.sync();
     int head = 0, tail = 1;
     while (head < tail) {
-        const MctsNode nd = nodes[queue[head++]];
-        const int ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
-        for (int c = 0; c < ne; c += W::W) {
-            const int k = c + w.lane;
+        const int q = head + w.lane;
+        const int level_end = tail;          // nodes numbered so far; this pass expands queue[head .. min(head + W, tail))
+        int ne = 0;
+        uint32_t eoff = 0u;
+        if (q < level_end) {
+            const MctsNode nd = nodes[queue[q]];
+            ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
+            eoff = nd.edge_off;
+        }
+        int max_ne = ne;
+#ifdef __CUDACC__
+        max_ne = __reduce_max_sync(0xffffffffu, max_ne);
+#endif
+        for (int k = 0; k < max_ne; k++) {
             bool fresh = false;
             uint32_t child = 0u;
             if (k < ne) {
-                child = edges[nd.edge_off + k].child;
+                child = edges[eoff + k].child;
                 if (child) {
 #ifdef __CUDACC__
-                    fresh = atomicExch(&mark[child - 1u], 1u) == 0u;
+                    fresh = atomicCAS(&mark[child - 1u], 0u, 0xFFFFFFFFu) == 0u;
 #else
                     fresh = mark[child - 1u] == 0u;
-                    mark[child - 1u] = 1u;
+                    if (fresh) mark[child - 1u] = 0xFFFFFFFFu;
 #endif
                 }
             }
             const uint32_t b = w.ballot(fresh);
-            if (fresh) queue[tail + SPL_POPC(b & w.lanemask_lt())] = child - 1u;
+            if (fresh) {
+                const int pos = tail + SPL_POPC(b & w.lanemask_lt());
+                queue[pos] = child - 1u;
+                mark[child - 1u] = (uint32_t)pos + 1u;
+            }
             tail += SPL_POPC(b);
             w.sync();
         }
+        head = level_end < head + W::W ? level_end : head + W::W;
     }
     w.sync();
+    return tail;
+}
+
+// Reachable cleaning, fast path: the reachable nodes (numbered breadth-first by mcts_mark_reachable, n_live of them) are
+// copied through the FREE TAIL of the pools - out to [n_old, n_old + n_live), then back to the front - so every copy is
+// independent: one lane per node, no ordering constraints (the in-place mcts_compact walks the nodes one by one).
+// New node index = breadth-first position; edge blocks follow in that order, so offsets still grow with the index.
+// Returns false (nothing changed) when the tails are too small; the caller then compacts in place.
+template <class W>
+SPL_D bool mcts_compact_reachable(const W& w, const MctsArena& A, int t, int n_live) {
+    MctsTree* T = A.trees + t;
+    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+    uint32_t* mark = A.htab + (size_t)t * A.hcap;
+    const uint32_t* queue = mark + A.cap;
+    int8_t* states = A.states + (size_t)t * A.cap * A.sp;
+    const int n_old = T->n_nodes, e_old = T->n_edges;
+    if (n_old + n_live > A.cap) return false;
+    int live_edges = 0;
+    for (int q = w.lane; q < n_live; q += W::W) {
+        const MctsNode nd = nodes[queue[q]];
+        live_edges += nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
+    }
+    live_edges = w.sum(live_edges);
+    if (e_old + live_edges > A.ecap) return false;
+    int pend_rel;
+    const int plen = mcts_path_make_relative(w, A, t, &pend_rel);
+    // pass 1: out to the tails (headers with their new edge offsets, states, edges with re-numbered children)
+    int ebase = 0;
+    for (int base = 0; base < n_live; base += W::W) {
+        const int q = base + w.lane;
+        MctsNode nd;
+        int ne = 0, old = 0;
+        if (q < n_live) {
+            old = (int)queue[q];
+            nd = nodes[old];
+            ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
+        }
+        int incl = ne;   // inclusive scan of the edge counts over the lanes
+#ifdef __CUDACC__
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (w.lane >= o) incl += v;
+        }
+#endif
+        const int new_off = ebase + incl - ne;
+        if (q < n_live) {
+            const uint32_t old_off = nd.edge_off;
+            if (nd.kind != MCTS_NODE_TERMINAL) nd.edge_off = (uint32_t)new_off;
+            nodes[n_old + q] = nd;
+            const uint4* s4 = reinterpret_cast<const uint4*>(states + (size_t)old * A.sp);
+            uint4* d4 = reinterpret_cast<uint4*>(states + (size_t)(n_old + q) * A.sp);
+            for (int k = 0; k < A.sp / 16; k++) d4[k] = s4[k];
+            for (int k = 0; k < ne; k++) {
+                MctsEdge e = edges[old_off + k];
+                if (e.child) e.child = mark[e.child - 1u];
+                edges[e_old + new_off + k] = e;
+            }
+        }
+#ifdef __CUDACC__
+        ebase += __shfl_sync(0xffffffffu, incl, 31);
+#else
+        ebase += incl;
+#endif
+        w.sync();
+    }
+    // pass 2: back to the front
+    for (int q = w.lane; q < n_live; q += W::W) {
+        nodes[q] = nodes[n_old + q];
+        const uint4* s4 = reinterpret_cast<const uint4*>(states + (size_t)(n_old + q) * A.sp);
+        uint4* d4 = reinterpret_cast<uint4*>(states + (size_t)q * A.sp);
+        for (int k = 0; k < A.sp / 16; k++) d4[k] = s4[k];
+    }
+    w.sync();
+    for (int k = w.lane; k < live_edges; k += W::W) {
+        MctsEdge e = edges[e_old + k];
+        if (e.child) e.child_eoff = nodes[e.child - 1u].edge_off;
+        edges[k] = e;
+    }
+    w.sync();
+    mcts_rebase_in_flight(w, A, t, mark, plen, pend_rel);
+    mcts_rebuild_table(w, A, t, n_live);
+    if (w.lane == 0) { T->n_nodes = n_live; T->n_edges = live_edges; T->compactions += 1; }
+    w.sync();
+    return true;
+}
+
+// reachable cleaning of tree t from `root`: fast path if the pools have room for it, in place otherwise
+template <class W>
+SPL_D void mcts_clean_reachable(const W& w, const MctsArena& A, int t, int root, bool in_place_only) {
+    const int n_live = mcts_mark_reachable(w, A, t, root);
+    if (in_place_only || !mcts_compact_reachable(w, A, t, n_live)) mcts_compact(w, A, t, 0, true);
 }
 
 // periodic cleaning between waves (any state of the search): trees whose pools are filled beyond the thresholds drop
@@ -807,12 +947,8 @@ template <class W>
 SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes, int max_edges, int gc_reachable) {
     MctsTree* T = A.trees + t;
     if (T->root < 0 || (T->n_nodes <= max_nodes && T->n_edges <= max_edges)) return;
-    if (gc_reachable) {
-        mcts_mark_reachable(w, A, t, T->root);
-        mcts_compact(w, A, t, 0, true);
-    } else {
-        mcts_compact(w, A, t, (int)A.nodes[(size_t)t * A.cap + T->root].ply, false);
-    }
+    if (gc_reachable) mcts_clean_reachable(w, A, t, T->root, gc_reachable == 2);
+    else mcts_compact(w, A, t, (int)A.nodes[(size_t)t * A.cap + T->root].ply, false);
 }
 
 template <class W>
@@ -851,8 +987,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
         if (gc_reachable) {
             const int old_root = mcts_lookup(w, A, t, st, h);
             if (old_root >= 0) {
-                mcts_mark_reachable(w, A, t, old_root);
-                mcts_compact(w, A, t, 0, true);
+                mcts_clean_reachable(w, A, t, old_root, gc_reachable == 2);
             } else {   // a root the tree has never seen (a card was revealed): nothing of the old tree can be reached
                 const int resets = T->resets;
                 mcts_clear_tree(w, A, t);
@@ -867,8 +1002,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
                 // nodes that only a not-yet-linked edge could transpose into are dropped)
                 const int old_root = mcts_lookup(w, A, t, st, h);
                 if (old_root >= 0) {
-                    mcts_mark_reachable(w, A, t, old_root);
-                    mcts_compact(w, A, t, 0, true);
+                    mcts_clean_reachable(w, A, t, old_root, false);
                     if (w.lane == 0) T->resets += 1;
                     w.sync();
                 }

@@ -120,7 +120,7 @@ class TreeSim:
     def __init__(self, n, num_sims, cpuct=1.0, fpu=0.0, forced_playouts=False, dirichlet_noise=False, ratio_full=5,
                  temperature0=1.0, cap=4096, ecap=None, edge_reserve=32, gc_reachable=False, limit=10, flags=F_RESERVE | F_GIVEBACK | F_REFCOMPAT):
         self.n, self.num_sims, self.forced, self.noise, self.ratio = n, num_sims, forced_playouts, dirichlet_noise, ratio_full
-        self._h = lib_mcts().hm_create(n, cap, ecap or cap * 48, limit, flags, cpuct, fpu, temperature0, edge_reserve, int(gc_reachable))
+        self._h = lib_mcts().hm_create(n, cap, ecap or cap * 48, limit, flags, cpuct, fpu, temperature0, edge_reserve, int(gc_reachable))   # gc_reachable: 0 ply rule, 1 reachable, 2 reachable, in place only
 
     def __del__(self):
         if getattr(self, "_h", None):

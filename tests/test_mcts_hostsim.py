@@ -152,3 +152,27 @@ def test_reachable_cleaning_in_the_middle_of_a_search_keeps_the_tree_consistent(
             assert t["ns"] >= sims + prev - 1            # the carried-over subtree kept its statistics
         a = int(np.argmax(t["nsa"])); prev = int(t["nsa"][a])
         b.make_move(a, 0, -1, 5, 1, 0); b.swap_players(1)
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_reachable_fast_path_equals_in_place(n):
+    """the out-of-place reachable compaction (breadth-first renumbering through the free tail of the pools) and the in-place
+    one keep the same set of nodes, so every later search must be identical - also when they run in the middle of a search"""
+    rng = np.random.default_rng(20 + n)
+    sims = 220
+    sims_a = hs.TreeSim(n, sims, cap=4096, cpuct=1.3, fpu=0.1, gc_reachable=1)
+    sims_b = hs.TreeSim(n, sims, cap=4096, cpuct=1.3, fpu=0.1, gc_reachable=2)
+    sims_a.set_clean(17, gc_reachable=1)
+    sims_b.set_clean(17, gc_reachable=2)
+    b = po.Board(n); b.init_philox(8, n)
+    for _ in range(18):
+        v = b.valid_moves(0)
+        b.make_move(int(rng.choice(np.flatnonzero(v))), 0, -2, 8, n, 0); b.swap_players(1)
+    for mv in range(6):
+        ta = sims_a.get_action_prob(b.state, temp=1.0, full_search=True)
+        tb = sims_b.get_action_prob(b.state, temp=1.0, full_search=True)
+        assert ta["status"] == 0 and tb["status"] == 0
+        assert np.array_equal(ta["nsa"], tb["nsa"]) and np.array_equal(ta["qsa"], tb["qsa"]) and ta["ns"] == tb["ns"]
+        assert ta["nodes"] == tb["nodes"] and ta["edges"] == tb["edges"] and ta["compactions"] == tb["compactions"] > 0
+        a = int(np.argmax(ta["nsa"]))
+        b.make_move(a, 0, -1, 8, n, 0); b.swap_players(1)
