@@ -414,7 +414,32 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     line["e2e"] = {"value": world * T * sims * ke / float(t.item()), "unit": UNIT_MCTS, "h2d_bytes_per_step": h2d // ke, "d2h_bytes_per_step": d2h // ke,
                    "call": "MCTSArena.get_action_prob_batch(host boards) -> host probs/q, then SplendorGame.getNextStateBatch(host boards, actions)",
                    "steps": ke}
+    if world > 1:
+        line["example_exchange"] = check_example_exchange(args, torch, dist, azg, world, rank, local)
     return line, eng
+
+
+def check_example_exchange(args, torch, dist, azg, world, rank, local):
+    """multi-GPU only: a short recorded self-play on every rank, then the per-iteration all-gather of the
+    finished-game examples over NCCL; every rank must end up with the same concatenation"""
+    n, T = args.players, 256
+    net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
+    eng = azg.SelfPlayEngine(n, T, net, 8, device=local, seed=args.seed, game_base=rank * T, node_cap=128, record_examples=True)
+    eng.env.rollout(40 * n, rotate=True)
+    eng.examples.cur_player.zero_()
+    for _ in range(40):
+        eng.play_move()
+    mine = eng.drain_examples(symmetries=True)
+    allx = azg.examples.gather_examples(mine)
+    local_n, total = int(mine["board"].shape[0]), int(allx["board"].shape[0])
+    chk = torch.tensor([float(allx["pi"].double().sum().item()), float(allx["board"].double().abs().sum().item())], dtype=torch.float64,
+                       device=f"cuda:{local}")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([local_n], dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(cnt)
+    return {"examples_local_rank0": local_n, "examples_gathered": total, "sum_of_local_counts": int(cnt.item()),
+            "identical_on_all_ranks": bool(torch.equal(lo, hi)), "backend": "nccl"}
 
 
 def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
