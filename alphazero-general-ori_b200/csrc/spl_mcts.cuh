@@ -126,7 +126,7 @@ struct MctsTree {   // 96 B
     int32_t nn_calls, resets, compactions;
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
     int32_t truncated; // searches cut short because a pool filled up mid-move (the next begin makes room again)
-    int32_t depth_sum; // sum of path lengths of this move's simulations (diagnostics)
+    int32_t depth_sum; // sum of path lengths of the simulations since the last reset (diagnostics)
     // state of the simulation in flight (it survives between the kernels of a wave):
     int32_t cur;         // >= 0: continue the descent at this node with path_len edges already recorded; -1: start at the root
     int32_t pend_edge;   // >= 0: the descent stopped at this (absolute) edge, whose child state is being computed / attached
@@ -1024,7 +1024,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
     if (w.lane == 0) {
         T->root = idx; T->leaf = -1; T->sims_done = 0; T->sims_target = idx < 0 ? 0 : sims_target; T->path_len = 0;
-        T->flags = flags; T->depth_sum = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
+        T->flags = flags; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
     }
     w.sync();
     // a root the tree already expanded gets the noise on its stored Ps before the first simulation picks (:150-154);

@@ -226,7 +226,7 @@ int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* s
  * info int32[T][16] = nodes, edges, root Ns, simulations done, network calls since reset, status bits | truncated searches << 8,
  *                     lossy resets * 65536 + cleanings, root Qs (float bits), then 4 floats (bits): the value vector the last
  *                     finished simulation returned at the root (what MCTS.search returns, :99-177), then the sum of the
- *                     path lengths of this move's simulations; 3 spare words */
+ *                     path lengths of the simulations since the last reset; 3 spare words */
 int  spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info, void* stream);
 /* deterministic stand-in network ("fixed NN outputs"): a pure function of the state bytes with exact dyadic outputs; the
  * golden MCTS fixtures were produced by the reference's own MCTS.py with this function as its network */
