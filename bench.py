@@ -384,7 +384,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
-                       "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now() + (W * T * sims if not args.async_moves else 0))), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
+                       "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
                        "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, sims_now())},
     }
     if rank == 0:
