@@ -23,6 +23,7 @@
 
 #ifdef __CUDACC__
 #define SPL_D __device__ __forceinline__
+#define SPL_COLD static __device__ __noinline__   // big, rarely or divergently executed blocks: kept out of the straight-line hot code (instruction cache)
 #define SPL_CTABLE static __constant__
 #define SPL_GTABLE static __device__ const
 #define SPL_KTABLE static constexpr
@@ -31,6 +32,7 @@
 #define SPL_MULHI(a, b) __umulhi((a), (b))
 #else
 #define SPL_D static inline
+#define SPL_COLD static
 #define SPL_CTABLE static const
 #define SPL_GTABLE static const
 #define SPL_KTABLE static constexpr
@@ -73,7 +75,7 @@ enum { SPL_GOLD = 5, SPL_PTS = 6 };
 struct SplPhilox {
     uint32_t v[4];
 };
-SPL_D SplPhilox spl_philox(uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
+SPL_COLD SplPhilox spl_philox(uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
     uint32_t c0 = game, c1 = episode, c2 = ply, c3 = stream, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int i = 0; i < 10; i++) {
@@ -192,35 +194,25 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
     const int tokens = g[0] + g[1] + g[2] + g[3] + g[4] + g[5] + g[6];   // players_gems[player].sum() incl. gold
     const int gold = g[5];
 
-    // --- buy visible 0..11 (_valid_buy :476-501) and card presence for reserve (:511)
-    uint32_t buy = 0, present = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
+    // --- buy visible 0..11 (_valid_buy :476-501), card presence for reserve (:511), buy reserved 27..29 (_valid_buy_reserve
+    // :538-552): one rolled loop over the 15 candidate cards (bit i of `buyable` / `present`)
+    uint32_t buyable = 0, present = 0;
+#pragma unroll 1
+    for (int i = 0; i < 15; i++) {
+        const int row = i < 12 ? L::CARDS + 2 * i : L::PRES + 6 * p + 2 * (i - 12);
         int missing = 0, tot = 0;
 #pragma unroll
         for (int c = 0; c < 5; c++) {
-            int cost = s.get(L::CARDS + 2 * i, c);
-            int d = (int)(int8_t)(cost - g[c] - pc[c]);
+            const int cost = s.get(row, c);
+            const int d = (int)(int8_t)(cost - g[c] - pc[c]);
             missing += d > 0 ? d : 0;
             tot += cost;
         }
-        buy |= (uint32_t)((missing <= gold) && (tot != 0)) << i;
+        buyable |= (uint32_t)((missing <= gold) && (tot != 0)) << i;
         present |= (uint32_t)(tot != 0) << i;
     }
-    // --- buy reserved 27..29 (_valid_buy_reserve :538-552)
-    uint32_t buyres = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        int missing = 0, tot = 0;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            int cost = s.get(L::PRES + 6 * p + 2 * i, c);
-            int d = (int)(int8_t)(cost - g[c] - pc[c]);
-            missing += d > 0 ? d : 0;
-            tot += cost;
-        }
-        buyres |= (uint32_t)((missing <= gold) && (tot != 0)) << i;
-    }
+    const uint32_t buy = buyable & 0xFFFu, buyres = (buyable >> 12) & 7u;
+    present &= 0xFFFu;
     // --- reserve 12..26 (_valid_reserve :508-515)
 #pragma unroll
     for (int t = 0; t < 3; t++) present |= (uint32_t)(spl_sum5(s, L::DECK + 2 * t) != 0) << (12 + t);
@@ -235,16 +227,16 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
 #pragma unroll
     for (int c = 0; c < 5; c++) bank_neg |= b[c] < 0;
     uint32_t T = 0, G = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 25; i++) T |= spl_ge5(bn, SPL_TAKE30[i]) << i;      // _valid_get_gems, is_limit=False :562-568
     if (bank_neg) T = 0;
 #pragma unroll
     for (int c = 0; c < 5; c++) T |= (uint32_t)(b[c] >= 4) << (25 + c);     // _valid_get_gems_identical :578-583
+    bool g_neg = false;
+#pragma unroll
+    for (int c = 0; c < 5; c++) g_neg |= g[c] < 0;
     if (r.flags & SPL_F_GIVEBACK) {
-        bool g_neg = false;
-#pragma unroll
-        for (int c = 0; c < 5; c++) g_neg |= g[c] < 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 20; i++) G |= spl_ge5(gn, SPL_GIVE20[i]) << i;  // _valid_give_gems :595, _identical :609
         if (g_neg) G &= 0xF8000u;   // a negative count fails every "different gems" row; identical rows look at one colour
     }
@@ -268,25 +260,32 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
         const int regime = tokens == r.limit - 2 ? 0 : (tokens == r.limit - 1 ? 1 : 2);
         spl_ex_words(m, T, G, regime);
         if (regime == 2) {
-            if (r.flags & SPL_F_GIVEBACK) {           // take 3 / give 3 (:672, _valid_give_gems3 :602-607)
-                bool g_neg = false;
+            if ((r.flags & SPL_F_GIVEBACK) && !g_neg) {   // take 3 / give 3 (:672, _valid_give_gems3 :602-607): actions 365..404
+                uint64_t g3 = 0;
+#pragma unroll 1
+                for (int tk = 0; tk < 10; tk++) {
+                    const uint64_t on = (T >> (15 + tk)) & 1u;
 #pragma unroll
-                for (int c = 0; c < 5; c++) g_neg |= g[c] < 0;
-                if (!g_neg) {
-#pragma unroll
-                    for (int k = 0; k < 40; k++) {
-                        const int a = 365 + k;
-                        uint32_t bit = ((T >> (15 + k / 4)) & 1u) & spl_ge5(gn, SPL_GIVE3[k]);
-                        m[a >> 5] |= bit << (a & 31);
-                    }
+                    for (int q = 0; q < 4; q++) g3 |= (on & spl_ge5(gn, SPL_GIVE3[4 * tk + q])) << (4 * tk + q);
                 }
+                m[11] |= (uint32_t)(g3 << 13);    // 365 = 11 * 32 + 13
+                m[12] |= (uint32_t)(g3 >> 19);
             }
-            if (b[SPL_GOLD] > 0) {                    // reserve + give 1 (:674-678)
-#pragma unroll
+            if (b[SPL_GOLD] > 0) {                    // reserve + give 1 (:674-678): actions 290 + 5 i + colour, 75 bits from bit 2 of word 9
+                const uint32_t grp = G & 0x1Fu;
+                uint32_t lo = 0, mid = 0, hi = 0;     // bits 0..31 | 32..63 | 64..74 of the 75-bit field
+#pragma unroll 1
                 for (int i = 0; i < 15; i++) {
-                    uint32_t grp = ((rsv_nolimit >> i) & 1u) ? (G & 0x1Fu) : 0u;
-                    spl_mask_or(m, 290 + 5 * i, grp, 5);
+                    if (!((rsv_nolimit >> i) & 1u)) continue;
+                    const int pos = 5 * i;
+                    const uint64_t v = (uint64_t)grp << (pos & 31);
+                    if (pos < 32) { lo |= (uint32_t)v; mid |= (uint32_t)(v >> 32); }
+                    else if (pos < 64) { mid |= (uint32_t)v; hi |= (uint32_t)(v >> 32); }
+                    else hi |= (uint32_t)v;
                 }
+                m[9] |= lo << 2;                       // 290 = 9 * 32 + 2
+                m[10] |= (lo >> 30) | (mid << 2);
+                m[11] |= (mid >> 30) | (hi << 2);
             }
         }
     }
@@ -301,7 +300,7 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
 // chance: draw from deck `tier` (count row 2t, MSB-first bitmask row 2t+1; :400-412)
 // ------------------------------------------------------------------------------------------
 template <int N, class S>
-SPL_D int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
+SPL_COLD int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
     typedef SplLay<N> L;
     int cnt[5], total = 0;
 #pragma unroll
@@ -454,38 +453,61 @@ SPL_D int spl_reserve(S& s, int i, int p, const SplChance& ch) {   // _reserve :
 }
 
 // returns next player, or <0 for a move the reference leaves undefined. Pass (405) only bumps the ply (patch P6).
+// Decode first, then ONE call site each for the card purchase, the reservation and the gem transfer: the lanes of a warp
+// play different kinds of moves every ply, so every inlined copy of those blocks was executed (and fetched) by every warp.
 template <int N, class S>
 SPL_D int spl_apply_move(S& s, int a, int p, const SplChance& ch) {
     typedef SplLay<N> L;
-    int rc = 0;
-    if (a < 12) {   // _buy :503-506
-        spl_buy_card<N>(s, L::CARDS + 2 * a, p);
-        spl_write_card(s, L::CARDS + 2 * a, spl_draw<N>(s, a >> 2, ch));
-    } else if (a < 27) {
-        rc = spl_reserve<N>(s, a - 12, p, ch);
-    } else if (a < 30) {   // _buy_reserve :554-560
-        const int i = a - 27, base = L::PRES + 6 * p;
-        spl_buy_card<N>(s, base + 2 * i, p);
-        for (int k = i; k < 2; k++) {
+    int buy_row = -1, res_idx = -1, comp_from = -1;
+    uint32_t take = 0u, give = 0u;   // gems taken from / given back to the bank, one nibble per colour
+    if (a < 12) {                                   // _buy :503-506
+        buy_row = L::CARDS + 2 * a;
+    } else if (a < 27) {                            // _reserve :517-536
+        res_idx = a - 12;
+    } else if (a < 30) {                            // _buy_reserve :554-560
+        comp_from = a - 27;
+        buy_row = L::PRES + 6 * p + 2 * comp_from;
+    } else if (a < 60) {                            // _get_gems :585-593
+        take = SPL_TAKE30_G[a - 30];
+    } else if (a < 290 || (a >= 365 && a < 405)) {  // _give_and_get_gems :697-756
+        take = SPL_TAKE30_G[SPL_EX_TAKE_G[a]];
+        give = SPL_GIVE20_G[SPL_EX_GIVE_G[a]];
+        if (a >= 365) give += SPL_GIVE20_G[SPL_EX_GIVE2_G[a]];   // two give operations; at most 3 of a colour in total
+    } else if (a < 365) {                           // _reserve_and_give :759-761
+        res_idx = (a - 290) / 5;
+        give = 1u << (4 * ((a - 290) % 5));
+    }
+    if (buy_row >= 0) {
+        spl_buy_card<N>(s, buy_row, p);
+        if (comp_from < 0) {
+            spl_write_card(s, buy_row, spl_draw<N>(s, a >> 2, ch));   // _fill_new_card :445-450
+        } else {                                                      // close the gap in the reserve
+            const int base = L::PRES + 6 * p;
+            for (int k = comp_from; k < 2; k++) {
 #pragma unroll
-            for (int c = 0; c < 7; c++) {
-                s.set(base + 2 * k, c, s.get(base + 2 * k + 2, c));
-                s.set(base + 2 * k + 1, c, s.get(base + 2 * k + 3, c));
+                for (int c = 0; c < 7; c++) {
+                    s.set(base + 2 * k, c, s.get(base + 2 * k + 2, c));
+                    s.set(base + 2 * k + 1, c, s.get(base + 2 * k + 3, c));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 7; c++) { s.set(base + 4, c, 0); s.set(base + 5, c, 0); }
+        }
+    }
+    if (res_idx >= 0) {
+        const int rc = spl_reserve<N>(s, res_idx, p, ch);
+        if (rc < 0) return rc;
+    }
+    if (take | give) {                              // _get_gems :585 then _give_gems :685 (the colour sets are disjoint)
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const int d = (int)((take >> (4 * c)) & 15u) - (int)((give >> (4 * c)) & 15u);
+            if (d != 0) {
+                s.set(L::BANK, c, s.get(L::BANK, c) - d);
+                s.set(L::PGEMS + p, c, s.get(L::PGEMS + p, c) + d);
             }
         }
-#pragma unroll
-        for (int c = 0; c < 7; c++) { s.set(base + 4, c, 0); s.set(base + 5, c, 0); }
-    } else if (a < 60) {
-        spl_move_gems<N>(s, p, SPL_TAKE30_G[a - 30], +1);
-    } else if (a < 290 || (a >= 365 && a < 405)) {   // _give_and_get_gems :697-756
-        spl_move_gems<N>(s, p, SPL_TAKE30_G[SPL_EX_TAKE_G[a]], +1);
-        spl_move_gems<N>(s, p, SPL_GIVE20_G[SPL_EX_GIVE_G[a]], -1);
-        if (a >= 365) spl_move_gems<N>(s, p, SPL_GIVE20_G[SPL_EX_GIVE2_G[a]], -1);
-    } else if (a < 365) {   // _reserve_and_give :759-761
-        rc = spl_reserve<N>(s, (a - 290) / 5, p, ch);
-        if (rc == 0) spl_move_gems<N>(s, p, 1u << (4 * ((a - 290) % 5)), -1);
     }
-    if (rc < 0) return rc;
     s.set(L::BANK, SPL_PTS, s.get(L::BANK, SPL_PTS) + 1);   // ply counter :287
     return (p + 1) % N;
 }
@@ -540,15 +562,31 @@ SPL_D bool spl_game_ended(const S& s, SplRules r, float* out) {
 // ------------------------------------------------------------------------------------------
 // canonical rotation: new[i] = old[(i + shift) % size] on the four per-player blocks (:338-347)
 // ------------------------------------------------------------------------------------------
+// new[i] = old[(i + SHIFT) % SIZE] in place by cycle-following ("juggling": gcd(SIZE, SHIFT) cycles, each row moved
+// once, one row of 7 cells held in registers). Rolled loops on purpose: the unrolled form was 300+ straight-line
+// instructions that every warp fetched every ply, and these kernels are bound by instruction fetch.
+template <int A, int B> struct SplGcd { static constexpr int value = SplGcd<B, A % B>::value; };
+template <int A> struct SplGcd<A, 0> { static constexpr int value = A; };
 template <int SIZE, int SHIFT, class S>
 SPL_D void spl_roll_block(S& s, int row0) {
+    constexpr int G = SplGcd<SIZE, SHIFT>::value;
+#pragma unroll 1
+    for (int start = 0; start < G; start++) {
+        int saved[7];
 #pragma unroll
-    for (int c = 0; c < 7; c++) {
-        int t[SIZE];
+        for (int c = 0; c < 7; c++) saved[c] = s.get(row0 + start, c);
+        int j = start;
+#pragma unroll 1
+        for (;;) {
+            int nxt = j + SHIFT;
+            nxt = nxt >= SIZE ? nxt - SIZE : nxt;
+            if (nxt == start) break;
 #pragma unroll
-        for (int i = 0; i < SIZE; i++) t[i] = s.get(row0 + i, c);
+            for (int c = 0; c < 7; c++) s.set(row0 + j, c, s.get(row0 + nxt, c));
+            j = nxt;
+        }
 #pragma unroll
-        for (int i = 0; i < SIZE; i++) s.set(row0 + i, c, t[(i + SHIFT) % SIZE]);
+        for (int c = 0; c < 7; c++) s.set(row0 + j, c, saved[c]);
     }
 }
 
@@ -606,7 +644,7 @@ SPL_D void spl_init_explicit(S& s, const uint8_t* deals, const uint8_t* nobles) 
 }
 
 template <int N, class S>
-SPL_D void spl_init_philox(S& s, uint64_t seed, uint32_t game, uint32_t episode) {
+SPL_COLD void spl_init_philox(S& s, uint64_t seed, uint32_t game, uint32_t episode) {
     typedef SplLay<N> L;
     spl_init_empty<N>(s);
     for (int slot = 0; slot < 12; slot++) {   // :237-239
@@ -635,22 +673,23 @@ SPL_D int spl_pick_random(const uint32_t* m, uint64_t seed, uint32_t game, uint3
     if (cnt == 0) return -1;
     SplPhilox ph = spl_philox(seed, game, episode, ply, 1);
     int k = (int)SPL_MULHI(ph.v[0], (uint32_t)cnt);
-    int action = -1;
+    uint32_t x = 0u;   // the word that holds the k-th (0-based) set bit, found by one branch-free scan ...
+    int base = 0;
+    bool found = false;
 #pragma unroll
     for (int w = 0; w < SPL_MASK_WORDS; w++) {
-        int pc = SPL_POPC(m[w]);
-        if (action < 0) {
-            if (k < pc) {
-                const uint32_t x = m[w];   // position of the k-th (0-based) set bit: popcount binary search
-                int bitpos = 0, kk = k;
-#pragma unroll
-                for (int sh = 16; sh >= 1; sh >>= 1) {
-                    const int c = SPL_POPC((x >> bitpos) & ((1u << sh) - 1u));
-                    if (kk >= c) { kk -= c; bitpos += sh; }
-                }
-                action = 32 * w + bitpos;
-            } else k -= pc;
-        }
+        const int pc = SPL_POPC(m[w]);
+        const bool take = !found && k < pc;
+        x = take ? m[w] : x;
+        base = take ? 32 * w : base;
+        found = found || take;
+        k = found ? k : k - pc;
     }
-    return action;
+    int bitpos = 0;    // ... then its position inside the word by a popcount binary search (no data-dependent loops)
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) {
+        const int c = SPL_POPC((x >> bitpos) & ((1u << sh) - 1u));
+        if (k >= c) { k -= c; bitpos += sh; }
+    }
+    return base + bitpos;
 }
