@@ -125,6 +125,48 @@ __device__ __forceinline__ void tile_store_drain(int lane) {
 __device__ __forceinline__ unsigned long long warp_sum(unsigned v) { return (unsigned long long)__reduce_add_sync(0xffffffffu, v); }
 
 // ------------------------------------------------------------------------------------------
+// game start for some lanes of a tile, by the whole warp (init_game :222-246 with Philox chance). A finished game
+// restarts in one lane at a time (one ply in three sees some lane of the warp finish), and the scalar spl_init_philox ran
+// ~3000 instructions with a single active lane. Here the warp works on that lane's column together: the empty position is
+// written 32 cells per instruction, the 14 Philox blocks (12 deals + nobles) are computed by 14 lanes at once, and the
+// three tiers deal in parallel (the four draws of a tier depend on each other). Same counters, same result as
+// spl_init_philox (the GPU tests compare every reset with the scalar form).
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tile_reset_lanes(int8_t* tile, uint32_t need, int lane, uint64_t seed, uint32_t game, uint32_t episode) {
+    typedef SplLay<N> L;
+    while (need) {
+        const int who = __ffs(need) - 1;
+        need &= need - 1u;
+        const uint32_t g = __shfl_sync(0xffffffffu, game, who), e = __shfl_sync(0xffffffffu, episode, who);
+        int8_t* col = tile + who;
+        for (int cell = lane; cell < L::CELLS; cell += 32) col[cell * TL] = (int8_t)spl_init_cell<N>(cell / 7, cell % 7);
+        SplPhilox ph;
+        ph.v[0] = ph.v[1] = ph.v[2] = ph.v[3] = 0u;
+        if (lane < 12) ph = spl_philox(seed, g, e, (uint32_t)lane, 2);          // deal of visible slot `lane`
+        else if (lane < 14) ph = spl_philox(seed, g, e, (uint32_t)(lane - 12), 3);   // nobles
+        __syncwarp();
+        TileAcc s{col};
+#pragma unroll 1
+        for (int round = 0; round < 4; round++) {   // lane t < 3 deals slot 4 t + round of tier t
+            const int slot = 4 * (lane < 3 ? lane : 0) + round;
+            const uint32_t w0 = __shfl_sync(0xffffffffu, ph.v[0], slot), w1 = __shfl_sync(0xffffffffu, ph.v[1], slot);
+            if (lane < 3) {
+                const int code = spl_draw_from<N>(s, lane, w0, w1);
+                spl_write_card(s, L::CARDS + 2 * slot, spl_deck_take<N>(s, lane, code));
+            }
+            __syncwarp();
+        }
+        uint32_t w[5];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __shfl_sync(0xffffffffu, ph.v[i], 12);
+        w[4] = __shfl_sync(0xffffffffu, ph.v[0], 13);
+        if (lane == 0) spl_init_nobles<N>(s, w);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // fused single-ply pass (spl_step): one launch = make_move + swap_players + check_end_game
 // (+ auto reset) + valid_moves (+ random pick) for every lane
 // ------------------------------------------------------------------------------------------
@@ -193,11 +235,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) spl_step_kernel(const StepPa
         if (ended && A.auto_reset) {
             finished = 1;
             episode += 1;
-            spl_init_philox<N>(s, A.seed, game, episode);
             cur = 0;
             if (A.episodes) A.episodes[gl] = episode;
         }
         if (A.status_out) A.status_out[gl] = status;
+    }
+    {   // finished lanes start their next game: the whole warp deals for them, one lane at a time
+        const uint32_t need = __ballot_sync(0xffffffffu, finished != 0);
+        if (need) tile_reset_lanes<N>(sm, need, lane, A.seed, game, episode);
+    }
+    if (active) {
         if (A.mask_out || A.next_actions) {
             uint32_t m[SPL_MASK_WORDS];
             spl_valid_mask<N>(s, cur, P.rules, m);
@@ -265,8 +312,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) spl_rollout_kernel(const Rol
         }
         int first_plies = 0;
         bool have_first = false;
-        if (active) {
-            for (int it = 0; it < A.plies; it++) {
+        for (int it = 0; it < A.plies; it++) {   // every lane of the warp runs the loop (padding lanes idle): the restart below is a warp job
+            bool restart = false;
+            if (active) {
                 uint32_t m[SPL_MASK_WORDS];
                 spl_valid_mask<N>(s, cur, P.rules, m);
                 const uint32_t ply = (uint32_t)(uint8_t)s.get(L::BANK, SPL_PTS);
@@ -290,10 +338,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) spl_rollout_kernel(const Rol
                         }
                     }
                     episode += 1;
-                    spl_init_philox<N>(s, A.seed, game, episode);
                     cur = 0;
+                    restart = true;
                 }
             }
+            const uint32_t need = __ballot_sync(0xffffffffu, restart);
+            if (need) tile_reset_lanes<N>(sm, need, lane, A.seed, game, episode);
+        }
+        if (active) {
             if (A.episodes) A.episodes[gl] = episode;
             if (A.players) A.players[gl] = (uint8_t)cur;
             if (A.first_plies) A.first_plies[gl] = have_first ? first_plies : 0;

@@ -226,19 +226,34 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
     bool bank_neg = false;
 #pragma unroll
     for (int c = 0; c < 5; c++) bank_neg |= b[c] < 0;
+    // The 25 "different gems" rows need one gem of each colour of the row: a subset test on the 5-bit set of colours
+    // the bank (or the player) holds. Rows 25..29 / 15..19 ("identical") look at one colour's count.
     uint32_t T = 0, G = 0;
-#pragma unroll 1
-    for (int i = 0; i < 25; i++) T |= spl_ge5(bn, SPL_TAKE30[i]) << i;      // _valid_get_gems, is_limit=False :562-568
-    if (bank_neg) T = 0;
-#pragma unroll
-    for (int c = 0; c < 5; c++) T |= (uint32_t)(b[c] >= 4) << (25 + c);     // _valid_get_gems_identical :578-583
+    uint32_t bank_has = 0, mine_has = 0;
     bool g_neg = false;
 #pragma unroll
-    for (int c = 0; c < 5; c++) g_neg |= g[c] < 0;
-    if (r.flags & SPL_F_GIVEBACK) {
+    for (int c = 0; c < 5; c++) {
+        bank_has |= (uint32_t)(b[c] >= 1) << c;
+        mine_has |= (uint32_t)(g[c] >= 1) << c;
+        g_neg |= g[c] < 0;
+    }
 #pragma unroll 1
-        for (int i = 0; i < 20; i++) G |= spl_ge5(gn, SPL_GIVE20[i]) << i;  // _valid_give_gems :595, _identical :609
+    for (int i = 0; i < 25; i++) {   // _valid_get_gems, is_limit=False :562-568; _valid_give_gems :595 (first 15 rows)
+        const uint32_t need = SPL_COMBO_BITS[i];
+        T |= (uint32_t)((bank_has & need) == need) << i;
+        G |= (uint32_t)((mine_has & need) == need) << i;
+    }
+    G &= 0x7FFFu;
+    if (bank_neg) T = 0;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        T |= (uint32_t)(b[c] >= 4) << (25 + c);     // _valid_get_gems_identical :578-583
+        G |= (uint32_t)(g[c] >= 2) << (15 + c);     // _valid_give_gems_identical :609
+    }
+    if (r.flags & SPL_F_GIVEBACK) {
         if (g_neg) G &= 0xF8000u;   // a negative count fails every "different gems" row; identical rows look at one colour
+    } else {
+        G = 0;
     }
     // --- take only 30..59 (:256, limits :567-574)
     int nspec = 0;
@@ -299,15 +314,16 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
 // ------------------------------------------------------------------------------------------
 // chance: draw from deck `tier` (count row 2t, MSB-first bitmask row 2t+1; :400-412)
 // ------------------------------------------------------------------------------------------
+// the two-stage choice of _get_deck_card (:400-412) from two 32-bit uniform words: colour with probability proportional
+// to its remaining count, then uniformly among that colour's remaining cards. Returns colour*8+idx or -1 (empty deck).
 template <int N, class S>
-SPL_COLD int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
+SPL_D int spl_draw_from(const S& s, int tier, uint32_t w0, uint32_t w1) {
     typedef SplLay<N> L;
     int cnt[5], total = 0;
 #pragma unroll
     for (int c = 0; c < 5; c++) { cnt[c] = s.get(L::DECK + 2 * tier, c); total += cnt[c]; }
     if (total == 0) return -1;
-    SplPhilox w = spl_philox(seed, game, episode, ply, stream);
-    int k = (int)SPL_MULHI(w.v[0], (uint32_t)total);
+    int k = (int)SPL_MULHI(w0, (uint32_t)total);
     int color = 4, acc = 0, ccount = cnt[4];
     bool found = false;
 #pragma unroll
@@ -316,7 +332,7 @@ SPL_COLD int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game,
         if (!found && acc > k) { color = c; ccount = cnt[c]; found = true; }
     }
     uint32_t bits = (uint32_t)(uint8_t)s.get(L::DECK + 2 * tier + 1, color);
-    int j = (int)SPL_MULHI(w.v[1], (uint32_t)ccount);
+    int j = (int)SPL_MULHI(w1, (uint32_t)ccount);
     int idx = -1;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -326,6 +342,11 @@ SPL_COLD int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game,
         }
     }
     return idx < 0 ? -1 : color * 8 + idx;
+}
+template <int N, class S>
+SPL_COLD int spl_draw_philox(const S& s, int tier, uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t stream) {
+    const SplPhilox w = spl_philox(seed, game, episode, ply, stream);
+    return spl_draw_from<N>(s, tier, w.v[0], w.v[1]);
 }
 
 // remove card (colour, idx) from deck `tier`; returns the packed card or 0 if it was not there
@@ -605,6 +626,42 @@ SPL_D void spl_rotate(S& s, int k, SplRules r) {
 // ------------------------------------------------------------------------------------------
 // game start
 // ------------------------------------------------------------------------------------------
+// value of cell (row, col) in the start position before any chance event (init_game :222-233)
+template <int N>
+SPL_D int spl_init_cell(int row, int col) {
+    typedef SplLay<N> L;
+    if (row == L::BANK) return col < 5 ? L::GEMS0 : (col == SPL_GOLD ? 5 : 0);
+    if (row >= L::DECK && row < L::DECK + 6 && col < 5) {
+        const int t = (row - L::DECK) >> 1, k = t == 0 ? 8 : (t == 1 ? 6 : 4);
+        return ((row - L::DECK) & 1) ? (int)(int8_t)(uint8_t)(0xFF00u >> k) : k;
+    }
+    return 0;
+}
+template <class S>
+SPL_D void spl_write_noble(S& s, int row, int noble_id) {
+    uint32_t pk = SPL_NOBLES[noble_id];
+#pragma unroll
+    for (int c = 0; c < 5; c++) s.set(row, c, (int)((pk >> (4 * c)) & 15u));
+    s.set(row, 5, 0);
+    s.set(row, 6, 3);
+}
+
+// the noble draw of init_game (:241): n+1 distinct ids of 10 by a partial Fisher-Yates over a nibble-packed permutation,
+// random words w[0..4] = Philox (counter 0, stream 3) words 0..3 then (counter 1, stream 3) word 0
+template <int N, class S>
+SPL_D void spl_init_nobles(S& s, const uint32_t* w) {
+    typedef SplLay<N> L;
+    uint64_t perm = 0x9876543210ull;
+#pragma unroll
+    for (int i = 0; i < L::NUM_NOBLES; i++) {
+        int j = i + (int)SPL_MULHI(w[i], (uint32_t)(10 - i));
+        uint32_t vi = (uint32_t)(perm >> (4 * i)) & 15u, vj = (uint32_t)(perm >> (4 * j)) & 15u;
+        perm &= ~((15ull << (4 * i)) | (15ull << (4 * j)));
+        perm |= ((uint64_t)vj << (4 * i)) | ((uint64_t)vi << (4 * j));
+        spl_write_noble(s, L::NOBLES + i, (int)vj);
+    }
+}
+
 template <int N, class S>
 SPL_D void spl_init_empty(S& s) {   // init_game :222-233 (no chance)
     typedef SplLay<N> L;
@@ -625,14 +682,6 @@ SPL_D void spl_init_empty(S& s) {   // init_game :222-233 (no chance)
     }
 }
 
-template <class S>
-SPL_D void spl_write_noble(S& s, int row, int noble_id) {
-    uint32_t pk = SPL_NOBLES[noble_id];
-#pragma unroll
-    for (int c = 0; c < 5; c++) s.set(row, c, (int)((pk >> (4 * c)) & 15u));
-    s.set(row, 5, 0);
-    s.set(row, 6, 3);
-}
 
 // explicit start: deals[12] = colour*8+idx per visible slot, nobles[N+1] = noble ids (replay of a reference game)
 template <int N, class S>
@@ -651,18 +700,10 @@ SPL_COLD void spl_init_philox(S& s, uint64_t seed, uint32_t game, uint32_t episo
         int code = spl_draw_philox<N>(s, slot >> 2, seed, game, episode, (uint32_t)slot, 2);
         spl_write_card(s, L::CARDS + 2 * slot, spl_deck_take<N>(s, slot >> 2, code));
     }
-    // n+1 distinct nobles of 10 (:241): partial Fisher-Yates over a nibble-packed permutation
-    SplPhilox w0 = spl_philox(seed, game, episode, 0, 3), w1 = spl_philox(seed, game, episode, 1, 3);
-    uint64_t perm = 0x9876543210ull;
-#pragma unroll
-    for (int i = 0; i < L::NUM_NOBLES; i++) {
-        uint32_t word = i < 4 ? w0.v[i & 3] : w1.v[i & 3];
-        int j = i + (int)SPL_MULHI(word, (uint32_t)(10 - i));
-        uint32_t vi = (uint32_t)(perm >> (4 * i)) & 15u, vj = (uint32_t)(perm >> (4 * j)) & 15u;
-        perm &= ~((15ull << (4 * i)) | (15ull << (4 * j)));
-        perm |= ((uint64_t)vj << (4 * i)) | ((uint64_t)vi << (4 * j));
-        spl_write_noble(s, L::NOBLES + i, (int)vj);
-    }
+    // n+1 distinct nobles of 10 (:241)
+    const SplPhilox w0 = spl_philox(seed, game, episode, 0, 3), w1 = spl_philox(seed, game, episode, 1, 3);
+    const uint32_t w[5] = {w0.v[0], w0.v[1], w0.v[2], w0.v[3], w1.v[0]};
+    spl_init_nobles<N>(s, w);
 }
 
 // uniform pick among the set bits of a mask (Philox stream 1): the bench's rollout policy
