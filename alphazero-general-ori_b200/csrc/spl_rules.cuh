@@ -107,6 +107,14 @@ SPL_D int spl_sum5(const S& s, int row) {
     return s.get(row, 0) + s.get(row, 1) + s.get(row, 2) + s.get(row, 3) + s.get(row, 4);
 }
 
+// "the five costs sum to non-zero" (the reference's emptiness test): with non-negative costs that is "some cost is set";
+// only if a negative cost shows up (never in a game) the exact sum is taken
+template <class S>
+SPL_D bool spl_sum5_nonzero(const S& s, int row, int or_of_costs) {
+    if (or_of_costs >= 0) return or_of_costs != 0;
+    return spl_sum5(s, row) != 0;
+}
+
 SPL_D uint32_t spl_nib5(const int* v) {   // clamp to [0,7] and pack one nibble per colour
     uint32_t x = 0;
 #pragma unroll
@@ -197,19 +205,23 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
     // --- buy visible 0..11 (_valid_buy :476-501), card presence for reserve (:511), buy reserved 27..29 (_valid_buy_reserve
     // :538-552): one rolled loop over the 15 candidate cards (bit i of `buyable` / `present`)
     uint32_t buyable = 0, present = 0;
+    int have[5];   // gems + bonuses per colour; the reference subtracts both from the cost in int8 arithmetic (wraps mod 256)
+#pragma unroll
+    for (int c = 0; c < 5; c++) have[c] = g[c] + pc[c];
 #pragma unroll 1
     for (int i = 0; i < 15; i++) {
         const int row = i < 12 ? L::CARDS + 2 * i : L::PRES + 6 * p + 2 * (i - 12);
-        int missing = 0, tot = 0;
+        int missing = 0, any = 0;
 #pragma unroll
         for (int c = 0; c < 5; c++) {
             const int cost = s.get(row, c);
-            const int d = (int)(int8_t)(cost - g[c] - pc[c]);
+            const int d = (int)(int8_t)(cost - have[c]);
             missing += d > 0 ? d : 0;
-            tot += cost;
+            any |= cost;
         }
-        buyable |= (uint32_t)((missing <= gold) && (tot != 0)) << i;
-        present |= (uint32_t)(tot != 0) << i;
+        const bool card = spl_sum5_nonzero(s, row, any);
+        buyable |= (uint32_t)((missing <= gold) && card) << i;
+        present |= (uint32_t)card << i;
     }
     const uint32_t buy = buyable & 0xFFFu, buyres = (buyable >> 12) & 7u;
     present &= 0xFFFu;
@@ -391,10 +403,11 @@ SPL_D uint32_t spl_draw(S& s, int tier, const SplChance& ch) {
 template <int N, class S>
 SPL_D void spl_give_nobles(S& s, int p) {   // _give_nobles_if_earned :763-768 (all earned nobles at once)
     typedef SplLay<N> L;
-    int pc[5];
+    int pc[5], most = 0;
 #pragma unroll
-    for (int c = 0; c < 5; c++) pc[c] = s.get(L::PCARDS + p, c);
-#pragma unroll
+    for (int c = 0; c < 5; c++) { pc[c] = s.get(L::PCARDS + p, c); most = pc[c] > most ? pc[c] : most; }
+    if (most < 3) return;   // every noble asks for at least 3 cards of some colour (SplendorLogic.py:320-332)
+#pragma unroll 1
     for (int i = 0; i < L::NUM_NOBLES; i++) {
         int nb[7], tot = 0;
         bool ok = true;
