@@ -1,7 +1,7 @@
 // libsplendor_b200.so - MCTS tree arena kernels for sm_100a and their C ABI (include/splendor_b200.h).
 // The per-tree logic lives in spl_mcts.cuh; this file is launch plumbing. A selection wave is three kernels:
 //   mcts_descend_kernel  one warp per tree, light (PUCT pick + path only, no rules code -> every tree resident at once)
-//   mcts_rules_kernel    one LANE per tree, 32 trees per warp on a shared-memory tile like the environment kernels:
+//   mcts_rules_kernel    one LANE per tree, a few trees per warp, states staged in shared memory by cp.async:
 //                        make_move + swap_players + getGameEnded + getValidMoves of the child of every pending edge
 //   mcts_attach_kernel   one warp per tree: hash, dictionary lookup / insertion, edge allocation, leaf hand-over
 // A tree whose new edge led into a node it already holds (transposition) or into a terminal node carries on in the next
@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "spl_internal.h"
@@ -22,7 +23,19 @@ struct spl_mcts {
     MctsArena A;
     MctsSearchParams P;
     int edge_reserve, gc_reachable, rounds, max_levels;
+    int rules_tpw;               // trees per warp of the rules kernel
+    int fuse_rules;              // spl_mcts_wave_nnet: rules step inside the descent kernel (no launch boundary) instead of mcts_rules_kernel
+    cudaStream_t side;           // spl_mcts_wave_nnet: the network runs here, next to the attach kernel
+    cudaEvent_t ev_fork, ev_join;
 };
+
+// diagnostics: per-tree time stamps when the arena carries a profile buffer (spl_mcts_debug_profile), lane 0 of the tree's warp
+__device__ __forceinline__ long long prof_globaltimer() {
+    unsigned long long x;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x));
+    return (long long)x;
+}
+#define PROF_STAMP(A, t, i, val) do { if ((A).prof && (threadIdx.x & 31) == 0) (A).prof[(size_t)(t) * 16 + (i)] = (val); } while (0)
 
 struct WarpScratch {
     int8_t* st;
@@ -53,7 +66,7 @@ __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSe
 }
 
 template <int N>
-__global__ void __launch_bounds__(MW * 32, 8) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int max_levels, int8_t* leaf_states,
+__global__ void __launch_bounds__(MW * 32, 7) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int max_levels, int8_t* leaf_states,
                                                                   uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
@@ -61,24 +74,29 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_descend_kernel(MctsArena A, M
     mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
 }
 
-// shared-memory tile accessor of the rules kernel: cell (row, col) of this lane's tree = byte [(7 row + col) * 32 + lane]
-struct TreeTileAcc {
-    int8_t* b;
-    __device__ __forceinline__ int get(int row, int col) const { return b[(row * 7 + col) * 32]; }
-    __device__ __forceinline__ void set(int row, int col, int v) { b[(row * 7 + col) * 32] = (int8_t)v; }
-};
-#define RW 2   // warps (tiles of 32 trees) per CTA of the rules kernel
+#define RW 2   // warps per CTA of the rules kernel
 
-template <int N>
+// One LANE per tree, TPW trees per warp (the other lanes only help with the copies). The kernel is bound by the latency of a
+// single warp walking through the rules code, so everything around that walk is kept short: the parent states (the reference's
+// own byte order, sp bytes each) come in with one batch of 16-byte cp.async per warp - all of them in flight at once - and
+// stay in that order in shared memory (row stride chosen so that the TPW lanes hit different banks), the rules code reads and
+// writes them through the AoS accessor, and the children go out to the staging rows as straight 16-byte copies.
+template <int N> struct RulesSmem {
+    static constexpr int SP = MctsLay<N>::SP;
+    static constexpr int STRIDE = (SP / 4) % 32 == 0 ? SP + 16 : SP;   // 432 / 528 / 624 bytes: lane strides of 12 / 4 / 28 banks
+};
+
+template <int N, int TPW>
 __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRules rules) {
     typedef MctsLay<N> ML;
+    constexpr int STRIDE = RulesSmem<N>::STRIDE, CH = ML::SP / 16;
     extern __shared__ __align__(16) int8_t tile_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * RW + warp) * 32 + lane;
-    int8_t* col = tile_smem + (size_t)warp * ML::S * 32 + lane;
+    const int t0 = (blockIdx.x * RW + warp) * TPW, t = t0 + lane;
+    int8_t* wsm = tile_smem + (size_t)warp * TPW * STRIDE;
     bool pending = false;
     int parent = 0, action = 0;
-    if (t < A.n_trees) {
+    if (lane < TPW && t < A.n_trees) {
         const MctsTree* T = A.trees + t;
         const int pe = T->pend_edge;
         if (pe >= 0 && T->leaf < 0) {
@@ -87,50 +105,75 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
             action = (int)A.edges[(size_t)t * A.ecap + pe].action;
         }
     }
-    if (!__any_sync(0xffffffffu, pending)) return;
+    const uint32_t pmask = __ballot_sync(0xffffffffu, pending);
+    if (pmask == 0u) return;
+    if (t0 < A.n_trees) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
+#pragma unroll
+    for (int j = 0; j < TPW; j++) {
+        const int par = __shfl_sync(0xffffffffu, parent, j);
+        if ((pmask >> j) & 1u) {
+            const int8_t* src = A.states + ((size_t)(t0 + j) * A.cap + par) * A.sp;
+            for (int i = lane; i < CH; i += 32) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + j * STRIDE + 16 * i);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (t0 < A.n_trees) PROF_STAMP(A, t0, 8, clock64());
+    bool ended = false;
+    float es[N];
+    uint32_t m[SPL_MASK_WORDS];
     if (pending) {
-        const uint4* src = reinterpret_cast<const uint4*>(A.states + ((size_t)t * A.cap + parent) * A.sp);
-#pragma unroll 5
-        for (int i = 0; i < ML::SP / 16; i++) {   // own state -> own column (every store of the warp hits one cell row: conflict-free)
-            const uint4 v = __ldg(src + i);
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        AosAcc s{wsm + lane * STRIDE};
+        ended = mcts_rules_core<N>(s, action, rules, es, m);
+    }
+    __syncwarp();
+    if (t0 < A.n_trees) PROF_STAMP(A, t0, 9, clock64());
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int cell = 16 * i + j;
-                if (cell < ML::S) col[cell * 32] = (int8_t)((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-            }
+    for (int j = 0; j < TPW; j++) {
+        if ((pmask >> j) & 1u) {
+            uint4* dst = reinterpret_cast<uint4*>(A.stage_state + (size_t)(t0 + j) * A.sp);
+            const uint4* src = reinterpret_cast<const uint4*>(wsm + j * STRIDE);
+            for (int i = lane; i < CH; i += 32) dst[i] = src[i];
         }
-        TreeTileAcc s{col};
-        float es[N];
-        uint32_t m[SPL_MASK_WORDS];
-        const bool ended = mcts_rules_core<N>(s, action, rules, es, m);
-        uint4* dst = reinterpret_cast<uint4*>(A.stage_state + (size_t)t * A.sp);
-#pragma unroll 5
-        for (int i = 0; i < ML::SP / 16; i++) {
-            uint32_t wv[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int cell = 16 * i + j;
-                if (cell < ML::S) wv[j >> 2] |= (uint32_t)(uint8_t)col[cell * 32] << (8 * (j & 3));
-            }
-            dst[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-        }
+    }
+    if (pending) {
 #pragma unroll
         for (int i = 0; i < SPL_MASK_WORDS; i++) A.stage_mask[(size_t)i * A.n_trees + t] = m[i];
 #pragma unroll
         for (int i = 0; i < 4; i++) A.stage_es[(size_t)t * 4 + i] = i < N ? es[i] : 0.f;
         A.stage_ended[t] = ended ? 1 : 0;
+        A.leaf_src[t] = 1;   // if this child needs the network, its input row is the staging row (spl_mcts_wave_nnet)
     }
+    if (t0 < A.n_trees) { PROF_STAMP(A, t0, 10, clock64()); PROF_STAMP(A, t0, 11, prof_globaltimer()); }
+}
+
+template <int N>
+static cudaError_t launch_rules(const MctsArena& A, const SplRules& rules, int tpw, cudaStream_t st) {
+    const int warps = (A.n_trees + tpw - 1) / tpw, grid = (warps + RW - 1) / RW;
+    const int smem = RW * tpw * RulesSmem<N>::STRIDE;
+    switch (tpw) {
+        case 16: mcts_rules_kernel<N, 16><<<grid, RW * 32, smem, st>>>(A, rules); break;
+        case 8: mcts_rules_kernel<N, 8><<<grid, RW * 32, smem, st>>>(A, rules); break;
+        case 4: mcts_rules_kernel<N, 4><<<grid, RW * 32, smem, st>>>(A, rules); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 template <int N>
 __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, MctsSearchParams P, int8_t* leaf_states, uint8_t* leaf_valids,
-                                                                 uint8_t* leaf_flags, int32_t* counters) {
+                                                                 uint8_t* leaf_flags, int32_t* counters, bool emit_rows) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
+    PROF_STAMP(A, t, 12, prof_globaltimer()); PROF_STAMP(A, t, 13, clock64());
     const int leaf = mcts_attach_tree<N>(w, A, t, P, A.stage_state + (size_t)t * A.sp, A.stage_ended[t] != 0, A.stage_es + (size_t)t * 4,
-                                         A.stage_mask + t, A.n_trees, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+                                         A.stage_mask + t, A.n_trees, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS,
+                                         emit_rows);
+    PROF_STAMP(A, t, 14, clock64()); PROF_STAMP(A, t, 15, prof_globaltimer());
     if (w.lane == 0) {
         leaf_flags[t] = (uint8_t)leaf;
         if (counters) {   // last round of the wave
@@ -150,17 +193,59 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_expand_kernel(MctsArena A, Mc
     mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
 }
 
-// expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree)
+// the rules step of ONE tree by its own warp (lane 0 walks the rules code, the warp does the copies): what mcts_rules_kernel does
+// for a few trees per warp, here without a kernel boundary between the descent and it. wsm: sp bytes of shared memory, 16-aligned.
 template <int N>
-__global__ void __launch_bounds__(MW * 32, 8) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
+__device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, const SplRules& rules, int8_t* wsm, int lane) {
+    constexpr int CH = MctsLay<N>::SP / 16;
+    const MctsTree* T = A.trees + t;
+    const int pe = T->pend_edge;
+    if (pe < 0 || T->leaf >= 0) return;
+    const int action = (int)A.edges[(size_t)t * A.ecap + pe].action;
+    const int8_t* src = A.states + ((size_t)t * A.cap + T->pend_parent) * A.sp;
+    for (int i = lane; i < CH; i += 32) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + 16 * i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        AosAcc s{wsm};
+        float es[N];
+        uint32_t m[SPL_MASK_WORDS];
+        const bool ended = mcts_rules_core<N>(s, action, rules, es, m);
+#pragma unroll
+        for (int i = 0; i < SPL_MASK_WORDS; i++) A.stage_mask[(size_t)i * A.n_trees + t] = m[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) A.stage_es[(size_t)t * 4 + i] = i < N ? es[i] : 0.f;
+        A.stage_ended[t] = ended ? 1 : 0;
+        A.leaf_src[t] = 1;
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(A.stage_state + (size_t)t * A.sp);
+    for (int i = lane; i < CH; i += 32) dst[i] = reinterpret_cast<const uint4*>(wsm)[i];
+}
+
+// expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree);
+// RULES: followed by the rules step of the tree's pending edge (spl_mcts_wave_nnet; otherwise mcts_rules_kernel does it)
+template <int N, bool RULES>
+__global__ void __launch_bounds__(MW * 32, 7) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
                                                                          int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
+    PROF_STAMP(A, t, 0, prof_globaltimer()); PROF_STAMP(A, t, 1, clock64());
     mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
     w.sync();
-    mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+    PROF_STAMP(A, t, 2, clock64());
+    const int r = mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+    PROF_STAMP(A, t, 3, clock64()); PROF_STAMP(A, t, 4, (long long)r * 1000 + A.trees[t].path_len);
+    if (RULES) {
+        if (r == 2) rules_for_own_tree<N>(A, t, P.rules, sc.st, w.lane);
+        PROF_STAMP(A, t, 9, clock64());
+    }
+    PROF_STAMP(A, t, 5, prof_globaltimer());
 }
 
 template <int N>
@@ -213,7 +298,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ArenaPlan {
     int sp, hcap, max_depth;
-    size_t off_states, off_nodes, off_edges, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, total;
+    size_t off_states, off_nodes, off_edges, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, off_lsrc, total;
 };
 static ArenaPlan plan_arena(int n, int T, int cap, int ecap) {
     ArenaPlan p;
@@ -232,6 +317,7 @@ static ArenaPlan plan_arena(int n, int T, int cap, int ecap) {
     p.off_smask = o;  o = align_up(o + (size_t)T * 13 * 4, 256);
     p.off_ses = o;    o = align_up(o + (size_t)T * 16, 256);
     p.off_sended = o; o = align_up(o + (size_t)T, 256);
+    p.off_lsrc = o;   o = align_up(o + (size_t)T, 256);
     p.total = o;
     return p;
 }
@@ -270,14 +356,36 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     m->A.stage_mask = (uint32_t*)(base + p.off_smask);
     m->A.stage_es = (float*)(base + p.off_ses);
     m->A.stage_ended = (uint8_t*)(base + p.off_sended);
+    m->A.leaf_src = (uint8_t*)(base + p.off_lsrc);
+    m->A.prof = nullptr;
     m->P.cpuct = 1.0; m->P.fpu = 0.0; m->P.temperature0 = 1.0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules = ctx->rules;
     m->edge_reserve = 32; m->gc_reachable = 0; m->rounds = 1; m->max_levels = 1 << 20;
+    m->rules_tpw = 8;
+    if (const char* e = getenv("SPL_MCTS_RULES_TPW")) {   // tuning hook (4, 8 or 16)
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16) m->rules_tpw = v;
+    }
+    m->fuse_rules = 1;
+    if (const char* e = getenv("SPL_MCTS_FUSE_RULES")) m->fuse_rules = atoi(e) != 0;   // tuning hook
+    m->side = nullptr; m->ev_fork = nullptr; m->ev_join = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete m;
+        return spl_fail_(SPL_E_CUDA, "spl_mcts_create: stream / event creation failed");
+    }
     *out = m;
     return SPL_OK;
 }
 
-void spl_mcts_destroy(spl_mcts* m) { delete m; }
+void spl_mcts_destroy(spl_mcts* m) {
+    if (!m) return;
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->side) cudaStreamDestroy(m->side);
+    delete m;
+}
 
 int spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p) {
     if (!m || !p) return spl_fail_(SPL_E_ARG, "spl_mcts_set_params: null argument");
@@ -319,17 +427,13 @@ int spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const 
 int spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream) {
     ENTER_M(m);
     if (!leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_select: bad argument");
-    const int tiles = (m->A.n_trees + 31) / 32;
     const SplRules rules = m->ctx->rules;
     DISPATCH_N(m->ctx->n, {
-        const int smem = RW * MctsLay<N>::S * 32;
-        auto rk = mcts_rules_kernel<N>;
-        CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
             mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
-            rk<<<(tiles + RW - 1) / RW, RW * 32, smem, st>>>(m->A, rules);
-            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt);
+            CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
+            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
         }
     });
     CU(cudaGetLastError());
@@ -340,19 +444,43 @@ int spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const d
                            uint8_t* leaf_flags, int32_t* counters, void* stream) {
     ENTER_M(m);
     if (!pi || !v || !leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_expand_select: bad argument");
-    const int tiles = (m->A.n_trees + 31) / 32;
     const SplRules rules = m->ctx->rules;
     DISPATCH_N(m->ctx->n, {
-        const int smem = RW * MctsLay<N>::S * 32;
-        auto rk = mcts_rules_kernel<N>;
-        CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
-            if (r == 0) mcts_expand_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            if (r == 0) mcts_expand_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
             else mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
-            rk<<<(tiles + RW - 1) / RW, RW * 32, smem, st>>>(m->A, rules);
-            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt);
+            CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
+            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
         }
+    });
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, const double* dir_values, int8_t* leaf_states,
+                       uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream) {
+    ENTER_M(m);
+    if (!nnet_blob || !pi || !v || !leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_wave_nnet: bad argument");
+    const SplRules rules = m->ctx->rules;
+    DISPATCH_N(m->ctx->n, {
+        m->P.rules = rules;
+        if (m->fuse_rules) {
+            mcts_expand_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+        } else {
+            mcts_expand_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
+        }
+        // fork: the network reads the rows the descent (leaf rows) or the rules kernel (staging rows) just wrote, while the
+        // attach kernel links the new children into the trees; join before the next wave's expansion reads pi / v
+        CU(cudaEventRecord(m->ev_fork, st));
+        CU(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+        const int rc = spl_nnet_forward_rows_(m->ctx, nnet_blob, leaf_states, leaf_valids, m->A.leaf_src, m->A.stage_state, m->A.sp, m->A.stage_mask,
+                                              m->A.n_trees, m->A.n_trees, pi, v, m->side);
+        if (rc != SPL_OK) return rc;
+        CU(cudaEventRecord(m->ev_join, m->side));
+        mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
+        CU(cudaStreamWaitEvent(st, m->ev_join, 0));
     });
     CU(cudaGetLastError());
     return SPL_OK;
@@ -378,6 +506,12 @@ int spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32
     ENTER_M(m);
     mcts_stats_kernel<<<grid, MW * 32, 0, st>>>(m->A, nsa, qsa, ps, info);
     CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_debug_profile(spl_mcts* m, long long* stamps) {   /* diagnostics only: int64[T][16] device buffer, NULL = off */
+    if (!m) return spl_fail_(SPL_E_ARG, "null mcts handle");
+    m->A.prof = stamps;
     return SPL_OK;
 }
 

@@ -68,13 +68,24 @@ struct MctsWarp {
         return v;
     }
     __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
-    __device__ __forceinline__ void best(double& u, int& idx) const {   // arg-max, lowest index wins ties; idx < 0 = none
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const double ou = __shfl_xor_sync(0xffffffffu, u, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (oi >= 0 && (idx < 0 || ou > u || (ou == u && oi < idx))) { u = ou; idx = oi; }
-        }
+    // arg-max, lowest index wins ties; idx < 0 = none. Three warp reductions (REDUX) on an order-preserving integer image of the
+    // double instead of five shuffle rounds: max of the high words, max of the low words among those, min index among those.
+    // u + 0.0 maps -0.0 to +0.0 so that equal doubles have equal images (no NaNs occur).
+    __device__ __forceinline__ void best(double& u, int& idx) const {
+        const long long b = __double_as_longlong(u + 0.0);
+        const unsigned long long key = idx < 0 ? 0ull : (b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull));
+        const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const bool win = idx >= 0 && hi == mh && lo == ml;
+        const int bi = __reduce_min_sync(0xffffffffu, win ? idx : 0x7fffffff);
+        idx = bi == 0x7fffffff ? -1 : bi;
+    }
+    // the two square roots of pick_highest_UCB in ONE pass through the sqrt sequence: odd lanes take b, even lanes a
+    __device__ __forceinline__ void sqrt2(double a, double b, double& ra, double& rb) const {
+        const double r = MC_DSQRT((lane & 1) ? b : a);
+        ra = __shfl_sync(0xffffffffu, r, 0);
+        rb = __shfl_sync(0xffffffffu, r, 1);
     }
 };
 #else
@@ -89,6 +100,7 @@ struct MctsWarp {
     double sumd_tree(double v) const { return v; }
     int shfl(int v, int) const { return v; }
     void best(double&, int&) const {}
+    void sqrt2(double a, double b, double& ra, double& rb) const { ra = MC_DSQRT(a); rb = MC_DSQRT(b); }
 };
 #endif
 
@@ -131,7 +143,8 @@ struct MctsTree {   // 96 B
     int32_t cur;         // >= 0: continue the descent at this node with path_len edges already recorded; -1: start at the root
     int32_t pend_edge;   // >= 0: the descent stopped at this (absolute) edge, whose child state is being computed / attached
     int32_t pend_parent; // node index of that edge's parent
-    int32_t pad[3];
+    int32_t spec_hits;   // diagnostics: levels of the descents that started from the early-fetched child (see mcts_descend_tree)
+    int32_t pad[2];
 };
 struct MctsArena {
     int n_trees, cap, ecap, hcap, sp, max_depth;
@@ -146,6 +159,9 @@ struct MctsArena {
     uint32_t* stage_mask;  // [13][T]
     float* stage_es;       // [T][4]
     uint8_t* stage_ended;  // [T]
+    long long* prof;       // diagnostics (normally NULL): [T][16] per-tree time stamps of the last wave (spl_mcts_debug_profile)
+    uint8_t* leaf_src;     // [T]  where the network input of the tree's leaf lives: 0 = its leaf row (bytes), 1 = the staging row
+                           //      (state bytes + mask words) the rules kernel wrote - lets the network start before the attach
 };
 struct MctsSearchParams {
     double cpuct, fpu, temperature0, dirichlet_alpha;
@@ -405,7 +421,8 @@ template <class W>
 SPL_D int mcts_pick(const W& w, const MctsEdge* ed, const MctsEdge& first, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced,
                     int n_iter) {   // `first` = ed[lane], fetched by the caller together with the node header
     const double fpu_init = P.fpu > 0.0 ? MC_DADD((double)Qs, -P.fpu) : P.fpu;   // :202
-    const double sq_ns = MC_DSQRT((double)Ns), sq_ns_eps = MC_DSQRT(MC_DADD((double)Ns, MCTS_EPS));
+    double sq_ns, sq_ns_eps;
+    w.sqrt2((double)Ns, MC_DADD((double)Ns, MCTS_EPS), sq_ns, sq_ns_eps);
     double best_u = 0.0;
     int best_i = -1, forced_i = 0x7fffffff;
     for (int i = w.lane; i < k; i += W::W) {
@@ -465,16 +482,20 @@ SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const f
 
 // hands a node that waits for the network to the leaf row of its tree (:136-138)
 template <int N, class W>
-SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid) {
+SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
+                          bool rows = true) {   // rows = false: the staging row of the rules kernel already holds this very state and mask
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
-    const MctsNode* nd = A.nodes + (size_t)t * A.cap + node;
-    const int8_t* src = A.states + ((size_t)t * A.cap + node) * A.sp;
-    for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
-    for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
-    w.sync();
-    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
-    for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
+    if (rows) {
+        const MctsNode* nd = A.nodes + (size_t)t * A.cap + node;
+        const int8_t* src = A.states + ((size_t)t * A.cap + node) * A.sp;
+        for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
+        for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
+        w.sync();
+        const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+        for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
+        if (w.lane == 0) A.leaf_src[t] = 0;
+    }
     if (w.lane == 0) { T->leaf = node; T->path_len = depth; T->sims_done = sims_done; T->cur = -1; T->pend_edge = -1; }
     w.sync();
 }
@@ -509,25 +530,66 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
     // where the edges of `cur` are expected: known from the parent's edge, or from the node header at the start of a walk
     uint32_t eoff = nodes[cur].edge_off;
     int ne = nodes[cur].kind == MCTS_NODE_TERMINAL ? 0 : (int)nodes[cur].n_edges;
+    // The child the PREVIOUS visit of a node chose is fetched (header + edges) while this visit is still computing its pick: the
+    // search tends to walk the same line again, and then the next level starts without a memory round trip. The hint lives in
+    // a spare word of the node header (edge position + 1); it never influences a result, only what is loaded early.
+    bool have_spec = false;
+    MctsEdge spec_first;
+    MctsNode spec_nd;
     while (sims_done < target) {
         for (;;) {
-            const MctsNode* ndp = nodes + cur;
             const MctsEdge* ed = edges + eoff;
             MctsEdge first;                                  // header and first 32 edges: one round trip
-            first.Q = MCTS_UNVISITED; first.P = 0.f; first.N = 0; first.child = 0u; first.action = 0; first.child_ne = 0; first.child_eoff = 0u; first.pad = 0u;
-            if (w.lane < ne) first = ed[w.lane];
-            const MctsNode nd = *ndp;
+            MctsNode nd;
+            if (have_spec) {
+                first = spec_first; nd = spec_nd;
+            } else {
+                first.Q = MCTS_UNVISITED; first.P = 0.f; first.N = 0; first.child = 0u; first.action = 0; first.child_ne = 0; first.child_eoff = 0u; first.pad = 0u;
+                if (w.lane < ne) first = ed[w.lane];
+                nd = nodes[cur];
+            }
+            have_spec = false;
             const int kind = nd.kind;
             if (kind == MCTS_NODE_NEEDS_NN) {
                 mcts_emit_leaf<N>(w, A, t, cur, depth, sims_done, leaf_state, leaf_valid);
                 return 1;
             }
             if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
+            int hp = -1;
+            const int hint = (int)nd.u.x.pad[0] - 1;
+#ifdef __CUDACC__
+            if (hint >= 0 && hint < 32 && hint < (int)nd.n_edges) {
+                const uint32_t hchild = __shfl_sync(0xffffffffu, first.child, hint);
+                const uint32_t heoff = __shfl_sync(0xffffffffu, first.child_eoff, hint);
+                const int hne = __shfl_sync(0xffffffffu, (int)first.child_ne, hint);
+                if (hchild != 0u) {
+                    hp = hint;
+                    spec_first.Q = MCTS_UNVISITED; spec_first.P = 0.f; spec_first.N = 0; spec_first.child = 0u; spec_first.action = 0;
+                    spec_first.child_ne = 0; spec_first.child_eoff = 0u; spec_first.pad = 0u;
+                    if (w.lane < hne) spec_first = edges[heoff + w.lane];
+                    spec_nd = nodes[hchild - 1u];
+                }
+            }
+#endif
             const int ei = mcts_pick(w, ed, first, (int)nd.n_edges, nd.u.x.Ns, nd.u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
-            if (w.lane == 0) { path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd.edge_off + (uint32_t)ei; }
+            if (w.lane == 0) {
+                path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd.edge_off + (uint32_t)ei;
+                if (ei != hint) nodes[cur].u.x.pad[0] = (uint32_t)ei + 1u;
+            }
             depth++;
-            const MctsEdge sel = ed[ei];
-            const uint32_t child = sel.child;
+            uint32_t child, child_eoff;
+            int child_ne;
+#ifdef __CUDACC__
+            if (ei < 32) {
+                child = __shfl_sync(0xffffffffu, first.child, ei);
+                child_eoff = __shfl_sync(0xffffffffu, first.child_eoff, ei);
+                child_ne = __shfl_sync(0xffffffffu, (int)first.child_ne, ei);
+            } else
+#endif
+            {
+                const MctsEdge sel = ed[ei];
+                child = sel.child; child_eoff = sel.child_eoff; child_ne = (int)sel.child_ne;
+            }
             if (child != 0u && --max_levels <= 0) {   // yield: a very deep path finishes in the next call instead of holding up the wave
                 if (w.lane == 0) { T->cur = (int)child - 1; T->path_len = depth; T->sims_done = sims_done; }
                 w.sync();
@@ -542,7 +604,11 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
                 return 2;
             }
             cur = (int)child - 1;
-            eoff = sel.child_eoff; ne = (int)sel.child_ne;
+            eoff = child_eoff; ne = child_ne;
+            have_spec = ei == hp;
+#ifdef __CUDACC__
+            if (have_spec && w.lane == 0) atomicAdd(&T->spec_hits, 1);
+#endif
         }
         {   // terminal: return Es up the path
             float v[N];
@@ -570,7 +636,7 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
 // from that node in the next mcts_descend_tree call. Returns 1 if a leaf row was written, 0 otherwise.
 template <int N, class W>
 SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* st, bool ended, const float* es,
-                           const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid) {
+                           const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid, bool emit_rows = true) {
     MctsTree* T = A.trees + t;
     const int pe = T->pend_edge;
     if (pe < 0) return T->leaf >= 0 ? 1 : 0;
@@ -593,7 +659,7 @@ SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSear
     const int kind = nodes[idx].kind;
     const int depth = T->path_len, sims_done = T->sims_done;
     if (kind == MCTS_NODE_NEEDS_NN) {
-        mcts_emit_leaf<N>(w, A, t, idx, depth, sims_done, leaf_state, leaf_valid);
+        mcts_emit_leaf<N>(w, A, t, idx, depth, sims_done, leaf_state, leaf_valid, emit_rows);
         return 1;
     }
     if (kind == MCTS_NODE_TERMINAL) {
@@ -958,7 +1024,7 @@ SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_a
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
         T->n_nodes = 0; T->n_edges = 0; T->root = -1; T->leaf = -1; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
-        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
+        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->spec_hits = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
     }
     w.sync();
 }
@@ -1112,6 +1178,7 @@ SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* 
         memcpy(&info[7], &qs, 4);
         memcpy(&info[8], T->last_v, 16);
         info[12] = T->depth_sum;
+        info[13] = T->spec_hits;
     }
     w.sync();
 }

@@ -161,31 +161,50 @@ __device__ __forceinline__ void strip_gemm(const uint32_t (&afr)[8][4], const __
     }
 }
 
-// stage B: 16 rows shared by all warps (A from shared memory), this warp computes ONE output tile (8 n) of the block
-template <int KS>
-__device__ __forceinline__ void tile_gemm(float (&c)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride, int lane) {
+// stage B: 16 rows shared by all warps (A from shared memory); this warp computes NT output tiles (8 n each, block rows at
+// w[t]) that share the A fragments. mma.sync has a long dependent latency, so the k-steps of every tile alternate between two
+// accumulators (summed at the end): 2 NT independent chains of KS / 2 instead of NT chains of KS one after the other.
+template <int KS, int NT>
+__device__ __forceinline__ void tiles_gemm(float (&c)[NT][4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* const (&w)[NT], int wstride,
+                                           int lane) {
+    float d[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[t][i] = 0.f;
     const __nv_bfloat16* al = a_lane_ptr(a, astride, lane);
-    const __nv_bfloat16* wl = b1_lane_ptr(w, wstride, lane);
 #pragma unroll
     for (int ks = 0; ks + 1 < KS; ks += 2) {
-        uint32_t a0[4], a1[4], b[4];
+        uint32_t a0[4], a1[4];
         ldsm4(a0, al + ks * 16);
         ldsm4(a1, al + ks * 16 + 16);
-        ldsm4(b, wl + ks * 16);
-        mma_bf16(c, a0, b[0], b[1]);
-        mma_bf16(c, a1, b[2], b[3]);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            uint32_t b[4];
+            ldsm4(b, b1_lane_ptr(w[t], wstride, lane) + ks * 16);
+            mma_bf16(c[t], a0, b[0], b[1]);
+            mma_bf16(d[t], a1, b[2], b[3]);
+        }
     }
     if (KS & 1) {
-        uint32_t a0[4], b0, b1;
+        uint32_t a0[4];
         ldsm4(a0, al + (KS - 1) * 16);
-        ldsm2(b0, b1, w + (lane & 7) * wstride + ((lane >> 3) & 1) * 8 + (KS - 1) * 16);
-        mma_bf16(c, a0, b0, b1);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            uint32_t b0, b1;
+            ldsm2(b0, b1, w[t] + (lane & 7) * wstride + ((lane >> 3) & 1) * 8 + (KS - 1) * 16);
+            mma_bf16(c[t], a0, b0, b1);
+        }
     }
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) c[t][i] += d[t][i];
 }
-// same A, TWO adjacent output tiles (16 n) of the block
+// same A, TWO adjacent output tiles (16 n) of the block; even / odd k-steps go to separate accumulator pairs
 template <int KS>
-__device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], const __nv_bfloat16* a, int astride, const __nv_bfloat16* w, int wstride,
-                                           int lane) {
+__device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], float (&d0)[4], float (&d1)[4], const __nv_bfloat16* a, int astride,
+                                           const __nv_bfloat16* w, int wstride, int lane) {
     const __nv_bfloat16* al = a_lane_ptr(a, astride, lane);
     const __nv_bfloat16* wl = b2_lane_ptr(w, wstride, lane);
 #pragma unroll
@@ -193,8 +212,8 @@ __device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], const
         uint32_t af[4], b[4];
         ldsm4(af, al + ks * 16);
         ldsm4(b, wl + ks * 16);
-        mma_bf16(c0, af, b[0], b[1]);
-        mma_bf16(c1, af, b[2], b[3]);
+        if (ks & 1) { mma_bf16(d0, af, b[0], b[1]); mma_bf16(d1, af, b[2], b[3]); }
+        else { mma_bf16(c0, af, b[0], b[1]); mma_bf16(c1, af, b[2], b[3]); }
     }
 }
 
@@ -203,8 +222,10 @@ __device__ long long g_nn_stamps[32];   // diagnostics: phase time stamps of CTA
 
 template <int NP>
 __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsigned char* __restrict__ blob, NnPlan plan, const int8_t* __restrict__ states,
-                                                                     const uint8_t* __restrict__ valids, int n_rows, float* __restrict__ pi,
-                                                                     float* __restrict__ vout) {
+                                                                     const uint8_t* __restrict__ valids, const uint8_t* __restrict__ row_src,
+                                                                     const int8_t* __restrict__ alt_states, int alt_stride,
+                                                                     const uint32_t* __restrict__ alt_mask, int alt_mask_stride, int n_rows,
+                                                                     float* __restrict__ pi, float* __restrict__ vout) {
     constexpr int R = 32 + 10 * NP + NP * NP, S = 7 * R, K1 = (R + 15) / 16 * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NnSmem& smem_all = *reinterpret_cast<NnSmem*>(smem_raw);
@@ -238,12 +259,14 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     };
     auto slot_of = [&](int b) -> const __nv_bfloat16* { return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]); };
     auto release = [&]() { __syncthreads(); };
+    while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // the first weight blocks travel while the input rows are converted
 
     // ---- input: act[c*16 + s][k] = state[s][k][c]  (int8 counts are exact in bf16), zero padding up to K1
     for (int i = gtid; i < NN_SB * K1; i += 256) {
         const int s = i / K1, k = i - s * K1;
         const bool in = k < R && s < live;
-        const int8_t* src = states + (size_t)(base + s) * S + k * 7;
+        const bool alt = in && row_src && row_src[base + s];   // the tree arena's staging row (written by its rules kernel)
+        const int8_t* src = (alt ? alt_states + (size_t)(base + s) * alt_stride : states + (size_t)(base + s) * S) + k * 7;
 #pragma unroll
         for (int c = 0; c < 7; c++) sm.act[(c * 16 + s) * ASTR + k] = __float2bfloat16(in ? (float)src[c] : 0.f);
     }
@@ -361,12 +384,22 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     // ---- L4: Linear(704,128) + ReLU. 16 rows; warp w owns output tiles 2w, 2w+1; accumulate over 11 k-blocks
     {
         float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[2][2][2][4];   // [k-block parity][k-step parity][tile]: eight independent accumulation chains
+#pragma unroll
+        for (int i = 0; i < 32; i++) (&acc[0][0][0][0])[i] = 0.f;
         for (int kb = 0; kb < 11; kb += 2) {   // two k-blocks per ring step
             const int cnt = kb + 1 < 11 ? 2 : 1;
             acquire(blk, cnt);
-            for (int q = 0; q < cnt; q++)
-                tile2_gemm<4>(c0, c1, sm.flat + (kb + q) * 64, FSTR, slot_of(blk + q) + (2 * warp) * 8 * 72, 72, lane);
+            tile2_gemm<4>(acc[0][0][0], acc[0][0][1], acc[0][1][0], acc[0][1][1], sm.flat + kb * 64, FSTR, slot_of(blk) + (2 * warp) * 8 * 72, 72, lane);
+            if (cnt == 2)
+                tile2_gemm<4>(acc[1][0][0], acc[1][0][1], acc[1][1][0], acc[1][1][1], sm.flat + (kb + 1) * 64, FSTR, slot_of(blk + 1) + (2 * warp) * 8 * 72,
+                              72, lane);
             release(); blk += cnt;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            c0[i] = (acc[0][0][0][i] + acc[0][1][0][i]) + (acc[1][0][0][i] + acc[1][1][0][i]);
+            c1[i] = (acc[0][0][1][i] + acc[0][1][1][i]) + (acc[1][0][1][i] + acc[1][1][1][i]);
         }
         __nv_bfloat16* o = sm.vec[0];
 #pragma unroll
@@ -382,11 +415,15 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     // stage B helpers: in -> out, the two [64 n][KB] blocks of a layer in ONE ring step, warp w owns tile w of each block
     auto dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias, bool relu) {
         acquire(blk, 2);
+        if (pbias == P_B5A) NN_STAMP(12);
+        float cc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        {
+            const __nv_bfloat16* const ws[2] = {slot_of(blk) + warp * 8 * ASTR, slot_of(blk + 1) + warp * 8 * ASTR};
+            tiles_gemm<8, 2>(cc, in, ASTR, ws, ASTR, lane);
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = slot_of(blk + h);
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<8>(c, in, ASTR, w + warp * 8 * ASTR, ASTR, lane);
+            float(&c)[4] = cc[h];
             const int n = h * 64 + warp * 8 + 2 * t;
             const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
             float v0 = c[0] + b0, v1 = c[1] + b1, v2 = c[2] + b0, v3 = c[3] + b1;
@@ -394,7 +431,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             sts_bf16x2(out + g * ASTR + n, v0, v1);
             sts_bf16x2(out + (g + 8) * ASTR + n, v2, v3);
         }
+        if (pbias == P_B5A) NN_STAMP(13);
         release(); blk += 2;
+        if (pbias == P_B5A) NN_STAMP(14);
     };
     auto pool_dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias) {   // 4 groups of 4 + Linear(112,120)+BN(1)+ReLU
         if (gtid < 64) {
@@ -406,11 +445,14 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             out[row * ASTR + 4 + grp] = __float2bfloat16((a.x + a.y + b.x + b.y) * 0.25f);
         }
         acquire(blk, 2);
+        float cc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        {
+            const __nv_bfloat16* const ws[2] = {slot_of(blk) + warp * 8 * 120, slot_of(blk + 1) + warp * 8 * 120};
+            tiles_gemm<7, 2>(cc, in + 16, ASTR, ws, 120, lane);
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = slot_of(blk + h);
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<7>(c, in + 16, ASTR, w + warp * 8 * 120, 120, lane);
+            float(&c)[4] = cc[h];
             const int n = h * 64 + warp * 8 + 2 * t;
             if (n < 120) {
                 const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
@@ -434,9 +476,13 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     for (int h = 0; h < 7; h += 2) {   // two 64-row blocks per ring step
         const int cnt = h + 1 < 7 ? 2 : 1;
         acquire(blk, cnt);
+        float cc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        {   // (the last step has one block: its second tile re-reads the first and is dropped)
+            const __nv_bfloat16* const ws[2] = {slot_of(blk) + warp * 8 * ASTR, slot_of(blk + cnt - 1) + warp * 8 * ASTR};
+            tiles_gemm<8, 2>(cc, sm.vec[1], ASTR, ws, ASTR, lane);
+        }
         for (int q = 0; q < cnt; q++) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<8>(c, sm.vec[1], ASTR, slot_of(blk + q) + warp * 8 * ASTR, ASTR, lane);
+            float(&c)[4] = cc[q];
             const int n = (h + q) * 64 + warp * 8 + 2 * t;
             if (n < LSTR) {
                 const float b0 = prm[P_BP1 + n], b1 = prm[P_BP1 + n + 1];
@@ -451,8 +497,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     {
         const __nv_bfloat16* w = acquire(blk, 1);
         if (warp == 0) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            tile_gemm<8>(c, sm.vec[2], ASTR, w, ASTR, lane);
+            float cc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+            const __nv_bfloat16* const ws[1] = {w};
+            tiles_gemm<8, 1>(cc, sm.vec[2], ASTR, ws, ASTR, lane);
+            float(&c)[4] = cc[0];
             const int n = 2 * t;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -467,12 +515,17 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     for (int s = warp * 2; s < warp * 2 + 2; s++) {
         if (s >= live) continue;
         const uint8_t* va = valids + (size_t)(base + s) * NN_ACTIONS;
+        const bool alt = row_src && row_src[base + s];
         float x[13], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 13; j++) {
             const int a = lane + 32 * j;
             x[j] = -INFINITY;
-            if (a < NN_ACTIONS) { x[j] = va[a] ? logits[s * LSTR + a] : -1e8f; mx = fmaxf(mx, x[j]); }
+            if (a < NN_ACTIONS) {
+                const bool ok = alt ? ((alt_mask[(size_t)j * alt_mask_stride + base + s] >> lane) & 1u) != 0u : va[a] != 0;
+                x[j] = ok ? logits[s * LSTR + a] : -1e8f;
+                mx = fmaxf(mx, x[j]);
+            }
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -588,21 +641,28 @@ int spl_nnet_debug_stamps(long long* out32) {   /* diagnostics only: SM-clock st
 }
 
 int spl_nnet_forward(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream) {
+    return spl_nnet_forward_rows_(c, blob, states, valids, nullptr, nullptr, 0, nullptr, 0, n_rows, pi, v, (cudaStream_t)stream);
+}
+
+}   // extern "C"
+
+int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, const uint8_t* row_src,
+                           const int8_t* alt_states, int alt_stride, const uint32_t* alt_mask, int alt_mask_stride, int n_rows, float* pi,
+                           float* v, cudaStream_t st) {
     if (!c) return spl_fail_(SPL_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
     if (!blob || !states || !valids || !pi || !v || n_rows <= 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: bad argument");
+    if (row_src && (!alt_states || !alt_mask)) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: row_src without staging rows");
     if (((uintptr_t)blob & 15u) != 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: blob must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     const NnPlan p = make_plan(c->n);
     const int grid = (n_rows + NN_SB * NN_GROUPS - 1) / (NN_SB * NN_GROUPS);
     const int smem = (int)sizeof(NnSmem);
     DISPATCH_N(c->n, {
         auto k = nnet_forward_kernel<N>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k<<<grid, NN_THREADS, smem, st>>>((const unsigned char*)blob, p, states, valids, n_rows, pi, v);
+        k<<<grid, NN_THREADS, smem, st>>>((const unsigned char*)blob, p, states, valids, row_src, alt_states, alt_stride, alt_mask, alt_mask_stride,
+                                          n_rows, pi, v);
     });
     CU(cudaGetLastError());
     return SPL_OK;
 }
-
-}   // extern "C"

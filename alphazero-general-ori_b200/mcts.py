@@ -59,6 +59,7 @@ class MCTSArena:
                            game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds), max_levels=int(max_levels))
         self.set_params()
         self.launches = 0
+        self._nn_pending, self._nn_dir = None, None
         self.reset()
 
     def __del__(self):
@@ -104,6 +105,7 @@ class MCTSArena:
 
     def select(self, count=False):
         """one selection wave (`rounds` x (descend, rules, attach) kernels)"""
+        self.drain_nnet()
         nat.check(self._lib.spl_mcts_select(self._m, _ptr(self.leaf_states), _ptr(self.leaf_valids), _ptr(self.leaf_flags),
                                             _ptr(self.counters) if count else None, self._stream()))
         self.launches += 3 * self.params["rounds"]
@@ -124,6 +126,26 @@ class MCTSArena:
         """steady-state wave for leaves that are already selected: network -> expand + next selection"""
         pi, v = evaluator(self.leaf_states, self.leaf_valids)
         self.expand_select(pi, v, dir_values)
+
+    def wave_nnet(self, net, dir_values=None):
+        """steady-state wave with the fused evaluator inside (spl_mcts_wave_nnet): expansion of the previous leaves + next
+        descent -> rules -> {attach || network}. `net` = FusedSplendorNNet; its static output rows carry the network results
+        from one wave to the next. Same results as `wave_steady`."""
+        pi, v = net.out_buffers(self.T)
+        if self._nn_pending is not net:      # leaves were selected the classic way: their rows need the network first
+            net(self.leaf_states, self.leaf_valids)
+            self._nn_pending = net
+        self._nn_dir = dir_values
+        nat.check(self._lib.spl_mcts_wave_nnet(self._m, C.c_void_p(net.blob_ptr), _ptr(pi), _ptr(v), _ptr(dir_values), _ptr(self.leaf_states),
+                                               _ptr(self.leaf_valids), _ptr(self.leaf_flags), None, self._stream()))
+        self.launches += 4
+
+    def drain_nnet(self, dir_values=None):
+        """after `wave_nnet`: back the pending network results up, so that the classic calls (select / expand / finish) can follow"""
+        if self._nn_pending is not None:
+            pi, v = self._nn_pending.out_buffers(self.T)
+            self._nn_pending = None
+            self.expand(pi, v, dir_values if dir_values is not None else self._nn_dir)
 
     def remaining(self):
         """one (leaf-less) selection wave that counts the trees whose budget is not spent yet -> int (host sync)"""
@@ -152,9 +174,19 @@ class MCTSArena:
         self.begin(roots, sims, move_flags, tree_select, dir_values)
         if waves is None:
             waves = int(sims.max().item())
-        for _ in range(waves):
-            self.wave(evaluator, dir_values)
+        if self._is_fused(evaluator):      # network inside the wave, next to the attach kernel (same results)
+            self.select()
+            for _ in range(waves):
+                self.wave_nnet(evaluator, dir_values)
+        else:
+            for _ in range(waves):
+                self.wave(evaluator, dir_values)
         self.finish(evaluator, dir_values)
+
+    @staticmethod
+    def _is_fused(evaluator):
+        from .nnet import FusedSplendorNNet
+        return isinstance(evaluator, FusedSplendorNNet)
 
     def wave(self, evaluator, dir_values=None):
         self.select()
@@ -165,12 +197,18 @@ class MCTSArena:
         """waves until every tree has spent its budget. One host synchronisation per `chunk()` call (default: 8 waves);
         returns the number of extra waves."""
         extra = 0
+        fused = chunk is None and self._is_fused(evaluator)
         while True:
             self.counters.zero_()
             self.select(count=True)
             left = int(self.counters[1].item())
             if left == 0:
                 return extra
+            if fused:
+                for _ in range(8):
+                    self.wave_nnet(evaluator, dir_values)
+                extra += 8
+                continue
             pi, v = evaluator(self.leaf_states, self.leaf_valids)
             self.expand(pi, v, dir_values)
             extra += 1
@@ -228,7 +266,7 @@ class MCTSArena:
         self.launches += 1
         return dict(nsa=nsa, qsa=qsa, ps=ps, nodes=info[:, 0], edges=info[:, 1], ns=info[:, 2], sims_done=info[:, 3],
                     nn_calls=info[:, 4], status=info[:, 5] & 0xFF, truncated=info[:, 5] >> 8, resets=info[:, 6] >> 16, cleanings=info[:, 6] & 0xFFFF,
-                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32), depth_sum=info[:, 12])
+                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32), depth_sum=info[:, 12], spec_hits=info[:, 13])
 
     def check_status(self):
         st = self.root_stats(want_arrays=False)["status"]

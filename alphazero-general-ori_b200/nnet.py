@@ -215,13 +215,21 @@ class FusedSplendorNNet:
         self._blob_view = self.blob[off:off + blob.numel()]
         self._blob_view.copy_(blob)
 
-    def __call__(self, states, valids):
-        B = states.shape[0]
+    def out_buffers(self, B):
         out = self._out.get(B)
         if out is None:
-            out = (torch.empty((B, NUM_ACTIONS), dtype=torch.float32, device=self.device),
-                   torch.empty((B, self.n), dtype=torch.float32, device=self.device))
+            out = (torch.zeros((B, NUM_ACTIONS), dtype=torch.float32, device=self.device),
+                   torch.zeros((B, self.n), dtype=torch.float32, device=self.device))
             self._out[B] = out
+        return out
+
+    @property
+    def blob_ptr(self):
+        return self._blob_view.data_ptr()
+
+    def __call__(self, states, valids):
+        B = states.shape[0]
+        out = self.out_buffers(B)
         C = self._C
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         self._nat.check(self._lib.spl_nnet_forward(self._ctx, C.c_void_p(self._blob_view.data_ptr()), C.c_void_p(states.data_ptr()),

@@ -24,10 +24,12 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50):
+                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
+        self._evaluator = None
+        self._overlap_req = overlap_nnet      # None: whenever the evaluator is the fused kernel
         self.evaluator = evaluator
         self.env = SplendorEnv(n_players, n_games, device=device, seed=seed, game_base=game_base)
         self.device = self.env.device
@@ -51,10 +53,24 @@ class SelfPlayEngine:
         self.games_finished = torch.zeros((), dtype=torch.int64, device=self.device)
         self.sims_total = torch.zeros((), dtype=torch.int64, device=self.device)   # simulations requested so far
 
+    @property
+    def evaluator(self):
+        return self._evaluator
+
+    @evaluator.setter
+    def evaluator(self, ev):
+        from .nnet import FusedSplendorNNet
+        self._evaluator = ev
+        fused = isinstance(ev, FusedSplendorNNet)
+        self.overlap_nnet = fused if self._overlap_req is None else (bool(self._overlap_req) and fused)
+
     # ------------------------------------------------------------------
     def _wave(self):
         if getattr(self, "_async", False):
-            self.arena.wave_steady(self.evaluator)     # leaves are always selected one wave ahead
+            if self.overlap_nnet:
+                self.arena.wave_nnet(self.evaluator)   # network next to the attach kernel (spl_mcts_wave_nnet)
+            else:
+                self.arena.wave_steady(self.evaluator)     # leaves are always selected one wave ahead
         else:
             self.arena.wave(self.evaluator)
 

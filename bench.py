@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
     ap.add_argument("--max-levels", type=int, default=16, help="edges a descend call walks before it yields to the next wave (0: no limit)")
+    ap.add_argument("--overlap", type=int, default=1, help="1: the fused network runs next to the attach kernel (spl_mcts_wave_nnet); 0: one stream")
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
@@ -282,7 +283,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     clean_every = max(1, int(args.clean_moves * sims / G0)) if args.async_moves else 0
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
                              edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels,
-                             clean_every=clean_every, clean_percent=45)
+                             clean_every=clean_every, clean_percent=45, overlap_nnet=None if args.overlap else False)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
         eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
@@ -361,6 +362,18 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     sel = sum(e[0].elapsed_time(e[1]) for e in evs[20:]) / (nb - 20)
     nnt = sum(e[1].elapsed_time(e[2]) for e in evs[20:]) / (nb - 20)
     exp = sum(e[2].elapsed_time(e[3]) for e in evs[20:]) / (nb - 20)
+    ovl = None
+    if eng.overlap_nnet:      # the wave as the timed region runs it: network next to the attach kernel
+        for _ in range(20):
+            ar.wave_nnet(eng.evaluator)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nb):
+            ar.wave_nnet(eng.evaluator)
+        e1.record()
+        torch.cuda.synchronize()
+        ovl = e0.elapsed_time(e1) / nb
+        ar.drain_nnet()
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
@@ -370,7 +383,8 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_sim": B_SIM[n],
                 "note": "one launch = one simulation of every tree; the search is bound by the latency of sequential waves, not bytes",
-                "wave_breakdown_ms": {"selection (descend+rules+attach kernels x rounds)": sel, "network_forward": nnt, "mcts_expand_kernel": exp}}
+                "wave_breakdown_ms": {"selection (descend+rules+attach kernels x rounds)": sel, "network_forward": nnt, "mcts_expand_kernel": exp,
+                                      "whole wave, network next to the attach kernel (plain launches)": ovl}}
 
     line = {
         "metric": METRIC_MCTS, "value": value, "unit": UNIT_MCTS, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -378,13 +392,14 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
-                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves),
+                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
                    "moves_completed": int(eng.moves_completed.item()) if args.async_moves else args.steps * T, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
                        "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
+                       "early_fetch_hit_rate": float(st["spec_hits"].sum()) / max(1.0, float(st["depth_sum"].sum())),
                        "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, sims_now())},
     }
     if rank == 0:

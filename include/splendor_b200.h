@@ -220,6 +220,15 @@ int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double*
  * of a search: network -> expand_select -> network -> ...) */
 int  spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const double* dir_values, int8_t* leaf_states,
                             uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
+/* The steady-state wave with the fused evaluator (spl_nnet_*) inside, four launches:
+ *     expansion of the previous wave's leaves from pi / v + next descent -> rules -> { attach  ||  network -> pi, v }
+ * The network starts as soon as the child states exist (it reads them where the rules kernel left them) and runs on an
+ * internal side stream next to the attach kernel; the call joins it back into `stream` (CUDA-graph capturable). pi float[T][406]
+ * and v float[T][n] are in/out: on entry the network outputs of the leaves selected by the previous wave (spl_mcts_select /
+ * spl_mcts_expand_select + spl_nnet_forward, or the previous spl_mcts_wave_nnet), on return those of the new leaves.
+ * nnet_blob = device copy of the packed weights (spl_nnet_pack). Same results as expand_select + spl_nnet_forward. */
+int  spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, const double* dir_values, int8_t* leaf_states,
+                        uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
 /* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */
 int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* stream);
 /* raw root statistics, any pointer may be NULL: nsa int32[T][406], qsa double[T][406] (-42 = unvisited), ps float[T][406],
@@ -228,6 +237,11 @@ int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* s
  *                     finished simulation returned at the root (what MCTS.search returns, :99-177), then the sum of the
  *                     path lengths of the simulations since the last reset; 3 spare words */
 int  spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info, void* stream);
+/* diagnostics: per-tree time stamps of the wave kernels into stamps int64[T][16] (device memory; NULL switches it off again):
+ * expand+descend kernel [0] globaltimer at start, [1..3] SM clock at start / after the expansion / after the descent, [4] result code
+ * * 1000 + path length, [5] globaltimer at the end; rules kernel (first tree of each warp) [6] globaltimer, [7..10] SM clock at
+ * start / states loaded / rules done / end, [11] globaltimer; attach kernel [12] globaltimer, [13..14] SM clock, [15] globaltimer */
+int  spl_mcts_debug_profile(spl_mcts* m, long long* stamps);
 /* deterministic stand-in network ("fixed NN outputs"): a pure function of the state bytes with exact dyadic outputs; the
  * golden MCTS fixtures were produced by the reference's own MCTS.py with this function as its network */
 int  spl_mcts_fixed_net(spl_ctx* ctx, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream);

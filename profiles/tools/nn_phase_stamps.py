@@ -12,4 +12,12 @@ lib.spl_nnet_debug_stamps(buf)
 s = np.array(buf[:12], dtype=np.int64)
 names = ["start->input", "input+L1", "L2", "G1", "L3", "flatten", "L4", "G4..V0", "PI1", "V1", "softmax"]
 d = np.diff(s) / 1.965e3
+s2 = np.array(buf[:16], dtype=np.int64)
+print("L5a step: acquire->gemm+epilogue", round((s2[13]-s2[12])/1.965e3, 3), "release", round((s2[14]-s2[13])/1.965e3, 3), "step start (after G4) -> acquire done", "n/a")
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(41)]
+evs[0].record()
+for i in range(40):
+    net(st, va); evs[i + 1].record()
+torch.cuda.synchronize()
+print("kernel, back-to-back launches, us:", round(1e3 * evs[0].elapsed_time(evs[40]) / 40, 2))
 print("us per phase:", dict(zip(names, np.round(d, 2))), "total", round((s[11]-s[0])/1.965e3, 2))

@@ -42,6 +42,7 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     A.htab = (uint32_t*)calloc(A.hcap, 4);
     A.trees = (MctsTree*)calloc(1, sizeof(MctsTree));
     A.path = (uint32_t*)calloc((size_t)A.max_depth * 2, 4);
+    A.leaf_src = (uint8_t*)calloc(1, 1);
     A.trees[0].root = -1; A.trees[0].leaf = -1;
     m->P.cpuct = cpuct; m->P.fpu = fpu; m->P.temperature0 = temperature0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules.limit = limit; m->P.rules.flags = rule_flags;
@@ -53,7 +54,7 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     return m;
 }
 void hm_destroy(HsMcts* m) {
-    free(m->A.states); free(m->A.nodes); free(m->A.edges); free(m->A.htab); free(m->A.trees); free(m->A.path);
+    free(m->A.states); free(m->A.nodes); free(m->A.edges); free(m->A.htab); free(m->A.trees); free(m->A.path); free(m->A.leaf_src);
     free(m->leaf_state); free(m->leaf_valid); free(m->pi); free(m->v); free(m);
 }
 void hm_reset(HsMcts* m) {

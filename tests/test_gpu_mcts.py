@@ -360,3 +360,52 @@ def test_cleaning_between_waves_is_result_neutral_on_the_device(golden_dir):
             assert np.array_equal(_np(st["nsa"][t]).astype(np.int64), g["nsa"][i]), (i, t)
             assert np.allclose(_np(st["qsa"][t]), g["qsa"][i], rtol=0, atol=1e-12)
         assert int(st["cleanings"].min()) > 10 * (i + 1)
+
+
+@pytest.mark.parametrize("n,T", [(2, 200), (3, 67)])
+def test_overlapped_wave_equals_classic_wave(n, T):
+    """spl_mcts_wave_nnet (network on a side stream next to the attach kernel, input rows taken from the rules kernel's
+    staging rows) must give bit-identical trees to select -> spl_nnet_forward -> expand: same visit counts, same Q, same
+    node counts; ragged tree count, cleaning between waves, several moves with tree reuse, plain launches and a captured graph"""
+    az = _azg()
+    sims = 48
+    env = az.SplendorEnv(n, T, seed=5)
+    env.reset(); env.rollout(25 * n, rotate=True)
+    net = az.FusedSplendorNNet(n, seed=4)
+    net2 = az.FusedSplendorNNet(n, seed=4)
+    a = az.MCTSArena(n, T, node_cap=1024, cpuct=1.1, fpu=0.1, max_levels=6)
+    b = az.MCTSArena(n, T, node_cap=1024, cpuct=1.1, fpu=0.1, max_levels=6)
+    simt = torch.full((T,), sims, dtype=torch.int32, device=a.device)
+    simt[::3] = sims // 4                                  # ragged budgets (playout cap)
+    graph = None
+    for move in range(3):
+        roots = env.states().clone()
+        a.search(roots, simt, net)                         # classic, lock-step
+        b.begin(roots, simt)
+        b.select()
+        if move < 2:
+            for w in range(sims + 8):
+                b.wave_nnet(net2)
+                if w % 7 == 3:
+                    b.clean(0)
+        else:                                              # the same call sequence captured once and replayed
+            b.wave_nnet(net2)                              # (first call evaluates the classic leaf rows: outside the capture)
+            side = torch.cuda.Stream(b.device)
+            side.wait_stream(torch.cuda.current_stream(b.device))
+            with torch.cuda.stream(side):
+                b.wave_nnet(net2)
+            torch.cuda.current_stream(b.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(4):
+                    b.wave_nnet(net2)
+            for _ in range((sims + 8) // 4):
+                graph.replay()
+        b.finish(net2)
+        a.check_status(); b.check_status()
+        sa, sb = a.root_stats(), b.root_stats()
+        assert torch.equal(sa["nsa"], sb["nsa"]) and torch.equal(sa["qsa"], sb["qsa"]) and torch.equal(sa["ps"], sb["ps"]), move
+        assert torch.equal(sa["sims_done"], sb["sims_done"]) and torch.equal(sa["nn_calls"], sb["nn_calls"]) and torch.equal(sa["ns"], sb["ns"])
+        assert int(sa["sims_done"].min()) >= sims // 4
+        probs, _ = a.policy(1.0)
+        env.step(probs.argmax(1).to(torch.int16), player=0, chance="philox", rotate=True)
