@@ -2,19 +2,24 @@
 //
 // Replaces, for the tree arena's leaf rows, GenericNNetWrapper.predict (GenericNNetWrapper.py:141-168) +
 // SplendorNNet.forward (SplendorNNet.py:127-159): int8 states + legal masks in, exp(log_softmax(masked pi)) and tanh(v)
-// out. The torch path (nnet.py) needs ~60 small kernels per wave; here one CTA carries 16 leaves through every layer
-// (two warp groups of 16 leaves each per CTA, sharing the weight stream) with the activations resident in shared memory:
+// out. The torch path (nnet.py) needs ~60 small kernels per wave; here one CTA carries 32 leaves (two groups of 16) through
+// every layer with the activations resident in shared memory:
 //
-//   stage A (the "2d" layers, one row per (leaf, gem column): 112 rows per CTA, warp c owns gem column c)
+//   stage A (the "2d" layers, one row per (leaf, gem column): 112 rows per group, padded to the 128-row UMMA tile)
 //       x[56|71|88] -> Linear+BN(7)+ReLU -> Linear+ReLU -> DenseAndPartialGPool(4x8) -> Linear+ReLU
+//       on the 5th-generation tensor cores: tcgen05.mma (M = 128, N = 128, bf16 x bf16 -> fp32) issued by one thread, both
+//       operands from shared memory in the canonical K-major core-matrix layout (spl_umma.cuh), accumulators in TMEM (one
+//       128-column block per group), completion through tcgen05.commit -> mbarrier, epilogues (bias / BatchNorm / ReLU /
+//       pooling) by all 16 warps straight from TMEM (tcgen05.ld, one accumulator row per thread) back into the next layer's
+//       operand tile. Whole-layer weight blocks stream from L2 into two 36 KB slots by cp.async, two layers ahead.
 //   FlattenAndPartialGPool(64, 5)  -> 704 features per leaf
-//   stage B (the "1d" layers, 16 rows per CTA, the 8 warps split the output columns)
+//   stage B (the "1d" layers, 16 rows per group, the 8 warps of a group split the output columns)
 //       704 -> 128 -> pool-dense -> 128 -> 128 -> pool-dense -> {PI: 128 -> 406 masked softmax, V: 128 -> n tanh}
+//       as warp-level mma.sync m16n8k16 (fragments by ldmatrix, interleaved accumulation chains): 16-row tiles would waste
+//       7/8 of a UMMA tile; weights in [n][k] blocks through a four-slot cp.async ring (the same shared memory).
 //
-// Matrix products run on the tensor cores as bf16 x bf16 -> fp32 (mma.sync m16n8k16, fragments by ldmatrix), weights are streamed from L2
-// through a four-slot cp.async ring in [n][k] blocks laid out exactly as they sit in shared memory (padded rows,
-// conflict-free fragment loads), biases / BatchNorm terms are applied in fp32 in the epilogues. BatchNorm is folded on
-// the host in double precision (eval mode); the score-difference head is not evaluated (MCTS never reads it).
+// Biases / BatchNorm terms are applied in fp32 in the epilogues. BatchNorm is folded on the host in double precision (eval
+// mode); the score-difference head is not evaluated (MCTS never reads it).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -22,6 +27,7 @@
 #include <string.h>
 
 #include "spl_internal.h"
+#include "spl_umma.cuh"
 
 namespace {
 
@@ -44,7 +50,8 @@ enum {
 };
 
 struct NnPlan {   // byte offsets of the weight blocks inside the blob (after the fp32 parameters)
-    int nblocks;
+    int a_off[4], a_bytes[4];   // stage A: whole layers [128 n][K] in the canonical UMMA layout (L1, L2, G1, L3)
+    int nblocks;                // stage B: [n][k] blocks with padded rows
     int off[NN_MAXBLK];
     int bytes[NN_MAXBLK];
     int kb[NN_MAXBLK];   // k extent of the block (row stride = kb + 8 elements)
@@ -60,10 +67,8 @@ NnPlan make_plan(int n) {
     auto add = [&](int nb, int kb) {
         p.off[b] = o; p.kb[b] = kb; p.bytes[b] = nb * (kb + 8) * 2; o += p.bytes[b]; b++;
     };
-    add(64, kpad1(n)); add(64, kpad1(n));       // L1   dense2d_1.0
-    add(64, 128); add(64, 128);                 // L2   dense2d_1.3
-    add(64, 96); add(64, 96);                   // G1   partialgpool_1.dense_part.0
-    add(64, 128); add(64, 128);                 // L3   dense2d_3.0
+    const int ka[4] = {kpad1(n), 128, 96, 128};   // L1 dense2d_1.0, L2 dense2d_1.3, G1 partialgpool_1.dense_part.0, L3 dense2d_3.0
+    for (int i = 0; i < 4; i++) { p.a_off[i] = o; p.a_bytes[i] = 128 * ka[i] * 2; o += p.a_bytes[i]; }
     for (int i = 0; i < 11; i++) add(128, 64);  // L4   dense1d_4.0 (704 = 11 x 64)
     add(64, 112); add(64, 112);                 // G4
     add(64, 128); add(64, 128);                 // L5a
@@ -82,17 +87,24 @@ constexpr int SLOT_BYTES = 128 * 72 * 2;   // largest block: [128 n][64 k]
 constexpr int NN_SLOTS = 4;                // weight ring: blocks are requested 3 steps ahead (a step is shorter than an L2 round trip)
 static_assert(SLOT_BYTES >= 64 * ASTR * 2, "slot holds a [64][128] block");
 
+constexpr int ATILE_BYTES = 128 * 128 * 2;   // stage A operand tile of a group: 128 rows x 128 k, canonical UMMA layout
 struct NnGroupSmem {
-    __nv_bfloat16 act[7 * NN_SB * ASTR];     // stage A activations; later the fp32 logits
+    // stage A: the UMMA operand tile (canonical layout); its last layer leaves the activations here as rows of ASTR elements
+    // (112 x 136 x 2 = 30,464 bytes) for the flatten step; later the fp32 logits
+    __align__(128) __nv_bfloat16 act[ATILE_BYTES / 2];
     __nv_bfloat16 flat[NN_SB * FSTR];
     __nv_bfloat16 vec[3][NN_SB * ASTR];
 };
 struct NnSmem {
-    float prm[P_TOTAL];                      // biases / BatchNorm terms: read in every epilogue, so not from L2
+    __align__(128) unsigned char slot[NN_SLOTS][SLOT_BYTES];   // stage B: four ring slots; stage A: two slots of 2 SLOT_BYTES (whole layers)
     NnGroupSmem grp[NN_GROUPS];
-    unsigned char slot[NN_SLOTS][SLOT_BYTES];
+    float prm[P_TOTAL];                      // biases / BatchNorm terms: read in every epilogue, so not from L2
+    uint64_t mma_bar;                        // tcgen05.commit arrives here
+    uint32_t tmem_base;
 };
-static_assert(sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR >= sizeof(float) * NN_SB * LSTR, "logits alias the activations");
+static_assert(ATILE_BYTES >= (int)sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR && ATILE_BYTES >= (int)sizeof(float) * NN_SB * LSTR, "aliases of the operand tile");
+static_assert(2 * SLOT_BYTES >= 128 * 128 * 2, "a whole 128 x 128 layer fits two ring slots");
+static_assert(sizeof(NnSmem) <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
                                                                      const uint32_t* __restrict__ alt_mask, int alt_mask_stride, int n_rows,
                                                                      float* __restrict__ pi, float* __restrict__ vout) {
     constexpr int R = 32 + 10 * NP + NP * NP, S = 7 * R, K1 = (R + 15) / 16 * 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     NnSmem& smem_all = *reinterpret_cast<NnSmem*>(smem_raw);
     const float* prm = smem_all.prm;
     for (int i = threadIdx.x; i < P_TOTAL; i += NN_THREADS) smem_all.prm[i] = reinterpret_cast<const float*>(blob)[i];
@@ -237,7 +249,19 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     const int live = max(0, min(NN_SB, n_rows - base));
     NN_STAMP(0);
 
-    // ---- weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
+    // ---- stage A weights: whole layers into the two big slots (layer l -> slot l & 1), one cp.async group per layer
+    auto issue_a = [&](int l) {
+        const unsigned char* src = blob + plan.a_off[l];
+        unsigned char* dst = smem_all.slot[2 * (l & 1)];
+        for (int i = tid * 16; i < plan.a_bytes[l]; i += NN_THREADS * 16) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue_a(0);
+    issue_a(1);
+    if (tid < 32) umma::tmem_alloc(&smem_all.tmem_base, 256);      // one 128-column accumulator block per group
+    if (tid == 32) umma::mbar_init(&smem_all.mma_bar, 1);
+
+    // ---- stage B weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
     auto issue = [&](int b) {
         const unsigned char* src = blob + plan.off[b];
         unsigned char* dst = smem_all.slot[b % NN_SLOTS];
@@ -259,107 +283,148 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     };
     auto slot_of = [&](int b) -> const __nv_bfloat16* { return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]); };
     auto release = [&]() { __syncthreads(); };
-    while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // the first weight blocks travel while the input rows are converted
 
-    // ---- input: act[c*16 + s][k] = state[s][k][c]  (int8 counts are exact in bf16), zero padding up to K1
-    for (int i = gtid; i < NN_SB * K1; i += 256) {
-        const int s = i / K1, k = i - s * K1;
-        const bool in = k < R && s < live;
-        const bool alt = in && row_src && row_src[base + s];   // the tree arena's staging row (written by its rules kernel)
-        const int8_t* src = (alt ? alt_states + (size_t)(base + s) * alt_stride : states + (size_t)(base + s) * S) + k * 7;
+    // ---- input: operand tile row c*16 + s, column k = state[s][k][c] (int8 counts are exact in bf16), zero padding up to K1.
+    // One thread per (leaf, 8 consecutive k): 56 consecutive state bytes in, seven 16-byte chunks out.
+    unsigned char* atile = reinterpret_cast<unsigned char*>(sm.act);
+    for (int i = gtid; i < NN_SB * (K1 / 8); i += 256) {
+        const int s = i / (K1 / 8), k8 = i - s * (K1 / 8);
+        const bool row_in = s < live;
+        const bool alt = row_in && row_src && row_src[base + s];   // the tree arena's staging row (written by its rules kernel)
+        const int8_t* src = (alt ? alt_states + (size_t)(base + s) * alt_stride : states + (size_t)(base + s) * S) + k8 * 56;
+        uint32_t packed[7][4];
 #pragma unroll
-        for (int c = 0; c < 7; c++) sm.act[(c * 16 + s) * ASTR + k] = __float2bfloat16(in ? (float)src[c] : 0.f);
+        for (int c = 0; c < 7; c++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) packed[c][q] = 0u;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const bool in = row_in && (k8 * 8 + kk) < R;
+#pragma unroll
+            for (int c = 0; c < 7; c++) {
+                const float f = in ? (float)src[kk * 7 + c] : 0.f;
+                const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(f));
+                packed[c][kk >> 1] |= hb << (16 * (kk & 1));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 7; c++)
+            *reinterpret_cast<uint4*>(atile + umma::chunk_off(c * 16 + s, k8, 16)) = make_uint4(packed[c][0], packed[c][1], packed[c][2], packed[c][3]);
     }
-    __syncthreads();
-
     NN_STAMP(1);
-    uint32_t afr[8][4];
-    __nv_bfloat16* arow = sm.act + warp * 16 * ASTR;   // this warp's strip (stage A, warps 0..6)
-    const bool strip = warp < 7;
-    int blk = 0;
 
-    // ---- L1: Linear(R,128) + BatchNorm1d(7) + ReLU
+    // ---- stage A on tcgen05: four layers, per layer  weights landed -> one thread issues the MMAs of both groups -> commit ->
+    // everyone waits on the mbarrier -> epilogue from TMEM into the operand tile of the next layer
     {
-        const float s1 = strip ? prm[P_S1 + warp] : 0.f, t1 = strip ? prm[P_T1 + warp] : 0.f;
-        if (strip) load_afrags<K1 / 16>(afr, arow, ASTR, lane);
-        __syncwarp();
-        for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk, 1);
-            if (strip)
-                strip_gemm<K1 / 16>(afr, w, K1 + 8, lane, [&](int nt, float (&c)[4]) {
-                    const int n = h * 64 + nt * 8 + 2 * t;
-                    const float b0 = prm[P_B1 + n], b1 = prm[P_B1 + n + 1];
-                    sts_bf16x2(arow + g * ASTR + n, fmaxf((c[0] + b0) * s1 + t1, 0.f), fmaxf((c[1] + b1) * s1 + t1, 0.f));
-                    sts_bf16x2(arow + (g + 8) * ASTR + n, fmaxf((c[2] + b0) * s1 + t1, 0.f), fmaxf((c[3] + b1) * s1 + t1, 0.f));
-                });
-            release(); blk++;
-        }
-    }
-    // ---- L2 and (after the pool layer) L3: Linear(128,128) + ReLU
-    auto dense_relu_strip = [&](int pbias) {
-        if (strip) load_afrags<8>(afr, arow, ASTR, lane);
-        __syncwarp();
-        for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk, 1);
-            if (strip)
-                strip_gemm<8>(afr, w, ASTR, lane, [&](int nt, float (&c)[4]) {
-                    const int n = h * 64 + nt * 8 + 2 * t;
-                    const float b0 = prm[pbias + n], b1 = prm[pbias + n + 1];
-                    sts_bf16x2(arow + g * ASTR + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
-                    sts_bf16x2(arow + (g + 8) * ASTR + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
-                });
-            release(); blk++;
-        }
-    };
-    NN_STAMP(2);
-    dense_relu_strip(P_B2);
-    NN_STAMP(3);
-    // ---- G1: DenseAndPartialGPool(128 -> 128; 4 groups of 8 max+avg, Linear(96,120)+BN(7)+ReLU)
-    {
-        const float sg = strip ? prm[P_SG1 + warp] : 0.f, tg = strip ? prm[P_TG1 + warp] : 0.f;
-        float pmx[2], pav[2];
-        if (strip) {
-            load_afrags<6>(afr, arow + 32, ASTR, lane);
-#pragma unroll
-            for (int q = 0; q < 2; q++) {   // 64 (row, group) pairs per strip, two per lane
-                const int pr = lane * 2 + q, row = pr >> 2, grp = pr & 3;
-                const uint4 raw = *reinterpret_cast<const uint4*>(arow + row * ASTR + grp * 8);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-                float mx = -INFINITY, sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 f = __bfloat1622float2(h2[j]);
-                    mx = fmaxf(mx, fmaxf(f.x, f.y)); sum += f.x + f.y;
+        const int row = 32 * (warp & 3) + lane;         // accumulator row = TMEM lane of this thread (its warp's lane quadrant)
+        const int half = warp >> 2;                     // which 64 of the 128 output columns this thread finishes
+        const int c = row >> 4;                         // gem column of the row (BatchNorm1d(7) channel); rows >= 112 are padding
+        const bool real = row < 7 * NN_SB;
+        const float s1 = real ? prm[P_S1 + c] : 0.f, t1 = real ? prm[P_T1 + c] : 0.f;
+        const float sg = real ? prm[P_SG1 + c] : 0.f, tg = real ? prm[P_TG1 + c] : 0.f;
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int l = 0; l < 4; l++) {
+            if (l == 3) cp_async_wait<0>(); else cp_async_wait<1>();      // this layer's weights (the next layer's may still be in flight)
+            umma::fence_smem_to_async();                                  // operand tile (st.shared) and weights -> visible to the tensor core
+            umma::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                const int ksteps = l == 0 ? K1 / 16 : (l == 2 ? 6 : 8);
+                const int kc_b = 2 * ksteps;                              // core matrices per row group of the weight tile
+                const uint32_t a_skip = l == 2 ? 4 * 128 : 0;             // G1 reads columns 32..127 of the tile
+                const uint32_t wbase = umma::smem_u32(smem_all.slot[2 * (l & 1)]);
+                const uint32_t idesc = umma::instr_desc_bf16(128, 128);
+                const uint32_t tb = smem_all.tmem_base;
+#pragma unroll 1
+                for (int gi = 0; gi < NN_GROUPS; gi++) {
+                    const uint32_t abase = umma::smem_u32(smem_all.grp[gi].act) + a_skip;
+                    for (int k = 0; k < ksteps; k++)
+                        umma::mma_bf16_ss(tb + gi * 128, umma::smem_desc(abase + k * 256, 128, 16 * 128), umma::smem_desc(wbase + k * 256, 128, kc_b * 128),
+                                          idesc, k > 0);
                 }
-                pmx[q] = mx; pav[q] = sum * 0.125f;
+                umma::commit(&smem_all.mma_bar);
             }
-        }
-        __syncwarp();
-        if (strip) {
+            umma::mbar_wait(&smem_all.mma_bar, phase);
+            phase ^= 1u;
+            umma::fence_after_sync();
+            if (l < 2) issue_a(l + 2);                                    // the slot this layer read is free again
+            if (l == 3) while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // stage B's first blocks travel during the epilogue
+            const uint32_t trow = umma::tmem_addr(smem_all.tmem_base, 32 * (warp & 3), group * 128 + half * 64);
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int pr = lane * 2 + q, row = pr >> 2, grp = pr & 3;
-                arow[row * ASTR + grp] = __float2bfloat16(pmx[q]);
-                arow[row * ASTR + 4 + grp] = __float2bfloat16(pav[q]);
-            }
-        }
-        for (int h = 0; h < 2; h++) {
-            const __nv_bfloat16* w = acquire(blk, 1);
-            if (strip)
-                strip_gemm<6>(afr, w, 96 + 8, lane, [&](int nt, float (&c)[4]) {
-                    const int n = h * 64 + nt * 8 + 2 * t;
-                    if (n < 120) {
-                        const float b0 = prm[P_BG1 + n], b1 = prm[P_BG1 + n + 1];
-                        sts_bf16x2(arow + g * ASTR + 8 + n, fmaxf((c[0] + b0) * sg + tg, 0.f), fmaxf((c[1] + b1) * sg + tg, 0.f));
-                        sts_bf16x2(arow + (g + 8) * ASTR + 8 + n, fmaxf((c[2] + b0) * sg + tg, 0.f), fmaxf((c[3] + b1) * sg + tg, 0.f));
+            for (int part = 0; part < 2; part++) {
+                float v[32];
+                __syncwarp();                                             // tcgen05.ld is warp-collective: padding rows rejoin here
+                umma::tmem_ld32(trow + part * 32, v);
+                const int n0 = half * 64 + part * 32;
+                if (real) {
+                uint32_t pk[16];
+                if (l == 0) {           // Linear(R,128) + BatchNorm1d(7) + ReLU
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf((v[j] + prm[P_B1 + n0 + j]) * s1 + t1, 0.f),
+                                                                        fmaxf((v[j + 1] + prm[P_B1 + n0 + j + 1]) * s1 + t1, 0.f));
+                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
                     }
-                });
-            release(); blk++;
+                } else if (l == 2) {    // DenseAndPartialGPool dense part: Linear(96,120) + BatchNorm1d(7) + ReLU -> columns 8..127
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const int n = n0 + j;
+                        const float b0 = n < 120 ? prm[P_BG1 + n] : 0.f, b1 = n < 120 ? prm[P_BG1 + n + 1] : 0.f;
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf((v[j] + b0) * sg + tg, 0.f), fmaxf((v[j + 1] + b1) * sg + tg, 0.f));
+                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                } else {                // Linear(128,128) + ReLU (L2, L3)
+                    const int pb = l == 1 ? P_B2 : P_B3;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[j] + prm[pb + n0 + j], 0.f), fmaxf(v[j + 1] + prm[pb + n0 + j + 1], 0.f));
+                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                }
+                if (l == 1 && n0 == 0) {
+                    // the pooled half of DenseAndPartialGPool: max and mean of the 4 groups of 8 leading columns (of the bf16
+                    // activations) replace columns 0..7, where the next layer leaves them next to its 120 dense outputs
+                    uint32_t pool[4];
+                    float mxs[4], avs[4];
+#pragma unroll
+                    for (int gq = 0; gq < 4; gq++) {
+                        float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[gq * 4 + q]));
+                            mx = fmaxf(mx, fmaxf(f.x, f.y)); sum += f.x + f.y;
+                        }
+                        mxs[gq] = mx; avs[gq] = sum * 0.125f;
+                    }
+                    const __nv_bfloat162 m01 = __floats2bfloat162_rn(mxs[0], mxs[1]), m23 = __floats2bfloat162_rn(mxs[2], mxs[3]);
+                    const __nv_bfloat162 a01 = __floats2bfloat162_rn(avs[0], avs[1]), a23 = __floats2bfloat162_rn(avs[2], avs[3]);
+                    pool[0] = *reinterpret_cast<const uint32_t*>(&m01); pool[1] = *reinterpret_cast<const uint32_t*>(&m23);
+                    pool[2] = *reinterpret_cast<const uint32_t*>(&a01); pool[3] = *reinterpret_cast<const uint32_t*>(&a23);
+                    pk[0] = pool[0]; pk[1] = pool[1]; pk[2] = pool[2]; pk[3] = pool[3];
+                }
+                if (l == 3) {           // last layer: rows of ASTR elements for the flatten step
+                    uint4* dst = reinterpret_cast<uint4*>(sm.act + row * ASTR + n0);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                } else {
+                    const int chunk0 = l == 2 ? 1 + n0 / 8 : n0 / 8;      // G1 writes its outputs to columns 8 + n
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (chunk0 + q < 16)
+                            *reinterpret_cast<uint4*>(atile + umma::chunk_off(row, chunk0 + q, 16)) =
+                                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+                }
+            }
+            NN_STAMP(2 + l);
         }
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid < 32) umma::tmem_dealloc(smem_all.tmem_base, 256);
     }
-    NN_STAMP(4);
-    dense_relu_strip(P_B3);
-    NN_STAMP(5);
+    int blk = 0;
 
     // ---- FlattenAndPartialGPool(64, 5): [max over the 5 gem colours | mean | gold, points rows | last 64 features of all 7]
     for (int i = gtid; i < NN_SB * 64; i += 256) {          // first 64 features of every row: pooled over the colour rows
@@ -575,6 +640,17 @@ void pack_block(unsigned char* dst, const float* W, int N, int K, int n0, int nb
         }
 }
 
+// W[N][K] (rows >= N and columns >= K zero) as a [128][kb] bf16 tile in the canonical UMMA K-major layout (spl_umma.cuh)
+void pack_canonical(unsigned char* dst, const float* W, int N, int K, int kb) {
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    const int kc = kb / 8;
+    for (int n = 0; n < 128; n++)
+        for (int k = 0; k < kb; k++) {
+            const size_t off = ((size_t)(n >> 3) * kc * 128 + (size_t)(k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) / 2;
+            d[off] = (n < N && k < K) ? to_bf16((double)W[(size_t)n * K + k]) : (uint16_t)0;
+        }
+}
+
 }   // namespace
 
 extern "C" {
@@ -617,10 +693,10 @@ int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_
         pack_block(B + p.off[b], W, N, K, 0, 64, 0, kb, scale); b++;
         pack_block(B + p.off[b], W, N, K, 64, 64, 0, kb, scale); b++;
     };
-    two(T[0], 128, R, K1, 1.0);
-    two(T[6], 128, 128, 128, 1.0);
-    two(T[8], 120, 96, 96, 1.0);
-    two(T[14], 128, 128, 128, 1.0);
+    pack_canonical(B + p.a_off[0], T[0], 128, R, K1);
+    pack_canonical(B + p.a_off[1], T[6], 128, 128, 128);
+    pack_canonical(B + p.a_off[2], T[8], 120, 96, 96);
+    pack_canonical(B + p.a_off[3], T[14], 128, 128, 128);
     for (int kbk = 0; kbk < 11; kbk++) { pack_block(B + p.off[b], T[16], 128, 704, 0, 128, kbk * 64, 64, 1.0); b++; }
     two(T[18], 120, 112, 112, bn4.s[0]);
     two(T[24], 128, 128, 128, bn5.s[0]);

@@ -264,6 +264,9 @@ int spl_nnet_pack(int n_players, const float* const* tensors, void* blob_host, s
  * packed weights (16-byte aligned) */
 int spl_nnet_forward(spl_ctx* ctx, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v,
                      void* stream);
+/* self-test of the tcgen05 / TMEM building blocks the evaluator is made of: out float[128][n] = A bf16[128][k] . B bf16[n][k]^T on
+ * one CTA (n a multiple of 32, k a multiple of 16, both <= 256; device pointers). *err_flag (device int) becomes 1 if the completion barrier timed out. */
+int spl_umma_selftest(spl_ctx* ctx, const void* a_bf16, const void* b_bf16, float* out, int n, int k, int* err_flag, void* stream);
 /* diagnostics: SM-clock time stamps of the phases of CTA 0 in the last spl_nnet_forward launch (long long[32]) */
 int spl_nnet_debug_stamps(long long* out32);
 

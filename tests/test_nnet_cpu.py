@@ -42,9 +42,13 @@ def test_blob_packer_folds_batchnorm_like_the_torch_path(n):
     assert np.allclose(prm[672:792], W["g4_b"].numpy(), rtol=1e-6, atol=1e-7)          # BatchNorm1d(1) folded into the bias
     assert np.allclose(prm[800:928], W["l5a_b"].numpy(), rtol=1e-6, atol=1e-7)
     assert np.allclose(prm[1312:1312 + 406], W["PI1_b"].numpy()) and np.allclose(prm[1888:1888 + n], W["V1_b"].numpy())
-    # first weight block: rows 0..63 of dense2d_1.0.weight as bf16, row stride K1 + 8, zero padded
+    # first weight block: dense2d_1.0.weight [128][R] as bf16 in the canonical UMMA K-major layout (csrc/spl_umma.cuh):
+    # element (row, k) at byte (row // 8) * (K1 // 8) * 128 + (k // 8) * 128 + (row % 8) * 16 + (k % 8) * 2, zero padded to K1
     R = 32 + 10 * n + n * n
     K1 = (R + 15) // 16 * 16
-    blk = blob[1896 * 4: 1896 * 4 + 64 * (K1 + 8) * 2].view(np.uint16).reshape(64, K1 + 8)
-    want = sd["dense2d_1.0.weight"][:64].to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
-    assert np.array_equal(blk[:, :R], want) and (blk[:, R:] == 0).all()
+    blk = blob[1896 * 4: 1896 * 4 + 128 * K1 * 2].view(np.uint16)
+    want = np.zeros((128, K1), dtype=np.uint16)
+    want[:, :R] = sd["dense2d_1.0.weight"].to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    rows, ks = np.meshgrid(np.arange(128), np.arange(K1), indexing="ij")
+    off = ((rows // 8) * (K1 // 8) * 128 + (ks // 8) * 128 + (rows % 8) * 16 + (ks % 8) * 2) // 2
+    assert np.array_equal(blk[off], want)
