@@ -29,7 +29,7 @@ EXPORTS = [
     "spl_scores", "spl_symmetries",
     "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
     "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_wave_nnet", "spl_mcts_debug_profile", "spl_mcts_policy", "spl_mcts_root_stats", "spl_mcts_fixed_net",
-    "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_umma_selftest",
+    "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_nnet_debug_cta_times", "spl_umma_selftest",
 ]
 MCTS_MOVE_FORCED, MCTS_MOVE_NOISE = 1, 2
 MCTS_INFO_WORDS = 16

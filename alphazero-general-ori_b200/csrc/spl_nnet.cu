@@ -99,7 +99,7 @@ struct NnSmem {
     __align__(128) unsigned char slot[NN_SLOTS][SLOT_BYTES];   // stage B: four ring slots; stage A: two slots of 2 SLOT_BYTES (whole layers)
     NnGroupSmem grp[NN_GROUPS];
     float prm[P_TOTAL];                      // biases / BatchNorm terms: read in every epilogue, so not from L2
-    uint64_t mma_bar;                        // tcgen05.commit arrives here
+    uint64_t mma_bar[NN_GROUPS];             // tcgen05.commit arrives here: one barrier per group's accumulator block
     uint32_t tmem_base;
 };
 static_assert(ATILE_BYTES >= (int)sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR && ATILE_BYTES >= (int)sizeof(float) * NN_SB * LSTR, "aliases of the operand tile");
@@ -229,6 +229,7 @@ __device__ __forceinline__ void tile2_gemm(float (&c0)[4], float (&c1)[4], float
     }
 }
 
+__device__ long long g_nn_cta[2 * 160];  // diagnostics: globaltimer at the start / end of the first 160 CTAs (slots 32.. of spl_nnet_debug_stamps)
 __device__ long long g_nn_stamps[32];   // diagnostics: phase time stamps of CTA 0 (SM clock), read by spl_nnet_debug_stamps
 #define NN_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_nn_stamps[i] = clock64(); } while (0)
 
@@ -248,6 +249,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     const int base = (blockIdx.x * NN_GROUPS + group) * NN_SB;
     const int live = max(0, min(NN_SB, n_rows - base));
     NN_STAMP(0);
+    if (threadIdx.x == 0 && blockIdx.x < 160) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_nn_cta[2 * blockIdx.x] = (long long)gt;
+    }
 
     // ---- stage A weights: whole layers into the two big slots (layer l -> slot l & 1), one cp.async group per layer
     auto issue_a = [&](int l) {
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     issue_a(0);
     issue_a(1);
     if (tid < 32) umma::tmem_alloc(&smem_all.tmem_base, 256);      // one 128-column accumulator block per group
-    if (tid == 32) umma::mbar_init(&smem_all.mma_bar, 1);
+    if (tid == 32) { umma::mbar_init(&smem_all.mma_bar[0], 1); umma::mbar_init(&smem_all.mma_bar[1], 1); }
 
     // ---- stage B weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
     auto issue = [&](int b) {
@@ -287,19 +293,17 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     // ---- input: operand tile row c*16 + s, column k = state[s][k][c] (int8 counts are exact in bf16), zero padding up to K1.
     // One thread per (leaf, 8 consecutive k): 56 consecutive state bytes in, seven 16-byte chunks out.
     unsigned char* atile = reinterpret_cast<unsigned char*>(sm.act);
-    for (int i = gtid; i < NN_SB * (K1 / 8); i += 256) {
-        const int s = i / (K1 / 8), k8 = i - s * (K1 / 8);
+    for (int i = gtid; i < NN_SB * (K1 / 4); i += 256) {   // one thread per (leaf, 4 consecutive k): 28 state bytes in, seven 8-byte half chunks out
+        const int s = i / (K1 / 4), k4 = i - s * (K1 / 4);
         const bool row_in = s < live;
         const bool alt = row_in && row_src && row_src[base + s];   // the tree arena's staging row (written by its rules kernel)
-        const int8_t* src = (alt ? alt_states + (size_t)(base + s) * alt_stride : states + (size_t)(base + s) * S) + k8 * 56;
-        uint32_t packed[7][4];
+        const int8_t* src = (alt ? alt_states + (size_t)(base + s) * alt_stride : states + (size_t)(base + s) * S) + k4 * 28;
+        uint32_t packed[7][2];
 #pragma unroll
-        for (int c = 0; c < 7; c++)
+        for (int c = 0; c < 7; c++) packed[c][0] = packed[c][1] = 0u;
 #pragma unroll
-            for (int q = 0; q < 4; q++) packed[c][q] = 0u;
-#pragma unroll
-        for (int kk = 0; kk < 8; kk++) {
-            const bool in = row_in && (k8 * 8 + kk) < R;
+        for (int kk = 0; kk < 4; kk++) {
+            const bool in = row_in && (k4 * 4 + kk) < R;
 #pragma unroll
             for (int c = 0; c < 7; c++) {
                 const float f = in ? (float)src[kk * 7 + c] : 0.f;
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         }
 #pragma unroll
         for (int c = 0; c < 7; c++)
-            *reinterpret_cast<uint4*>(atile + umma::chunk_off(c * 16 + s, k8, 16)) = make_uint4(packed[c][0], packed[c][1], packed[c][2], packed[c][3]);
+            *reinterpret_cast<uint2*>(atile + umma::chunk_off(c * 16 + s, k4 >> 1, 16) + 8 * (k4 & 1)) = make_uint2(packed[c][0], packed[c][1]);
     }
     NN_STAMP(1);
 
@@ -325,32 +329,32 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         uint32_t phase = 0;
 #pragma unroll 1
         for (int l = 0; l < 4; l++) {
+            if (l == 1) NN_STAMP(16);
             if (l == 3) cp_async_wait<0>(); else cp_async_wait<1>();      // this layer's weights (the next layer's may still be in flight)
             umma::fence_smem_to_async();                                  // operand tile (st.shared) and weights -> visible to the tensor core
             umma::fence_before_sync();
             __syncthreads();
+            if (l == 1) NN_STAMP(17);
             if (tid == 0) {
                 umma::fence_after_sync();
                 const int ksteps = l == 0 ? K1 / 16 : (l == 2 ? 6 : 8);
-                const int kc_b = 2 * ksteps;                              // core matrices per row group of the weight tile
                 const uint32_t a_skip = l == 2 ? 4 * 128 : 0;             // G1 reads columns 32..127 of the tile
-                const uint32_t wbase = umma::smem_u32(smem_all.slot[2 * (l & 1)]);
-                const uint32_t idesc = umma::instr_desc_bf16(128, 128);
+                // descriptors of k-step 0; step k starts 256 bytes further = +16 in the (address >> 4) field
+                const uint64_t bd0 = umma::smem_desc(umma::smem_u32(smem_all.slot[2 * (l & 1)]), 128, 2 * ksteps * 128);
                 const uint32_t tb = smem_all.tmem_base;
-#pragma unroll 1
+#pragma unroll
                 for (int gi = 0; gi < NN_GROUPS; gi++) {
-                    const uint32_t abase = umma::smem_u32(smem_all.grp[gi].act) + a_skip;
-                    for (int k = 0; k < ksteps; k++)
-                        umma::mma_bf16_ss(tb + gi * 128, umma::smem_desc(abase + k * 256, 128, 16 * 128), umma::smem_desc(wbase + k * 256, 128, kc_b * 128),
-                                          idesc, k > 0);
+                    const uint64_t ad0 = umma::smem_desc(umma::smem_u32(smem_all.grp[gi].act) + a_skip, 128, 16 * 128);
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (k < ksteps) umma::mma_bf16_ss(tb + gi * 128, ad0 + (uint64_t)(16 * k), bd0 + (uint64_t)(16 * k), umma::instr_desc_bf16(128, 128), k > 0);
+                    umma::commit(&smem_all.mma_bar[gi]);                  // group 0's epilogue runs under group 1's MMAs
                 }
-                umma::commit(&smem_all.mma_bar);
             }
-            umma::mbar_wait(&smem_all.mma_bar, phase);
-            phase ^= 1u;
+            if (l == 1) NN_STAMP(18);
+            umma::mbar_wait(&smem_all.mma_bar[group], phase);
             umma::fence_after_sync();
-            if (l < 2) issue_a(l + 2);                                    // the slot this layer read is free again
-            if (l == 3) while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // stage B's first blocks travel during the epilogue
+            if (l == 1) NN_STAMP(19);
             const uint32_t trow = umma::tmem_addr(smem_all.tmem_base, 32 * (warp & 3), group * 128 + half * 64);
 #pragma unroll
             for (int part = 0; part < 2; part++) {
@@ -360,28 +364,17 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
                 const int n0 = half * 64 + part * 32;
                 if (real) {
                 uint32_t pk[16];
-                if (l == 0) {           // Linear(R,128) + BatchNorm1d(7) + ReLU
+                // bias (+ BatchNorm1d(7) of the row's gem column) + ReLU; biases four at a time (the G1 bias block is followed by
+                // its BatchNorm terms, which the dropped columns 120..127 read harmlessly)
+                const int pb = l == 0 ? P_B1 : (l == 1 ? P_B2 : (l == 2 ? P_BG1 : P_B3));
+                const float sc = l == 0 ? s1 : (l == 2 ? sg : 1.f), sh = l == 0 ? t1 : (l == 2 ? tg : 0.f);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf((v[j] + prm[P_B1 + n0 + j]) * s1 + t1, 0.f),
-                                                                        fmaxf((v[j + 1] + prm[P_B1 + n0 + j + 1]) * s1 + t1, 0.f));
-                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                } else if (l == 2) {    // DenseAndPartialGPool dense part: Linear(96,120) + BatchNorm1d(7) + ReLU -> columns 8..127
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int n = n0 + j;
-                        const float b0 = n < 120 ? prm[P_BG1 + n] : 0.f, b1 = n < 120 ? prm[P_BG1 + n + 1] : 0.f;
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf((v[j] + b0) * sg + tg, 0.f), fmaxf((v[j + 1] + b1) * sg + tg, 0.f));
-                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                } else {                // Linear(128,128) + ReLU (L2, L3)
-                    const int pb = l == 1 ? P_B2 : P_B3;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[j] + prm[pb + n0 + j], 0.f), fmaxf(v[j + 1] + prm[pb + n0 + j + 1], 0.f));
-                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(prm + pb + n0 + j);
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(fmaxf((v[j] + b4.x) * sc + sh, 0.f), fmaxf((v[j + 1] + b4.y) * sc + sh, 0.f));
+                    const __nv_bfloat162 h23 = __floats2bfloat162_rn(fmaxf((v[j + 2] + b4.z) * sc + sh, 0.f), fmaxf((v[j + 3] + b4.w) * sc + sh, 0.f));
+                    pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h01);
+                    pk[(j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h23);
                 }
                 if (l == 1 && n0 == 0) {
                     // the pooled half of DenseAndPartialGPool: max and mean of the 4 groups of 8 leading columns (of the bf16
@@ -418,6 +411,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
                 }
                 }
             }
+            if (l == 1) NN_STAMP(20);
+            if (group == 0) umma::mbar_wait(&smem_all.mma_bar[1], phase);   // every MMA of the layer is done: its weight slot is free again
+            phase ^= 1u;
+            if (l < 2) issue_a(l + 2);
+            if (l == 3) while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // stage B's first blocks
             NN_STAMP(2 + l);
         }
         umma::fence_before_sync();
@@ -610,6 +608,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         }
     }
     NN_STAMP(11);
+    if (threadIdx.x == 0 && blockIdx.x < 160) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_nn_cta[2 * blockIdx.x + 1] = (long long)gt;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host: BatchNorm folding + blob packing
@@ -713,6 +716,12 @@ int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_
 int spl_nnet_debug_stamps(long long* out32) {   /* diagnostics only: SM-clock stamps of the last launch's CTA 0 */
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpyFromSymbol(out32, g_nn_stamps, sizeof(long long) * 32));
+    return SPL_OK;
+}
+
+int spl_nnet_debug_cta_times(long long* out320) {   /* diagnostics only: globaltimer (ns) at the start / end of the first 160 CTAs */
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out320, g_nn_cta, sizeof(long long) * 320));
     return SPL_OK;
 }
 

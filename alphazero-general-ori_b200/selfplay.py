@@ -46,6 +46,9 @@ class SelfPlayEngine:
         self.graph_waves = int(graph_waves)
         self.clean_every, self.clean_percent, self._ticks = int(clean_every), int(clean_percent), 0
         self._graph = None
+        self.tick_graph = True                 # asynchronous mode: replay the per-tick move logic as a CUDA graph too
+        self._tick_graph, self._tick_state, self._tick_temp = None, 0, None
+        self._fin8 = torch.zeros(n_games, dtype=torch.uint8, device=self.device)
         self.env.reset()
         self.examples = ExampleBuffer(n_players, n_games, self.env.R, self.device) if record_examples else None
         self.moves = 0
@@ -176,7 +179,10 @@ class SelfPlayEngine:
         new_flags = torch.where(is_full, fl, 0).to(torch.uint8)
         self.sims.copy_(torch.where(lanes, new_sims, self.sims))
         self.flags.copy_(torch.where(lanes, new_flags, self.flags))
-        self._is_full = torch.where(lanes, is_full, getattr(self, "_is_full", is_full))
+        if not hasattr(self, "_is_full"):
+            self._is_full = is_full.clone()
+        else:
+            self._is_full.copy_(torch.where(lanes, is_full, self._is_full))
 
     def tick(self, waves=None, temp=1.0):
         """`waves` selection waves (default: one graph replay) for every tree, then the lanes whose search is complete move on"""
@@ -188,6 +194,25 @@ class SelfPlayEngine:
         self._ticks += 1
         if self.clean_every > 0 and self._ticks % self.clean_every == 0:
             self.arena.clean(self.clean_percent)      # every tree that needs it, in one launch, off the path of begin
+        # the moves themselves: ~50 small launches (statistics, policy, sampling, env step, resets, begin). With captured waves
+        # they are captured too (once, after one eager pass) and replayed as one graph: the launch gaps between them were ~10 %
+        # of the run at 64 waves per tick. Example recording keeps the eager path (its buffers grow).
+        if self.graph_waves > 0 and self.examples is None and self.tick_graph:
+            if self._tick_state == 0 or self._tick_temp != temp:
+                self._tick_tail(temp)
+                self._tick_state, self._tick_temp, self._tick_graph = 1, temp, None
+            else:
+                if self._tick_graph is None:
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self._tick_graph = torch.cuda.CUDAGraph()
+                    self._tick_graph.register_generator_state(self.gen)
+                    with torch.cuda.graph(self._tick_graph):
+                        self._tick_tail(temp)
+                self._tick_graph.replay()
+        else:
+            self._tick_tail(temp)
+
+    def _tick_tail(self, temp):
         st = self.arena.root_stats(want_arrays=False)
         fin = (st["sims_done"] >= self.sims) | (st["status"] != 0)
         probs, q = self.arena.policy(temp)
@@ -213,7 +238,8 @@ class SelfPlayEngine:
         self.moves_completed += fin.sum()
         self._assign_budgets(fin)
         self.env.states(out=self.roots)
-        self.arena.begin(self.roots, self.sims, self.flags, fin.to(torch.uint8))
+        self._fin8.copy_(fin)
+        self.arena.begin(self.roots, self.sims, self.flags, self._fin8)
 
     def sims_in_flight(self):
         return self.arena.root_stats(want_arrays=False)["sims_done"].sum()

@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
     ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
-    ap.add_argument("--graph-waves", type=int, default=64, help="waves per CUDA-graph replay (0: plain launches)")
+    ap.add_argument("--graph-waves", type=int, default=128, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--gc", default="reachable", choices=["ply", "reachable"],
                     help="tree cleaning: ply = exact (keeps every node that could still be looked up), reachable = only what the root reaches")
     ap.add_argument("--clean-moves", type=float, default=4.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")

@@ -269,6 +269,8 @@ int spl_nnet_forward(spl_ctx* ctx, const void* blob, const int8_t* states, const
 int spl_umma_selftest(spl_ctx* ctx, const void* a_bf16, const void* b_bf16, float* out, int n, int k, int* err_flag, void* stream);
 /* diagnostics: SM-clock time stamps of the phases of CTA 0 in the last spl_nnet_forward launch (long long[32]) */
 int spl_nnet_debug_stamps(long long* out32);
+/* diagnostics: globaltimer (ns) at the start and the end of the first 160 CTAs of the last spl_nnet_forward launch (long long[320]) */
+int spl_nnet_debug_cta_times(long long* out320);
 
 #ifdef __cplusplus
 }
