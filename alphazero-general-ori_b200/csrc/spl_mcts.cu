@@ -366,7 +366,10 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
         const int v = atoi(e);
         if (v == 4 || v == 8 || v == 16) m->rules_tpw = v;
     }
-    m->fuse_rules = 1;
+    // rules step inside the descent kernel: one launch boundary less on the critical path of a wave, but the step then runs on one
+    // lane per warp - right while every tree's warp is resident at once (latency-bound, measured 102 -> 98 us per wave at 4096
+    // trees), wrong in the throughput regime (65,536 trees: 32x the issue slots of mcts_rules_kernel)
+    m->fuse_rules = n_trees <= 6144;
     if (const char* e = getenv("SPL_MCTS_FUSE_RULES")) m->fuse_rules = atoi(e) != 0;   // tuning hook
     m->side = nullptr; m->ev_fork = nullptr; m->ev_join = nullptr;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
