@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
     ap.add_argument("--max-levels", type=int, default=16, help="edges a descend call walks before it yields to the next wave (0: no limit)")
     ap.add_argument("--overlap", type=int, default=1, help="1: the fused network runs next to the attach kernel (spl_mcts_wave_nnet); 0: one stream")
+    ap.add_argument("--e2e-max-levels", type=int, default=0, help="max_levels of the lock-step e2e leg (0: a descent never yields)")
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
@@ -410,7 +411,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     import numpy as np
     boards = eng.env.states().cpu().numpy()
     ar.reset()
-    ar.set_params(max_levels=0)     # lock-step calls wait for the slowest tree: no yielding inside a descent
+    ar.set_params(max_levels=args.e2e_max_levels)     # lock-step calls wait for the slowest tree (0: no yielding inside a descent)
     ke = 3
     h2d = d2h = 0
     barrier()
@@ -629,7 +630,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the first communicator comes up; stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:

@@ -50,6 +50,9 @@ SCENARIOS = {
     "e_n2_cap":     dict(n=2, sims=400, cpuct=1.0, fpu=0.2, forced=True, noise=True, prob_full=0.0, ratio=4, force=False, moves=4, start="init"),
     "f_n2_late":    dict(n=2, sims=300, cpuct=1.5, fpu=0.0, forced=False, noise=False, prob_full=1.0, ratio=5, force=True, moves=5, start="late"),
     "g_n3_late":    dict(n=3, sims=200, cpuct=1.0, fpu=0.25, forced=True, noise=False, prob_full=1.0, ratio=5, force=True, moves=4, start="late"),
+    # root softmax with args.temperature[0] != 1 before the noise (MCTS.py:141-143,150-153,244-250; main.py's default 1.25)
+    "h_n2_temp":    dict(n=2, sims=400, cpuct=1.0, fpu=0.0, forced=True, noise=True, prob_full=1.0, ratio=5, force=True, moves=5, start="init", temp0=1.25),
+    "i_n3_temp":    dict(n=3, sims=200, cpuct=1.25, fpu=0.1, forced=False, noise=True, prob_full=1.0, ratio=5, force=True, moves=4, start="late", temp0=0.8),
 }
 
 
@@ -68,7 +71,7 @@ def run(name, sc):
     n = sc["n"]
     game = SplendorGame(n)
     args = dotdict(numMCTSSims=sc["sims"], prob_fullMCTS=sc["prob_full"], ratio_fullMCTS=sc["ratio"], forced_playouts=sc["forced"],
-                   cpuct=sc["cpuct"], fpu=sc["fpu"], no_mem_optim=True, temperature=[1.0, 1.0], dirichletAlpha=0.3)
+                   cpuct=sc["cpuct"], fpu=sc["fpu"], no_mem_optim=True, temperature=[sc.get("temp0", 1.0), 1.0], dirichletAlpha=0.3)
     nnet = fakenn.FakeNNet(n)
     mcts = MCTS(game, nnet, args, dirichlet_noise=sc["noise"])
     mcts.rng = FakeRng(0.5, seed=hash(name) & 0xFFFF if False else sum(map(ord, name)))
@@ -77,7 +80,7 @@ def run(name, sc):
         board = gg["init_state"][1].copy()          # a reference-dealt start position (player 0 to move: canonical)
     else:
         board = late_state(game, n)
-    rec = {k: [] for k in ["root", "full", "dir", "dir_len", "probs", "q", "nsa", "qsa", "ns", "qs", "nodes", "action", "nn_calls"]}
+    rec = {k: [] for k in ["root", "full", "dir", "dir_len", "probs", "q", "nsa", "qsa", "ns", "qs", "nodes", "action", "nn_calls", "ps"]}
     for mv in range(sc["moves"]):
         if game.getGameEnded(board, 0).any():
             break
@@ -93,14 +96,19 @@ def run(name, sc):
         rec["nsa"].append(np.array(Nsa, dtype=np.int64)); rec["qsa"].append(np.array(Qsa, dtype=np.float64))
         rec["ns"].append(int(Ns)); rec["qs"].append(np.float32(Qs)); rec["nodes"].append(len(mcts.nodes_data))
         rec["nn_calls"].append(nnet.calls)
+        rec["ps"].append(np.array(Ps, dtype=np.float32))        # the root's stored priors (after softmax + noise): compared bit for bit
         a = int(np.argmax(np.array(Nsa)))
         rec["action"].append(a)
         # advance the real game without a reveal (deterministic=True keeps the fixture free of the reference's RNG)
         nb, nxt = game.getNextState(board, 0, a, deterministic=True)
         board = game.getCanonicalForm(nb.copy(), nxt).copy()
     out = {k: np.array(v) for k, v in rec.items()}
+    if "temp0" not in sc:
+        del out["ps"]                                           # the older fixtures stay byte-identical
     out["cfg"] = np.array([sc["n"], sc["sims"], int(sc["forced"]), int(sc["noise"]), sc["ratio"], int(sc["force"])], dtype=np.int64)
     out["cfgf"] = np.array([sc["cpuct"], sc["fpu"], sc["prob_full"]], dtype=np.float64)
+    if "temp0" in sc:
+        out["temp0"] = np.float64(sc["temp0"])
     np.savez_compressed(os.path.join(GOLD, f"mcts_{name}.npz"), **out)
     print(name, "moves", len(rec["ns"]), "Ns", rec["ns"], "nodes", rec["nodes"], "nn", rec["nn_calls"])
 
@@ -109,8 +117,10 @@ def main():
     build_patched_ref.import_ref()
     import warnings
     warnings.filterwarnings("ignore")
+    only = set(sys.argv[1:])          # optional: names of the scenarios to (re)generate; default all
     for name, sc in SCENARIOS.items():
-        run(name, sc)
+        if not only or name in only:
+            run(name, sc)
 
 
 if __name__ == "__main__":

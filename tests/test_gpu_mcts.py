@@ -35,7 +35,8 @@ def test_arena_reproduces_reference_mcts(golden_dir, name):
     n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
     cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
     T = 3   # the same search in three trees at once: they must not disturb each other
-    ar = az.MCTSArena(n, T, node_cap=4096, cpuct=cpuct, fpu=fpu)
+    temp0 = float(g["temp0"]) if "temp0" in g else 1.0          # args.temperature[0]: root softmax before the noise
+    ar = az.MCTSArena(n, T, node_cap=4096, cpuct=cpuct, fpu=fpu, temperature0=temp0)
     dev = ar.device
     for i in range(len(g["ns"])):
         full = bool(g["full"][i])
@@ -56,6 +57,8 @@ def test_arena_reproduces_reference_mcts(golden_dir, name):
             assert _np(st["qs"])[t] == g["qs"][i]
             assert np.allclose(_np(probs[t]), g["probs"][i], rtol=0, atol=1e-12)
             assert np.allclose(_np(q[t]), g["q"][i], rtol=0, atol=1e-12)
+            if "ps" in g:      # root priors after the temperature softmax + noise: 2 float32 ulps (the reference's fastmath sums)
+                assert np.abs(_np(st["ps"][t]) - g["ps"][i]).max() <= 2.4e-7
 
 
 @pytest.mark.parametrize("n", [2, 3, 4])
@@ -150,7 +153,7 @@ class _DotDict(dict):
         return self[name]
 
 
-@pytest.mark.parametrize("name", ["b_n2_forced_noise", "e_n2_cap", "g_n3_late"])
+@pytest.mark.parametrize("name", ["b_n2_forced_noise", "e_n2_cap", "g_n3_late", "h_n2_temp"])
 def test_mcts_class_is_a_drop_in(golden_dir, name):
     """the reference-surface class driven exactly as oracle/refgen/gen_mcts_golden.py drove the reference's MCTS:
     same args object, a host `predict` network, an injected rng - same returned probs / q / flags"""
@@ -161,7 +164,7 @@ def test_mcts_class_is_a_drop_in(golden_dir, name):
     cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
     game = az.SplendorGame(n)
     args = _DotDict(numMCTSSims=sims, prob_fullMCTS=prob_full, ratio_fullMCTS=ratio, forced_playouts=bool(forced), cpuct=cpuct, fpu=fpu,
-                    no_mem_optim=True, temperature=[1.0, 1.0], dirichletAlpha=0.3)
+                    no_mem_optim=True, temperature=[float(g["temp0"]) if "temp0" in g else 1.0, 1.0], dirichletAlpha=0.3)
     nnet = fakenn.FakeNNet(n)
     mcts = az.MCTS(game, nnet, args, dirichlet_noise=bool(noise))
     mcts.rng = _FakeRng(0.5, seed=sum(map(ord, name)))

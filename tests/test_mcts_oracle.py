@@ -34,7 +34,9 @@ def test_oracle_reproduces_reference_mcts(golden_dir, name):
     g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
     n, sims, forced, noise, ratio, force = [int(x) for x in g["cfg"]]
     cpuct, fpu, prob_full = [float(x) for x in g["cfgf"]]
-    m = po.MCTSOracle(n, sims, cpuct=cpuct, fpu=fpu, forced_playouts=bool(forced), dirichlet_noise=bool(noise), ratio_full=ratio)
+    temp0 = float(g["temp0"]) if "temp0" in g else 1.0          # args.temperature[0]: root softmax before the noise
+    m = po.MCTSOracle(n, sims, cpuct=cpuct, fpu=fpu, forced_playouts=bool(forced), dirichlet_noise=bool(noise), ratio_full=ratio,
+                      temperature0=temp0)
     for i in range(len(g["ns"])):
         d = g["dir"][i] if g["dir_len"][i] > 0 else (np.zeros(406) if noise else None)
         out = m.get_action_prob(g["root"][i], temp=1.0, full_search=bool(g["full"][i]), dir_values=d)
