@@ -11,6 +11,7 @@ from .mcts import MCTS, MCTSArena
 from .nnet import FusedSplendorNNet, SplendorNNetB200
 from .selfplay import SelfPlayEngine
 from .arena import BatchedArena
-from . import examples, nnet
+from . import examples, nnet, trainbatch
+from .trainbatch import TrainBatcher
 
-__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "BatchedArena", "nnet", "examples", "observation_size", "action_size", "rows", "_native"]
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "BatchedArena", "TrainBatcher", "nnet", "examples", "trainbatch", "observation_size", "action_size", "rows", "_native"]

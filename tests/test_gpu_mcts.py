@@ -412,3 +412,27 @@ def test_overlapped_wave_equals_classic_wave(n, T):
         assert int(sa["sims_done"].min()) >= sims // 4
         probs, _ = a.policy(1.0)
         env.step(probs.argmax(1).to(torch.int16), player=0, chance="philox", rotate=True)
+
+
+def test_train_batches_from_selfplay_examples_stay_on_the_device():
+    """N4: the examples batched self-play produced feed the training mini-batch assembly without leaving the GPU"""
+    az = _azg()
+    n, T = 2, 96
+    eng = az.SelfPlayEngine(n, T, None, 12, seed=21, node_cap=256, record_examples=True)
+    eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v)
+    eng.env.rollout(70, rotate=True)
+    eng.examples.cur_player.zero_()
+    for _ in range(40):
+        eng.play_move()
+    ex = eng.drain_examples(symmetries=True)
+    E = int(ex["board"].shape[0])
+    assert E >= 64
+    b = az.TrainBatcher(ex, 64, seed=5)
+    out = b.batch()
+    for k in ("boards", "valid_actions", "target_pis", "target_vs", "target_scdiffs"):
+        assert out[k].is_cuda and out[k].shape[0] == 64
+    assert out["boards"].dtype == torch.float32 and out["valid_actions"].dtype == torch.bool and tuple(out["target_scdiffs"].shape) == (64, 31, n)
+    ids = out["ids"]
+    assert torch.equal(out["boards"], ex["board"][ids].float()) and float(out["target_scdiffs"].sum()) == 64 * n
+    sd = (ex["scdiff"][ids].long() + 15).clamp(0, 30)
+    assert bool((out["target_scdiffs"].argmax(1) == sd).all())
