@@ -16,10 +16,11 @@ int spl_fail_(int code, const char* what, cudaError_t e = cudaSuccess);   // rec
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return spl_fail_(SPL_E_CUDA, #call, e_); } while (0)
 
 // spl_nnet.cu: the fused evaluator on rows that live in one of two places (row_src[r] = 0: states / valids bytes, 1: alt_states
-// with alt_stride bytes per row + 13 mask words at alt_mask[w * alt_mask_stride + r]); row_src == NULL: all rows from states / valids
+// with alt_stride bytes per row + 13 mask words at alt_mask[w * alt_mask_stride + r]); row_src == NULL: all rows from states / valids.
+// programmatic_dependent: launched as a programmatic dependent of the previous kernel in `st` (its set-up overlaps that kernel's tail)
 int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, const uint8_t* row_src,
                            const int8_t* alt_states, int alt_stride, const uint32_t* alt_mask, int alt_mask_stride, int n_rows, float* pi,
-                           float* v, cudaStream_t st);
+                           float* v, cudaStream_t st, bool programmatic_dependent = false);
 
 #define DISPATCH_N(n, ...)                                   \
     switch (n) {                                             \

@@ -24,6 +24,7 @@ struct spl_mcts {
     MctsSearchParams P;
     int edge_reserve, gc_reachable, rounds, max_levels;
     int rules_tpw;               // trees per warp of the rules kernel
+    int pdl;                     // spl_mcts_wave_nnet: descent and network as programmatic dependent launches on one stream
     int fuse_rules;              // spl_mcts_wave_nnet: rules step inside the descent kernel (no launch boundary) instead of mcts_rules_kernel
     cudaStream_t side;           // spl_mcts_wave_nnet: the network runs here, next to the attach kernel
     cudaEvent_t ev_fork, ev_join;
@@ -233,6 +234,10 @@ __global__ void __launch_bounds__(MW * 32, 7) mcts_expand_descend_kernel(MctsAre
                                                                          int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);
+    // programmatic dependent launch (spl_mcts_wave_nnet): this grid may become resident while the network of the previous wave is
+    // still running; nothing is read before that grid has completed and its pi / v rows are visible. A no-op otherwise.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // once every block of this grid is running, the next grid may move in behind it
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
     PROF_STAMP(A, t, 0, prof_globaltimer()); PROF_STAMP(A, t, 1, clock64());
@@ -371,6 +376,8 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     // trees), wrong in the throughput regime (65,536 trees: 32x the issue slots of mcts_rules_kernel)
     m->fuse_rules = n_trees <= 6144;
     if (const char* e = getenv("SPL_MCTS_FUSE_RULES")) m->fuse_rules = atoi(e) != 0;   // tuning hook
+    m->pdl = 1;
+    if (const char* e = getenv("SPL_MCTS_PDL")) m->pdl = atoi(e) != 0;   // tuning hook
     m->side = nullptr; m->ev_fork = nullptr; m->ev_join = nullptr;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -468,6 +475,29 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
     const SplRules rules = m->ctx->rules;
     DISPATCH_N(m->ctx->n, {
         m->P.rules = rules;
+        if (m->fuse_rules && m->pdl) {
+            // stream: [expand + descend + rules] -> [network] -> next wave, both launched as programmatic dependents of their
+            // predecessor (their blocks become resident - and the network does its set-up: parameters, TMEM, first weight tiles -
+            // while the predecessor drains; griddepcontrol.wait guards the first dependent read); the attach kernel runs on the
+            // side stream between this wave's descent and the next one's expansion
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(MW * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, mcts_expand_descend_kernel<N, true>, m->A, m->P, (const float*)pi, (const float*)v, dir_values, m->max_levels,
+                                  leaf_states, leaf_valids));
+            CU(cudaEventRecord(m->ev_fork, st));
+            CU(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+            mcts_attach_kernel<N><<<grid, MW * 32, 0, m->side>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
+            CU(cudaEventRecord(m->ev_join, m->side));
+            const int rc = spl_nnet_forward_rows_(m->ctx, nnet_blob, leaf_states, leaf_valids, m->A.leaf_src, m->A.stage_state, m->A.sp, m->A.stage_mask,
+                                                  m->A.n_trees, m->A.n_trees, pi, v, st, true);
+            if (rc != SPL_OK) return rc;
+            CU(cudaStreamWaitEvent(st, m->ev_join, 0));
+            CU(cudaGetLastError());
+            return SPL_OK;
+        }
         if (m->fuse_rules) {
             mcts_expand_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
         } else {
@@ -479,7 +509,7 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
         CU(cudaEventRecord(m->ev_fork, st));
         CU(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
         const int rc = spl_nnet_forward_rows_(m->ctx, nnet_blob, leaf_states, leaf_valids, m->A.leaf_src, m->A.stage_state, m->A.sp, m->A.stage_mask,
-                                              m->A.n_trees, m->A.n_trees, pi, v, m->side);
+                                              m->A.n_trees, m->A.n_trees, pi, v, m->side, false);
         if (rc != SPL_OK) return rc;
         CU(cudaEventRecord(m->ev_join, m->side));
         mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);

@@ -683,6 +683,61 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
     const int leaf = T->leaf;
     if (leaf < 0) return;
     MctsNode* nd = A.nodes + (size_t)t * A.cap + leaf;
+#ifdef __CUDACC__
+    {
+        // The common case in three rounds of loads instead of seven dependent ones: (1) the leaf's header, the value vector and
+        // the recorded path, (2) the leaf's edge actions and the statistics of the path's nodes and edges, (3) the network's
+        // probabilities; the float32 normalisation sums in action order through shuffles (same additions as `normalise :239`),
+        // the backup (:168-177) uses the statistics fetched in round 2. Same arithmetic as the general path below.
+        const int depth = T->path_len;
+        const bool noise = leaf == T->root && T->sims_done == 0 && (T->flags & MCTS_F_NOISE);
+        const MctsNode hdr = *nd;
+        const int k = hdr.n_edges;
+        if (!noise && k <= 32 && depth <= 32) {
+            MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+            MctsEdge* edges = A.edges + (size_t)t * A.ecap;
+            const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+            float v[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = vin[i];
+            uint32_t pn = 0u, pe = 0u;
+            if (w.lane < depth) { pn = path[2 * w.lane]; pe = path[2 * w.lane + 1]; }
+            MctsEdge* ed = edges + hdr.edge_off;
+            int act = 0;
+            if (w.lane < k) act = ed[w.lane].action;
+            int eN = 0, nNs = 0;
+            double eQ = 0.0;
+            float nQs = 0.f;
+            if (w.lane < depth) { eN = edges[pe].N; eQ = edges[pe].Q; nNs = nodes[pn].u.x.Ns; nQs = nodes[pn].u.x.Qs; }
+            float p = w.lane < k ? pi[act] : 0.f;
+            float s = 0.f;
+            for (int i = 0; i < k; i++) s = MC_FADD(s, __shfl_sync(0xffffffffu, p, i));
+            if (w.lane < k) ed[w.lane].P = MC_FDIV(p, s);
+            if (w.lane == 0) {
+                nd->u.x.Ns = 0;
+                nd->u.x.Qs = v[0];   // :147
+                nd->kind = MCTS_NODE_EXPANDED;
+            }
+            if (w.lane < depth) {
+                const float v0 = mcts_vsel<N>(v, ((w.lane - depth) % N + N) % N);
+                edges[pe].Q = MC_DDIV(MC_DADD(MC_DMUL((double)eN, eQ), (double)v0), (double)(eN + 1));                 // :171
+                nodes[pn].u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nNs + 1), nQs), v0), (float)(nNs + 2));             // :172
+                edges[pe].N = eN + 1;
+                nodes[pn].u.x.Ns = nNs + 1;
+            }
+            if (w.lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? mcts_vsel<N>(v, ((i - depth) % N + N) % N) : 0.f;
+                T->depth_sum += depth;
+                T->sims_done += 1;
+                T->leaf = -1; T->cur = -1; T->pend_edge = -1; T->path_len = 0;
+                T->nn_calls += 1;
+            }
+            w.sync();
+            return;
+        }
+    }
+#endif
     MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
     const int k = nd->n_edges;
     for (int i = w.lane; i < k; i += W::W) ed[i].P = pi[ed[i].action];

@@ -290,6 +290,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     auto slot_of = [&](int b) -> const __nv_bfloat16* { return reinterpret_cast<const __nv_bfloat16*>(smem_all.slot[b % NN_SLOTS]); };
     auto release = [&]() { __syncthreads(); };
 
+    // programmatic dependent launch: everything above (parameters, TMEM, barriers, the first weight tiles) may run while the
+    // kernel that produces the input rows is still draining; the rows themselves are read only after it has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next wave's descent may move in behind this grid
     // ---- input: operand tile row c*16 + s, column k = state[s][k][c] (int8 counts are exact in bf16), zero padding up to K1.
     // One thread per (leaf, 8 consecutive k): 56 consecutive state bytes in, seven 16-byte chunks out.
     unsigned char* atile = reinterpret_cast<unsigned char*>(sm.act);
@@ -726,14 +730,14 @@ int spl_nnet_debug_cta_times(long long* out320) {   /* diagnostics only: globalt
 }
 
 int spl_nnet_forward(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, int n_rows, float* pi, float* v, void* stream) {
-    return spl_nnet_forward_rows_(c, blob, states, valids, nullptr, nullptr, 0, nullptr, 0, n_rows, pi, v, (cudaStream_t)stream);
+    return spl_nnet_forward_rows_(c, blob, states, valids, nullptr, nullptr, 0, nullptr, 0, n_rows, pi, v, (cudaStream_t)stream, false);
 }
 
 }   // extern "C"
 
 int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, const uint8_t* row_src,
                            const int8_t* alt_states, int alt_stride, const uint32_t* alt_mask, int alt_mask_stride, int n_rows, float* pi,
-                           float* v, cudaStream_t st) {
+                           float* v, cudaStream_t st, bool programmatic_dependent) {
     if (!c) return spl_fail_(SPL_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
     if (!blob || !states || !valids || !pi || !v || n_rows <= 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: bad argument");
@@ -745,8 +749,13 @@ int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, c
     DISPATCH_N(c->n, {
         auto k = nnet_forward_kernel<N>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k<<<grid, NN_THREADS, smem, st>>>((const unsigned char*)blob, p, states, valids, row_src, alt_states, alt_stride, alt_mask, alt_mask_stride,
-                                          n_rows, pi, v);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = programmatic_dependent ? 1 : 0;
+        CU(cudaLaunchKernelEx(&cfg, k, (const unsigned char*)blob, p, states, valids, row_src, alt_states, alt_stride, alt_mask, alt_mask_stride, n_rows, pi, v));
     });
     CU(cudaGetLastError());
     return SPL_OK;

@@ -24,7 +24,7 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None):
+                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -46,7 +46,8 @@ class SelfPlayEngine:
         self.graph_waves = int(graph_waves)
         self.clean_every, self.clean_percent, self._ticks = int(clean_every), int(clean_percent), 0
         self._graph = None
-        self.tick_graph = True                 # asynchronous mode: replay the per-tick move logic as a CUDA graph too
+        # asynchronous mode: replay the per-tick move logic as a CUDA graph (default: whenever the waves are captured)
+        self.tick_graph = (self.graph_waves > 0) if tick_graph is None else bool(tick_graph)
         self._tick_graph, self._tick_state, self._tick_temp = None, 0, None
         self._fin8 = torch.zeros(n_games, dtype=torch.uint8, device=self.device)
         self.env.reset()
@@ -197,7 +198,7 @@ class SelfPlayEngine:
         # the moves themselves: ~50 small launches (statistics, policy, sampling, env step, resets, begin). With captured waves
         # they are captured too (once, after one eager pass) and replayed as one graph: the launch gaps between them were ~10 %
         # of the run at 64 waves per tick. Example recording keeps the eager path (its buffers grow).
-        if self.graph_waves > 0 and self.examples is None and self.tick_graph:
+        if self.examples is None and self.tick_graph:
             if self._tick_state == 0 or self._tick_temp != temp:
                 self._tick_tail(temp)
                 self._tick_state, self._tick_temp, self._tick_graph = 1, temp, None

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
     ap.add_argument("--graph-waves", type=int, default=128, help="waves per CUDA-graph replay (0: plain launches)")
+    ap.add_argument("--tick-waves", type=int, default=0, help="waves between two rounds of moves (0: --graph-waves, or 16 with plain launches)")
     ap.add_argument("--gc", default="reachable", choices=["ply", "reachable"],
                     help="tree cleaning: ply = exact (keeps every node that could still be looked up), reachable = only what the root reaches")
     ap.add_argument("--clean-moves", type=float, default=4.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")
@@ -280,11 +281,11 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16)
     reach = args.gc == "reachable"
     cap = args.node_cap or 8 * sims
-    G0 = args.graph_waves if args.graph_waves > 0 else 16
+    G0 = args.tick_waves or (args.graph_waves if args.graph_waves > 0 else 16)
     clean_every = max(1, int(args.clean_moves * sims / G0)) if args.async_moves else 0
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
                              edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels,
-                             clean_every=clean_every, clean_percent=45, overlap_nnet=None if args.overlap else False)
+                             clean_every=clean_every, clean_percent=45, overlap_nnet=None if args.overlap else False, tick_graph=True)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
         eng.evaluator = lambda s, v: eng.arena.fixed_net(s, v, pi_buf, v_buf)
@@ -295,7 +296,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     eng.env.rollout(args.opening_plies, rotate=True)    # mid-game positions, lanes de-synchronised by the random openings
 
     W = max(args.warmup, 3)
-    G = args.graph_waves if args.graph_waves > 0 else 16
+    G = G0
     ticks_per_step = -(-sims // G)
     if args.async_moves:
         eng.start_async()
@@ -393,7 +394,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
-                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
+                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "waves_per_tick": G, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
                    "moves_completed": int(eng.moves_completed.item()) if args.async_moves else args.steps * T, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
