@@ -571,7 +571,14 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
                 }
             }
 #endif
+#ifdef __CUDACC__
+            long long prof_t0 = 0;
+            if (A.prof) prof_t0 = clock64();
+#endif
             const int ei = mcts_pick(w, ed, first, (int)nd.n_edges, nd.u.x.Ns, nd.u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
+#ifdef __CUDACC__
+            if (A.prof && w.lane == 0) { A.prof[(size_t)t * 16 + 6] += clock64() - prof_t0; A.prof[(size_t)t * 16 + 7] += 1; }   // diagnostics: cycles inside the pick, levels
+#endif
             if (w.lane == 0) {
                 path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd.edge_off + (uint32_t)ei;
                 if (ei != hint) nodes[cur].u.x.pad[0] = (uint32_t)ei + 1u;

@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
     ap.add_argument("--wide-trees", type=int, default=65536, help="second MCTS point: this many games per GPU (0: skip)")
+    ap.add_argument("--wide-tick-waves", type=int, default=16, help="waves between two rounds of moves of the second MCTS point")
     ap.add_argument("--wide-sims", type=int, default=64, help="simulations per move of the second MCTS point")
     # env (configs[4])
     ap.add_argument("--lanes", type=int, default=1 << 20, help="game lanes per GPU")
@@ -465,10 +466,11 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     n, T, sims = args.players, args.wide_trees, args.wide_sims
     net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
     cap = 8 * sims
-    G = min(16, args.graph_waves) if args.graph_waves > 0 else 16      # short budgets: look for finished lanes every 16 waves
+    G = min(args.wide_tick_waves, args.graph_waves) if args.graph_waves > 0 else args.wide_tick_waves      # short budgets: look for finished lanes often
     eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
                              gc_reachable=args.gc == "reachable", graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds,
-                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if args.async_moves else 0, clean_percent=45)
+                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if args.async_moves else 0, clean_percent=45,
+                             tick_graph=True)
     eng.env.rollout(args.opening_plies, rotate=True)
     ticks = -(-sims // G)
     if args.async_moves:

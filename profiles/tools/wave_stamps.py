@@ -57,7 +57,7 @@ def main():
         if w < 5:
             continue
         ed_us = (p[:, 3] - p[:, 1]) / mhz
-        rw = p[:, 7] != 0
+        rw = p[:, 11] != 0
         at = p[:, 13] != 0
         cur = {
             "ed_kernel_span_us": (p[:, 5].max() - p[:, 0].min()) / 1e3,
@@ -77,6 +77,9 @@ def main():
                 "attach_start_after_rules_end_us": (p[at, 12].min() - p[rw, 11].max()) / 1e3,
             })
         else:             # rules step inside the descent kernel
+            lv = p[:, 7] > 0
+            cur["ed_pick_us_per_level"] = pct((p[lv, 6] / p[lv, 7]) / mhz)
+            cur["ed_pick_share_of_descent"] = float((p[lv, 6] / mhz).sum() / ((p[lv, 3] - p[lv, 2]) / mhz).sum())
             fr = (p[:, 4] // 1000) == 2
             cur.update({"ed_rules_step_us": pct((p[fr, 9] - p[fr, 3]) / mhz), "ed_warp_with_rules_us": pct((p[:, 9] - p[:, 1]) / mhz),
                         "attach_start_after_ed_end_us": (p[at, 12].min() - p[:, 5].max()) / 1e3})
