@@ -416,6 +416,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     ar.set_params(max_levels=args.e2e_max_levels)     # lock-step calls wait for the slowest tree (0: no yielding inside a descent)
     ke = 3
     h2d = d2h = 0
+    launches0 = ar.launches
     barrier()
     t0 = time.perf_counter()
     for _ in range(ke):
@@ -431,7 +432,9 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     line["e2e"] = {"value": world * T * sims * ke / float(t.item()), "unit": UNIT_MCTS, "h2d_bytes_per_step": h2d // ke, "d2h_bytes_per_step": d2h // ke,
                    "call": "MCTSArena.get_action_prob_batch(host boards) -> host probs/q, then SplendorGame.getNextStateBatch(host boards, actions)",
-                   "steps": ke}
+                   "steps": ke, "waves_per_move": (ar.launches - launches0) / 4.0 / ke,
+                   "note": "lock-step: every wave lasts as long as the deepest descent of any tree and the call returns when the slowest tree "
+                           "has spent its budget (its ~1600 sequential simulations bound the call from below)"}
     if world > 1:
         line["example_exchange"] = check_example_exchange(args, torch, dist, azg, world, rank, local)
     return line, eng
