@@ -379,10 +379,14 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         ar.drain_nnet()
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = B_SIM[n] * T / (sel * 1e-3) / 1e9
+    # B_SIM covers a whole simulation (selection + backup + expansion + network I/O), so it is divided by the whole wave: the
+    # one-call wave when the fused evaluator is in use, else selection + network + expansion
+    wave_ms = ovl if ovl is not None else sel + nnt + exp
+    achieved = B_SIM[n] * T / (wave_ms * 1e-3) / 1e9
     tr = load_traffic(f"mcts_wave_n{n}_bytes_per_sim")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None if tr is None else tr * T,
-                "kernel": "selection wave (mcts_expand_descend_kernel + mcts_rules_kernel + mcts_attach_kernel)", "avg_launch_ms": sel,
+                "kernel": "steady-state wave: mcts_expand_descend_kernel (expansion + descent + rules step) -> nnet_forward_kernel || mcts_attach_kernel",
+                "avg_launch_ms": wave_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_sim": B_SIM[n],
                 "note": "one launch = one simulation of every tree; the search is bound by the latency of sequential waves, not bytes",
