@@ -1,9 +1,11 @@
 // libsplendor_b200.so - MCTS tree arena kernels for sm_100a and their C ABI (include/splendor_b200.h).
-// The per-tree logic lives in spl_mcts.cuh; this file is launch plumbing. A selection wave is three kernels:
-//   mcts_descend_kernel  one warp per tree, light (PUCT pick + path only, no rules code -> every tree resident at once)
-//   mcts_rules_kernel    one LANE per tree, a few trees per warp, states staged in shared memory by cp.async:
+// The per-tree logic lives in spl_mcts.cuh; this file is launch plumbing. A selection wave is
+//   mcts_descend_kernel / mcts_expand_descend_kernel   one warp per tree: (expansion of the previous leaf +) PUCT descent + path;
+//                        with RULES also the rules step of the tree's pending edge (lane 0 of the warp)
+//   mcts_rules_kernel    the rules step as its own launch: one LANE per tree, a few trees per warp, states staged by cp.async:
 //                        make_move + swap_players + getGameEnded + getValidMoves of the child of every pending edge
 //   mcts_attach_kernel   one warp per tree: hash, dictionary lookup / insertion, edge allocation, leaf hand-over
+// spl_mcts_wave_nnet chains them with the fused evaluator (spl_nnet.cu): descent -> network, attach on a side stream.
 // A tree whose new edge led into a node it already holds (transposition) or into a terminal node carries on in the next
 // wave; `rounds` > 1 repeats the three kernels inside one wave instead (measured: not worth the extra straggler-bound launches).
 #include <cuda_runtime.h>

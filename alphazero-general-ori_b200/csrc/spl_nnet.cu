@@ -145,34 +145,6 @@ __device__ __forceinline__ const __nv_bfloat16* b1_lane_ptr(const __nv_bfloat16*
     return w + (lane & 7) * stride + (lane >> 3) * 8;
 }
 
-// A fragments of a 16-row strip
-template <int KS>
-__device__ __forceinline__ void load_afrags(uint32_t (&afr)[8][4], const __nv_bfloat16* a, int stride, int lane) {
-    const __nv_bfloat16* p = a_lane_ptr(a, stride, lane);
-#pragma unroll
-    for (int ks = 0; ks < KS; ks++) ldsm4(afr[ks], p + ks * 16);
-}
-
-// stage A: one warp = one 16-row strip, A in registers, one [64 n][KB] weight block -> 8 output tiles, two at a time
-template <int KS, class Epi>
-__device__ __forceinline__ void strip_gemm(const uint32_t (&afr)[8][4], const __nv_bfloat16* w, int wstride, int lane, Epi epi) {
-    const __nv_bfloat16* wl = b2_lane_ptr(w, wstride, lane);
-#pragma unroll 2
-    for (int np = 0; np < 4; np++) {
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-        const __nv_bfloat16* wr = wl + np * 16 * wstride;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            uint32_t b[4];
-            ldsm4(b, wr + ks * 16);
-            mma_bf16(c0, afr[ks], b[0], b[1]);
-            mma_bf16(c1, afr[ks], b[2], b[3]);
-        }
-        epi(2 * np, c0);
-        epi(2 * np + 1, c1);
-    }
-}
-
 // stage B: 16 rows shared by all warps (A from shared memory); this warp computes NT output tiles (8 n each, block rows at
 // w[t]) that share the A fragments. mma.sync has a long dependent latency, so the k-steps of every tile alternate between two
 // accumulators (summed at the end): 2 NT independent chains of KS / 2 instead of NT chains of KS one after the other.
