@@ -436,3 +436,34 @@ def test_train_batches_from_selfplay_examples_stay_on_the_device():
     assert torch.equal(out["boards"], ex["board"][ids].float()) and float(out["target_scdiffs"].sum()) == 64 * n
     sd = (ex["scdiff"][ids].long() + 15).clamp(0, 30)
     assert bool((out["target_scdiffs"].argmax(1) == sd).all())
+
+
+def test_selfplay_async_graph_replay_path():
+    """the configuration bench.py times: captured waves (spl_mcts_wave_nnet under a CUDA graph: programmatic dependent launches,
+    attach on the side stream) + the per-tick move logic replayed as a second graph. Invariants: every completed move spent
+    exactly its budget, games finish and restart, no tree overflows, the network evaluates about one row per simulation."""
+    az = _azg()
+    n, T, sims = 2, 256, 32
+    net = az.FusedSplendorNNet(n, seed=2)
+    eng = az.SelfPlayEngine(n, T, net, sims, seed=13, node_cap=8 * sims, gc_reachable=True, graph_waves=8, max_levels=16,
+                            clean_every=6, clean_percent=45, tick_graph=True)
+    assert eng.overlap_nnet
+    eng.env.rollout(60, rotate=True)
+    eng.start_async()
+    for _ in range(80):
+        eng.tick(8)
+    assert eng._tick_graph is not None and eng._graph is not None          # both graphs were captured and replayed
+    moves, done_sims = int(eng.moves_completed.item()), int(eng.sims_completed.item())
+    assert moves > 8 * T and done_sims == moves * sims
+    assert int(eng.games_finished.item()) >= 5
+    st = eng.arena.root_stats(want_arrays=False)
+    assert int(st["status"].max()) == 0 and int(st["truncated"].sum()) == 0
+    rows = float(st["nn_calls"].sum()) / max(1, done_sims + int(eng.sims_in_flight().item()))
+    assert 0.5 < rows < 1.2
+    # the boards the engine holds are consistent game states: the rules oracle accepts them and agrees on the legal moves
+    from oracle import pyoracle as po
+    eng.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
+    boards, valids = _np(eng.env.states()), _np(eng.env.valids())
+    for i in range(0, T, 17):
+        b = po.Board(n).set_state(boards[i])
+        assert np.array_equal(b.valid_moves(0), valids[i].astype(bool))
