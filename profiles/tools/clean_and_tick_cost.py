@@ -1,0 +1,28 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+import azg_b200 as azg
+n, T, sims = 2, 4096, 1600
+net = azg.FusedSplendorNNet(n, seed=1)
+cap = 8 * sims
+eng = azg.SelfPlayEngine(n, T, net, sims, seed=1, node_cap=cap, edge_cap=cap * 36, gc_reachable=True, graph_waves=128, max_levels=16, clean_every=0, tick_graph=True)
+eng.env.rollout(24, rotate=True)
+eng.start_async()
+ticks_per_move = sims // 128
+for mv in range(12):
+    for _ in range(ticks_per_move):
+        eng.tick(128)
+    if mv % 4 == 3:
+        st = eng.arena.root_stats(want_arrays=False)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.arena.clean(45); b.record(); torch.cuda.synchronize()
+        st2 = eng.arena.root_stats(want_arrays=False)
+        print("move", mv + 1, "clean ms %.2f" % a.elapsed_time(b), "nodes before mean/max", float(st["nodes"].float().mean()), int(st["nodes"].max()),
+              "after", float(st2["nodes"].float().mean()), int(st2["nodes"].max()), "cleaned trees", int((st2["cleanings"] - st["cleanings"]).sum()))
+# tick tail cost
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+a.record()
+for _ in range(20):
+    eng._tick_graph.replay()
+b.record(); torch.cuda.synchronize()
+print("tick tail graph replay ms", a.elapsed_time(b) / 20)
