@@ -37,7 +37,7 @@ constexpr int NN_GROUPS = 2;     // warp groups per CTA: both consume the same w
                                  // 190 MB of weights through L2 per 4096-leaf wave)
 constexpr int NN_THREADS = 256 * NN_GROUPS;
 constexpr int ASTR = 136;        // activation row stride in bf16 elements (128 + 8: conflict-free fragment loads)
-constexpr int FSTR = 712;        // flattened row stride (704 + 8)
+constexpr int FLAT_KC = 88;      // 704 flattened features = 88 core matrices per row group of the L4 operand
 constexpr int LSTR = 416;        // logits row stride (fp32)
 constexpr int NN_ACTIONS = 406;
 constexpr int NN_MAXBLK = 48;
@@ -69,7 +69,7 @@ NnPlan make_plan(int n) {
     };
     const int ka[4] = {kpad1(n), 128, 96, 128};   // L1 dense2d_1.0, L2 dense2d_1.3, G1 partialgpool_1.dense_part.0, L3 dense2d_3.0
     for (int i = 0; i < 4; i++) { p.a_off[i] = o; p.a_bytes[i] = 128 * ka[i] * 2; o += p.a_bytes[i]; }
-    for (int i = 0; i < 11; i++) add(128, 64);  // L4   dense1d_4.0 (704 = 11 x 64)
+    for (int i = 0; i < 11; i++) { p.off[b] = o; p.kb[b] = 64; p.bytes[b] = 128 * 64 * 2; o += p.bytes[b]; b++; }   // L4 dense1d_4.0 (704 = 11 x 64): canonical UMMA tiles
     add(64, 112); add(64, 112);                 // G4
     add(64, 128); add(64, 128);                 // L5a
     add(64, 128); add(64, 128);                 // L5b
@@ -84,6 +84,7 @@ NnPlan make_plan(int n) {
 }
 
 constexpr int SLOT_BYTES = 128 * 72 * 2;   // largest block: [128 n][64 k]
+constexpr int L4_SLOTS = 8;                // L4's own ring: the four slots below + the two dead stage A operand tiles (two tiles each)
 constexpr int NN_SLOTS = 4;                // weight ring: blocks are requested 3 steps ahead (a step is shorter than an L2 round trip)
 static_assert(SLOT_BYTES >= 64 * ASTR * 2, "slot holds a [64][128] block");
 
@@ -92,19 +93,24 @@ struct NnGroupSmem {
     // stage A: the UMMA operand tile (canonical layout); its last layer leaves the activations here as rows of ASTR elements
     // (112 x 136 x 2 = 30,464 bytes) for the flatten step; later the fp32 logits
     __align__(128) __nv_bfloat16 act[ATILE_BYTES / 2];
-    __nv_bfloat16 flat[NN_SB * FSTR];
     __nv_bfloat16 vec[3][NN_SB * ASTR];
 };
 struct NnSmem {
+    // L4 (704 -> 128) runs as ONE M = 128 UMMA tile whose rows 0..31 are the CTA's 32 leaves: the tensor core also reads the 96
+    // rows "behind" them (16 row groups x 11,264 bytes = 176 KB from the start of `flat`) and fills accumulator rows nobody
+    // looks at. `flat` therefore comes first, so that those reads stay inside this allocation.
+    __align__(128) unsigned char flat[4 * FLAT_KC * 128];      // 32 leaves x 704 features, canonical UMMA layout (KC = 88)
     __align__(128) unsigned char slot[NN_SLOTS][SLOT_BYTES];   // stage B: four ring slots; stage A: two slots of 2 SLOT_BYTES (whole layers)
     NnGroupSmem grp[NN_GROUPS];
     float prm[P_TOTAL];                      // biases / BatchNorm terms: read in every epilogue, so not from L2
-    uint64_t mma_bar[NN_GROUPS];             // tcgen05.commit arrives here: one barrier per group's accumulator block
+    uint64_t mma_bar[NN_GROUPS];             // stage A: tcgen05.commit arrives here: one barrier per group's accumulator block
+    uint64_t l4_full[L4_SLOTS], l4_empty[L4_SLOTS], l4_done;   // L4: TMA producer -> MMA issuer -> slot free / accumulator ready
     uint32_t tmem_base;
 };
 static_assert(ATILE_BYTES >= (int)sizeof(__nv_bfloat16) * 7 * NN_SB * ASTR && ATILE_BYTES >= (int)sizeof(float) * NN_SB * LSTR, "aliases of the operand tile");
 static_assert(2 * SLOT_BYTES >= 128 * 128 * 2, "a whole 128 x 128 layer fits two ring slots");
 static_assert(sizeof(NnSmem) <= 227 * 1024, "shared memory budget");
+static_assert(16 * FLAT_KC * 128 <= (int)sizeof(NnSmem), "the rows the tensor core reads behind the 32 real ones lie inside the allocation");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -237,7 +243,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     issue_a(0);
     issue_a(1);
     if (tid < 32) umma::tmem_alloc(&smem_all.tmem_base, 256);      // one 128-column accumulator block per group
-    if (tid == 32) { umma::mbar_init(&smem_all.mma_bar[0], 1); umma::mbar_init(&smem_all.mma_bar[1], 1); }
+    if (tid == 32) {
+        umma::mbar_init(&smem_all.mma_bar[0], 1); umma::mbar_init(&smem_all.mma_bar[1], 1); umma::mbar_init(&smem_all.l4_done, 1);
+        for (int i = 0; i < L4_SLOTS; i++) { umma::mbar_init(&smem_all.l4_full[i], 1); umma::mbar_init(&smem_all.l4_empty[i], 1); }
+    }
 
     // ---- stage B weight-block ring: block b lives in slot b % NN_SLOTS and is requested NN_SLOTS - 1 steps before its use
     auto issue = [&](int b) {
@@ -391,66 +400,105 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
             if (group == 0) umma::mbar_wait(&smem_all.mma_bar[1], phase);   // every MMA of the layer is done: its weight slot is free again
             phase ^= 1u;
             if (l < 2) issue_a(l + 2);
-            if (l == 3) while (next_issue < min(plan.nblocks, NN_SLOTS)) issue(next_issue++);   // stage B's first blocks
+            if (l == 3 && tid == 0)                                       // L4's first four weight tiles travel from here on
+                for (int j = 0; j < NN_SLOTS; j++) {
+                    umma::mbar_expect(&smem_all.l4_full[j], 128 * 64 * 2);
+                    umma::bulk_load(smem_all.slot[j], blob + plan.off[j], 128 * 64 * 2, &smem_all.l4_full[j]);
+                }
             NN_STAMP(2 + l);
         }
         umma::fence_before_sync();
         __syncthreads();
-        if (tid < 32) umma::tmem_dealloc(smem_all.tmem_base, 256);
     }
-    int blk = 0;
 
     // ---- FlattenAndPartialGPool(64, 5): [max over the 5 gem colours | mean | gold, points rows | last 64 features of all 7]
+    // -> row (group * 16 + leaf) of the L4 operand (canonical UMMA layout, 88 core matrices per row group)
+    auto flat_at = [&](int r, int k) -> __nv_bfloat16* {
+        return reinterpret_cast<__nv_bfloat16*>(smem_all.flat + umma::chunk_off(r, k >> 3, FLAT_KC) + (k & 7) * 2);
+    };
     for (int i = gtid; i < NN_SB * 64; i += 256) {          // first 64 features of every row: pooled over the colour rows
-        const int s = i >> 6, j = i & 63;
+        const int s = i >> 6, j = i & 63, r = group * NN_SB + s;
         float a[7];
 #pragma unroll
         for (int c = 0; c < 7; c++) a[c] = __bfloat162float(sm.act[(c * 16 + s) * ASTR + j]);
         const float mx = fmaxf(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])), a[4]);
         const float sum = a[0] + a[1] + a[2] + a[3] + a[4];
-        __nv_bfloat16* o = sm.flat + s * FSTR + j;
-        o[0] = __float2bfloat16(mx); o[64] = __float2bfloat16(sum * 0.2f);
-        o[128] = __float2bfloat16(a[5]); o[192] = __float2bfloat16(a[6]);
+        *flat_at(r, j) = __float2bfloat16(mx); *flat_at(r, 64 + j) = __float2bfloat16(sum * 0.2f);
+        *flat_at(r, 128 + j) = __float2bfloat16(a[5]); *flat_at(r, 192 + j) = __float2bfloat16(a[6]);
     }
     for (int i = gtid; i < NN_SB * 7 * 32; i += 256) {      // last 64 features of all 7 rows: copied, two at a time
-        const int s = i / 224, r = i - s * 224, c = r >> 5, jj = (r & 31) * 2;
-        *reinterpret_cast<uint32_t*>(sm.flat + s * FSTR + 256 + c * 64 + jj) =
-            *reinterpret_cast<const uint32_t*>(sm.act + (c * 16 + s) * ASTR + 64 + jj);
+        const int s = i / 224, rr = i - s * 224, c = rr >> 5, jj = (rr & 31) * 2;
+        *reinterpret_cast<uint32_t*>(flat_at(group * NN_SB + s, 256 + c * 64 + jj)) = *reinterpret_cast<const uint32_t*>(sm.act + (c * 16 + s) * ASTR + 64 + jj);
     }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
     __syncthreads();
 
     NN_STAMP(6);
-    // ---- L4: Linear(704,128) + ReLU. 16 rows; warp w owns output tiles 2w, 2w+1; accumulate over 11 k-blocks
+    // ---- L4: Linear(704,128) + ReLU on tcgen05 as a three-role pipeline over the four ring slots: one thread streams the eleven
+    // [128 n][64 k] weight tiles by TMA bulk copies (mbarrier complete_tx), one thread issues four MMAs per tile as it lands and
+    // frees the slot with tcgen05.commit, everybody else sleeps on the barrier of the finished accumulator (TMEM columns 0..127).
+    // Eight slots: the four ring slots (their tiles are requested as soon as stage A's last MMAs are done, i.e. they travel during
+    // that layer's epilogue and the flatten step) and the two operand tiles of stage A, which are dead once the flatten step has
+    // read them (a 16 KB tile takes ~1 us to arrive, an MMA group 0.13 us: the depth of the ring is what sets the pace).
     {
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-        float acc[2][2][2][4];   // [k-block parity][k-step parity][tile]: eight independent accumulation chains
+        const int wc = tid >> 5;
+        auto l4_slot = [&](int i) -> unsigned char* {
+            return i < NN_SLOTS ? smem_all.slot[i] : reinterpret_cast<unsigned char*>(smem_all.grp[(i - NN_SLOTS) >> 1].act) + ((i - NN_SLOTS) & 1) * (128 * 64 * 2);
+        };
+        if (wc == 0) {
+            if (lane == 0) {
+                for (int j = NN_SLOTS; j < 11; j++) {                     // tiles 0..3 were requested after stage A's last MMAs
+                    const int sl = j % L4_SLOTS;
+                    if (j >= L4_SLOTS) umma::mbar_wait(&smem_all.l4_empty[sl], (uint32_t)((j / L4_SLOTS - 1) & 1));
+                    umma::mbar_expect(&smem_all.l4_full[sl], 128 * 64 * 2);
+                    umma::bulk_load(l4_slot(sl), blob + plan.off[j], 128 * 64 * 2, &smem_all.l4_full[sl]);
+                }
+            }
+            __syncwarp();
+        } else if (wc == 1) {
+            if (lane == 0) {
+                umma::fence_after_sync();
+                const uint32_t idesc = umma::instr_desc_bf16(128, 128);
+                const uint32_t tb = smem_all.tmem_base;
+                for (int j = 0; j < 11; j++) {
+                    const int sl = j % L4_SLOTS;
+                    umma::mbar_wait(&smem_all.l4_full[sl], (uint32_t)((j / L4_SLOTS) & 1));
+                    umma::fence_after_sync();
+                    const uint64_t ad0 = umma::smem_desc(umma::smem_u32(smem_all.flat) + j * 8 * 128, 128, FLAT_KC * 128);
+                    const uint64_t bd0 = umma::smem_desc(umma::smem_u32(l4_slot(sl)), 128, 8 * 128);
 #pragma unroll
-        for (int i = 0; i < 32; i++) (&acc[0][0][0][0])[i] = 0.f;
-        for (int kb = 0; kb < 11; kb += 2) {   // two k-blocks per ring step
-            const int cnt = kb + 1 < 11 ? 2 : 1;
-            acquire(blk, cnt);
-            tile2_gemm<4>(acc[0][0][0], acc[0][0][1], acc[0][1][0], acc[0][1][1], sm.flat + kb * 64, FSTR, slot_of(blk) + (2 * warp) * 8 * 72, 72, lane);
-            if (cnt == 2)
-                tile2_gemm<4>(acc[1][0][0], acc[1][0][1], acc[1][1][0], acc[1][1][1], sm.flat + (kb + 1) * 64, FSTR, slot_of(blk + 1) + (2 * warp) * 8 * 72,
-                              72, lane);
-            release(); blk += cnt;
+                    for (int k = 0; k < 4; k++) umma::mma_bf16_ss(tb, ad0 + (uint64_t)(16 * k), bd0 + (uint64_t)(16 * k), idesc, j > 0 || k > 0);
+                    umma::commit(&smem_all.l4_empty[sl]);
+                }
+                umma::commit(&smem_all.l4_done);
+            }
+            __syncwarp();
         }
+        umma::mbar_wait(&smem_all.l4_done, 0);
+        umma::fence_after_sync();
+        if ((wc & 3) == 0) {      // the four warps that own TMEM lanes 0..31: lane = leaf, 32 output columns each -> bias + ReLU -> vec[0]
+            float v[32];
+            umma::tmem_ld32(umma::tmem_addr(smem_all.tmem_base, 0, 32 * (wc >> 2)), v);
+            __nv_bfloat16* o = smem_all.grp[lane >> 4].vec[0] + (lane & 15) * ASTR + 32 * (wc >> 2);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            c0[i] = (acc[0][0][0][i] + acc[0][1][0][i]) + (acc[1][0][0][i] + acc[1][1][0][i]);
-            c1[i] = (acc[0][0][1][i] + acc[0][1][1][i]) + (acc[1][0][1][i] + acc[1][1][1][i]);
+            for (int j = 0; j < 32; j += 8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(prm + P_B4 + 32 * (wc >> 2) + j);
+                const float4 b1 = *reinterpret_cast<const float4*>(prm + P_B4 + 32 * (wc >> 2) + j + 4);
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(v[j] + b0.x, 0.f), fmaxf(v[j + 1] + b0.y, 0.f));
+                const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(v[j + 2] + b0.z, 0.f), fmaxf(v[j + 3] + b0.w, 0.f));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[j + 4] + b1.x, 0.f), fmaxf(v[j + 5] + b1.y, 0.f));
+                const __nv_bfloat162 h3 = __floats2bfloat162_rn(fmaxf(v[j + 6] + b1.z, 0.f), fmaxf(v[j + 7] + b1.w, 0.f));
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                              *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+            }
         }
-        __nv_bfloat16* o = sm.vec[0];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            float(&c)[4] = q ? c1 : c0;
-            const int n = (2 * warp + q) * 8 + 2 * t;
-            const float b0 = prm[P_B4 + n], b1 = prm[P_B4 + n + 1];
-            sts_bf16x2(o + g * ASTR + n, fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f));
-            sts_bf16x2(o + (g + 8) * ASTR + n, fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f));
-        }
+        umma::fence_before_sync();
         __syncthreads();
+        if (tid < 32) umma::tmem_dealloc(smem_all.tmem_base, 256);
     }
+    int blk = 11;          // the remaining stage B tiles go through the cp.async ring (all four slots are free again)
+    next_issue = 11;
     // stage B helpers: in -> out, the two [64 n][KB] blocks of a layer in ONE ring step, warp w owns tile w of each block
     auto dense_vec = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int pbias, bool relu) {
         acquire(blk, 2);
@@ -619,13 +667,15 @@ void pack_block(unsigned char* dst, const float* W, int N, int K, int n0, int nb
         }
 }
 
-// W[N][K] (rows >= N and columns >= K zero) as a [128][kb] bf16 tile in the canonical UMMA K-major layout (spl_umma.cuh)
-void pack_canonical(unsigned char* dst, const float* W, int N, int K, int kb) {
+// rows [n0, n0 + nb) x columns [k0, k0 + kb) of W[N][K] (zero outside W) as a [nb][kb] bf16 tile in the canonical UMMA K-major
+// layout (spl_umma.cuh): element (r, c) at byte (r / 8) * (kb / 8) * 128 + (c / 8) * 128 + (r % 8) * 16 + (c % 8) * 2
+void pack_canonical(unsigned char* dst, const float* W, int N, int K, int n0, int nb, int k0, int kb) {
     uint16_t* d = reinterpret_cast<uint16_t*>(dst);
     const int kc = kb / 8;
-    for (int n = 0; n < 128; n++)
-        for (int k = 0; k < kb; k++) {
-            const size_t off = ((size_t)(n >> 3) * kc * 128 + (size_t)(k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) / 2;
+    for (int r = 0; r < nb; r++)
+        for (int c = 0; c < kb; c++) {
+            const int n = n0 + r, k = k0 + c;
+            const size_t off = ((size_t)(r >> 3) * kc * 128 + (size_t)(c >> 3) * 128 + (r & 7) * 16 + (c & 7) * 2) / 2;
             d[off] = (n < N && k < K) ? to_bf16((double)W[(size_t)n * K + k]) : (uint16_t)0;
         }
 }
@@ -672,11 +722,11 @@ int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_
         pack_block(B + p.off[b], W, N, K, 0, 64, 0, kb, scale); b++;
         pack_block(B + p.off[b], W, N, K, 64, 64, 0, kb, scale); b++;
     };
-    pack_canonical(B + p.a_off[0], T[0], 128, R, K1);
-    pack_canonical(B + p.a_off[1], T[6], 128, 128, 128);
-    pack_canonical(B + p.a_off[2], T[8], 120, 96, 96);
-    pack_canonical(B + p.a_off[3], T[14], 128, 128, 128);
-    for (int kbk = 0; kbk < 11; kbk++) { pack_block(B + p.off[b], T[16], 128, 704, 0, 128, kbk * 64, 64, 1.0); b++; }
+    pack_canonical(B + p.a_off[0], T[0], 128, R, 0, 128, 0, K1);
+    pack_canonical(B + p.a_off[1], T[6], 128, 128, 0, 128, 0, 128);
+    pack_canonical(B + p.a_off[2], T[8], 120, 96, 0, 128, 0, 96);
+    pack_canonical(B + p.a_off[3], T[14], 128, 128, 0, 128, 0, 128);
+    for (int kbk = 0; kbk < 11; kbk++) { pack_canonical(B + p.off[b], T[16], 128, 704, 0, 128, kbk * 64, 64); b++; }
     two(T[18], 120, 112, 112, bn4.s[0]);
     two(T[24], 128, 128, 128, bn5.s[0]);
     two(T[30], 128, 128, 128, 1.0);
