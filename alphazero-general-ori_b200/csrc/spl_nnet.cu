@@ -275,6 +275,24 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     // kernel that produces the input rows is still draining; the rows themselves are read only after it has completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next wave's descent may move in behind this grid
+    // the legality bits of the two rows this warp finishes in the softmax (bit j of vbits[q] = action lane + 32 j of row 2 warp + q):
+    // requested now, consumed ~30 us later, so the softmax does not start with a global-memory round trip
+    uint32_t vbits[2] = {0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int s = warp * 2 + q;
+        if (s < live) {
+            if (row_src && row_src[base + s]) {
+#pragma unroll
+                for (int j = 0; j < 13; j++) vbits[q] |= ((alt_mask[(size_t)j * alt_mask_stride + base + s] >> lane) & 1u) << j;
+            } else {
+                const uint8_t* va = valids + (size_t)(base + s) * NN_ACTIONS;
+#pragma unroll
+                for (int j = 0; j < 13; j++)
+                    if (lane + 32 * j < NN_ACTIONS) vbits[q] |= (va[lane + 32 * j] != 0 ? 1u : 0u) << j;
+            }
+        }
+    }
     // ---- input: operand tile row c*16 + s, column k = state[s][k][c] (int8 counts are exact in bf16), zero padding up to K1.
     // One thread per (leaf, 8 consecutive k): 56 consecutive state bytes in, seven 16-byte chunks out.
     unsigned char* atile = reinterpret_cast<unsigned char*>(sm.act);
@@ -426,9 +444,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
         *flat_at(r, j) = __float2bfloat16(mx); *flat_at(r, 64 + j) = __float2bfloat16(sum * 0.2f);
         *flat_at(r, 128 + j) = __float2bfloat16(a[5]); *flat_at(r, 192 + j) = __float2bfloat16(a[6]);
     }
-    for (int i = gtid; i < NN_SB * 7 * 32; i += 256) {      // last 64 features of all 7 rows: copied, two at a time
-        const int s = i / 224, rr = i - s * 224, c = rr >> 5, jj = (rr & 31) * 2;
-        *reinterpret_cast<uint32_t*>(flat_at(group * NN_SB + s, 256 + c * 64 + jj)) = *reinterpret_cast<const uint32_t*>(sm.act + (c * 16 + s) * ASTR + 64 + jj);
+    for (int i = gtid; i < NN_SB * 7 * 8; i += 256) {       // last 64 features of all 7 rows: copied, one 16-byte chunk (8 features) at a time
+        const int s = i / 56, rr = i - s * 56, c = rr >> 3, j8 = rr & 7;
+        *reinterpret_cast<uint4*>(flat_at(group * NN_SB + s, 256 + c * 64 + j8 * 8)) = *reinterpret_cast<const uint4*>(sm.act + (c * 16 + s) * ASTR + 64 + j8 * 8);
     }
     umma::fence_smem_to_async();
     umma::fence_before_sync();
@@ -601,16 +619,14 @@ __global__ void __launch_bounds__(NN_THREADS, 1) nnet_forward_kernel(const unsig
     // ---- masked softmax: log_softmax(where(valid, pi, -1e8)) then exp (SplendorNNet.py:153-159, GenericNNetWrapper.py:166)
     for (int s = warp * 2; s < warp * 2 + 2; s++) {
         if (s >= live) continue;
-        const uint8_t* va = valids + (size_t)(base + s) * NN_ACTIONS;
-        const bool alt = row_src && row_src[base + s];
+        const uint32_t vb = vbits[s - warp * 2];
         float x[13], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 13; j++) {
             const int a = lane + 32 * j;
             x[j] = -INFINITY;
             if (a < NN_ACTIONS) {
-                const bool ok = alt ? ((alt_mask[(size_t)j * alt_mask_stride + base + s] >> lane) & 1u) != 0u : va[a] != 0;
-                x[j] = ok ? logits[s * LSTR + a] : -1e8f;
+                x[j] = ((vb >> j) & 1u) ? logits[s * LSTR + a] : -1e8f;
                 mx = fmaxf(mx, x[j]);
             }
         }
