@@ -196,6 +196,26 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_expand_kernel(MctsArena A, Mc
     mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
 }
 
+// rotation of a contiguous block of BYTES bytes by `shift` bytes, all lanes of the warp: new[i] = old[(i + shift) mod BYTES]
+template <int BYTES>
+__device__ __forceinline__ void coop_roll_rows(int8_t* base, int shift, int lane) {
+    int8_t v[(BYTES + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (BYTES + 31) / 32; q++) {
+        const int i = lane + 32 * q;
+        int j = i + shift;
+        j = j >= BYTES ? j - BYTES : j;
+        v[q] = i < BYTES ? base[j] : (int8_t)0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < (BYTES + 31) / 32; q++) {
+        const int i = lane + 32 * q;
+        if (i < BYTES) base[i] = v[q];
+    }
+    __syncwarp();
+}
+
 // the rules step of ONE tree by its own warp (lane 0 walks the rules code, the warp does the copies): what mcts_rules_kernel does
 // for a few trees per warp, here without a kernel boundary between the descent and it. wsm: sp bytes of shared memory, 16-aligned.
 template <int N>
@@ -212,11 +232,43 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    // make_move on lane 0; swap_players (a byte rotation of the four per-player blocks) and the 15 candidate cards of valid_moves
+    // spread over the lanes; the rest of valid_moves and getGameEnded on lane 0 again - the same arithmetic as mcts_rules_core
+    typedef SplLay<N> L;
+    int nxt = 0;
+    if (lane == 0) {
+        AosAcc s{wsm};
+        SplChance ch;
+        ch.mode = 0; ch.code = 0; ch.seed = 0; ch.game = 0; ch.episode = 0; ch.ply = 0;
+        nxt = spl_apply_move<N>(s, action, 0, ch);
+    }
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    __syncwarp();
+    for (int it = 0; it < nxt; it++) {          // spl_rotate: new row j of a block = old row (j + shift) mod size, for four blocks
+        const int nob_shift = ((rules.flags & SPL_F_REFCOMPAT) || N == 2) ? 3 % (N * (N + 1)) : N + 1;   // :345 (F7a)
+        coop_roll_rows<N * 7>(wsm + 7 * L::PGEMS, 7, lane);
+        coop_roll_rows<N * (N + 1) * 7>(wsm + 7 * L::PNOBLES, 7 * nob_shift, lane);
+        coop_roll_rows<N * 7>(wsm + 7 * L::PCARDS, 7, lane);
+        coop_roll_rows<6 * N * 7>(wsm + 7 * L::PRES, 42, lane);
+    }
+    uint32_t pre[2] = {0u, 0u};
+    if (lane < 15) {
+        AosAcc s{wsm};
+        int have[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) have[c] = s.get(L::PGEMS, c) + s.get(L::PCARDS, c);
+        spl_card_bits<N>(s, 0, lane, have, s.get(L::PGEMS, 5), pre[0], pre[1]);
+    }
+    pre[0] = __reduce_or_sync(0xffffffffu, pre[0]);
+    pre[1] = __reduce_or_sync(0xffffffffu, pre[1]);
     if (lane == 0) {
         AosAcc s{wsm};
         float es[N];
         uint32_t m[SPL_MASK_WORDS];
-        const bool ended = mcts_rules_core<N>(s, action, rules, es, m);
+        const bool ended = spl_game_ended<N>(s, rules, es);
+        if (!ended) spl_valid_mask<N>(s, 0, rules, m, pre);
+        else
+            for (int i = 0; i < SPL_MASK_WORDS; i++) m[i] = 0u;
 #pragma unroll
         for (int i = 0; i < SPL_MASK_WORDS; i++) A.stage_mask[(size_t)i * A.n_trees + t] = m[i];
 #pragma unroll

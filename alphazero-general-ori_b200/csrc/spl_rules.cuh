@@ -186,8 +186,29 @@ SPL_D void spl_ex_words(uint32_t* m, uint32_t T, uint32_t G, int regime) {   // 
 // ------------------------------------------------------------------------------------------
 // legality mask (406 bits, little-endian in 13 words) for `player`
 // ------------------------------------------------------------------------------------------
+// candidate card i of valid_moves (0..11 visible, 12..14 the player's reserved slots): bit i of `buyable` (_valid_buy :476-501,
+// _valid_buy_reserve :538-552) and of `present` (:511). have[c] = gems + bonuses of colour c, gold = the player's gold.
 template <int N, class S>
-SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
+SPL_D void spl_card_bits(const S& s, int p, int i, const int* have, int gold, uint32_t& buyable, uint32_t& present) {
+    typedef SplLay<N> L;
+    const int row = i < 12 ? L::CARDS + 2 * i : L::PRES + 6 * p + 2 * (i - 12);
+    int missing = 0, any = 0;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const int cost = s.get(row, c);
+        const int d = (int)(int8_t)(cost - have[c]);
+        missing += d > 0 ? d : 0;
+        any |= cost;
+    }
+    const bool card = spl_sum5_nonzero(s, row, any);
+    buyable |= (uint32_t)((missing <= gold) && card) << i;
+    present |= (uint32_t)card << i;
+}
+
+// pre (may be NULL): {buyable, present} of the 15 candidate cards, computed elsewhere by spl_card_bits (the tree kernels spread
+// them over the lanes of a warp)
+template <int N, class S>
+SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint32_t* pre = nullptr) {
     typedef SplLay<N> L;
 #pragma unroll
     for (int w = 0; w < SPL_MASK_WORDS; w++) m[w] = 0;
@@ -208,20 +229,11 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m) {
     int have[5];   // gems + bonuses per colour; the reference subtracts both from the cost in int8 arithmetic (wraps mod 256)
 #pragma unroll
     for (int c = 0; c < 5; c++) have[c] = g[c] + pc[c];
+    if (pre) {
+        buyable = pre[0]; present = pre[1];
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < 15; i++) {
-        const int row = i < 12 ? L::CARDS + 2 * i : L::PRES + 6 * p + 2 * (i - 12);
-        int missing = 0, any = 0;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const int cost = s.get(row, c);
-            const int d = (int)(int8_t)(cost - have[c]);
-            missing += d > 0 ? d : 0;
-            any |= cost;
-        }
-        const bool card = spl_sum5_nonzero(s, row, any);
-        buyable |= (uint32_t)((missing <= gold) && card) << i;
-        present |= (uint32_t)card << i;
+        for (int i = 0; i < 15; i++) spl_card_bits<N>(s, p, i, have, gold, buyable, present);
     }
     const uint32_t buy = buyable & 0xFFFu, buyres = (buyable >> 12) & 7u;
     present &= 0xFFFu;
