@@ -232,6 +232,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    PROF_STAMP(A, t, 8, clock64());
     // make_move on lane 0; swap_players (a byte rotation of the four per-player blocks) and the 15 candidate cards of valid_moves
     // spread over the lanes; the rest of valid_moves and getGameEnded on lane 0 again - the same arithmetic as mcts_rules_core
     typedef SplLay<N> L;
@@ -251,6 +252,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
         coop_roll_rows<N * 7>(wsm + 7 * L::PCARDS, 7, lane);
         coop_roll_rows<6 * N * 7>(wsm + 7 * L::PRES, 42, lane);
     }
+    PROF_STAMP(A, t, 10, clock64());
     uint32_t pre[2] = {0u, 0u};
     if (lane < 15) {
         AosAcc s{wsm};
@@ -261,6 +263,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     }
     pre[0] = __reduce_or_sync(0xffffffffu, pre[0]);
     pre[1] = __reduce_or_sync(0xffffffffu, pre[1]);
+    PROF_STAMP(A, t, 11, clock64());
     if (lane == 0) {
         AosAcc s{wsm};
         float es[N];

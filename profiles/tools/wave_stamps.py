@@ -57,7 +57,7 @@ def main():
         if w < 5:
             continue
         ed_us = (p[:, 3] - p[:, 1]) / mhz
-        rw = p[:, 11] != 0
+        rw = p[:, 6] > 1e15      # (the separate rules kernel stamps a globaltimer there; the fused path keeps small counters in these slots)
         at = p[:, 13] != 0
         cur = {
             "ed_kernel_span_us": (p[:, 5].max() - p[:, 0].min()) / 1e3,
@@ -81,6 +81,9 @@ def main():
             cur["ed_pick_us_per_level"] = pct((p[lv, 6] / p[lv, 7]) / mhz)
             cur["ed_pick_share_of_descent"] = float((p[lv, 6] / mhz).sum() / ((p[lv, 3] - p[lv, 2]) / mhz).sum())
             fr = (p[:, 4] // 1000) == 2
+            fr = fr & (p[:, 8] != 0)
+            cur.update({"rules_load_us": pct((p[fr, 8] - p[fr, 3]) / mhz), "rules_move_and_rotate_us": pct((p[fr, 10] - p[fr, 8]) / mhz),
+                        "rules_card_flags_us": pct((p[fr, 11] - p[fr, 10]) / mhz), "rules_ended_mask_store_us": pct((p[fr, 9] - p[fr, 11]) / mhz)})
             cur.update({"ed_rules_step_us": pct((p[fr, 9] - p[fr, 3]) / mhz), "ed_warp_with_rules_us": pct((p[:, 9] - p[:, 1]) / mhz),
                         "attach_start_after_ed_end_us": (p[at, 12].min() - p[:, 5].max()) / 1e3})
         for k, v in cur.items():
