@@ -28,7 +28,7 @@ EXPORTS = [
     "spl_pack", "spl_unpack", "spl_mask_unpack", "spl_reset_philox", "spl_reset_explicit", "spl_step", "spl_rollout",
     "spl_scores", "spl_symmetries",
     "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
-    "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_wave_nnet", "spl_mcts_debug_profile", "spl_mcts_policy", "spl_mcts_root_stats", "spl_mcts_fixed_net",
+    "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_wave_nnet", "spl_mcts_debug_profile", "spl_mcts_policy", "spl_mcts_sample_moves", "spl_mcts_root_stats", "spl_mcts_fixed_net",
     "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_nnet_debug_cta_times", "spl_umma_selftest",
 ]
 MCTS_MOVE_FORCED, MCTS_MOVE_NOISE = 1, 2
@@ -136,6 +136,7 @@ def lib():
         L.spl_mcts_wave_nnet.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.spl_mcts_debug_profile.argtypes = [vp, vp]
         L.spl_mcts_policy.argtypes = [vp, C.c_double, vp, vp, vp]
+        L.spl_mcts_sample_moves.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp]
         L.spl_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]
         L.spl_mcts_fixed_net.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         L.spl_nnet_blob_bytes.argtypes = [ci]

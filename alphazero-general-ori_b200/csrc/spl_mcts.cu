@@ -319,6 +319,24 @@ __global__ void __launch_bounds__(MW * 32) mcts_policy_kernel(MctsArena A, doubl
     mcts_policy_tree<N>(w, A, t, temp, probs + (size_t)t * SPL_ACTIONS, q + (size_t)t * N, sc.dwords);
 }
 
+template <int N>
+__global__ void __launch_bounds__(MW * 32) mcts_sample_kernel(MctsArena A, MctsSearchParams P, double temp, const uint32_t* episodes, int16_t* actions, uint8_t* finished,
+                                                              long long* counters) {
+    const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
+    if (t >= A.n_trees) return;
+    MctsWarp w{(int)(threadIdx.x & 31)};
+    bool fin = false;
+    const int a = mcts_sample_tree<N>(w, A, t, P, temp, episodes ? episodes[t] : 0u, &fin);
+    if (w.lane == 0) {
+        actions[t] = (int16_t)(fin ? a : -1);
+        finished[t] = fin ? 1 : 0;
+        if (counters && fin) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counters[0]), (unsigned long long)A.trees[t].sims_done);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counters[1]), 1ull);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MW * 32) mcts_stats_kernel(MctsArena A, int32_t* nsa, double* qsa, float* ps, int32_t* info) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
@@ -588,6 +606,14 @@ int spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* st
     ENTER_M(m);
     if (!probs || !q || temp < 0.0) return spl_fail_(SPL_E_ARG, "spl_mcts_policy: bad argument");
     DISPATCH_N(m->ctx->n, mcts_policy_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, temp, probs, q));
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_sample_moves(spl_mcts* m, double temp, const uint32_t* episodes, int16_t* actions, uint8_t* finished, long long* counters, void* stream) {
+    ENTER_M(m);
+    if (!actions || !finished || temp < 0.0) return spl_fail_(SPL_E_ARG, "spl_mcts_sample_moves: bad argument");
+    DISPATCH_N(m->ctx->n, mcts_sample_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, temp, episodes, actions, finished, counters));
     CU(cudaGetLastError());
     return SPL_OK;
 }

@@ -1210,6 +1210,57 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
     w.sync();
 }
 
+// getActionProb's tail + the caller's pick from it, for a tree whose budget is spent (Coach.py:75-86: `pi = getActionProb(...)`,
+// `action = np.random.choice(len(pi), p=pi)`), without materialising the 406 probabilities: the weights of mcts_policy_tree
+// (counts -> policy-target pruning -> temperature), then one uniform from Philox keyed (seed, game, episode, root ply) and a walk
+// through the cumulative weights in action order. Returns the action, or -1 while the tree's search is still running.
+// temp == 0: the first most visited action. A finished tree without a single visit (never in a game in progress) gives -1 too.
+template <int N, class W>
+SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, double temp, uint32_t episode, bool* finished) {
+    const MctsTree* T = A.trees + t;
+    const bool fin = T->root >= 0 && (T->sims_done >= T->sims_target || T->status != 0u);
+    *finished = fin;
+    if (!fin) return -1;
+    const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+    if (nd->kind != MCTS_NODE_EXPANDED) return -1;
+    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
+    const int k = nd->n_edges;
+    const bool forced = (T->flags & MCTS_F_FORCED) != 0u;
+    int action = -1;
+    if (w.lane == 0) {
+        int best = 0;
+        for (int i = 0; i < k; i++) best = ed[i].N > best ? ed[i].N : best;
+        double sum = 0.0, bestc = -1.0;
+        int besti = -1;
+        for (int pass = 0; pass < 2; pass++) {      // pass 0: total weight, pass 1: the walk up to u * total
+            double target = 0.0, acc = 0.0;
+            if (pass == 1) {
+                if (temp == 0.0 || !(sum > 0.0)) break;
+                const SplPhilox r = spl_philox(P.seed, P.game_base + (uint32_t)t, episode, (uint32_t)nd->ply, 5);
+                target = MC_DMUL(mcts_u01(r.v[0], r.v[1]), sum);
+            }
+            for (int i = 0; i < k; i++) {
+                double c = (double)ed[i].N;
+                if (forced) {   // policy target pruning :69-74
+                    if (ed[i].N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)ed[i].P), (double)T->sims_target));
+                    c = c > 1.0 ? c : 0.0;
+                }
+                if (pass == 0 && c > bestc) { bestc = c; besti = i; }
+                if (temp != 0.0 && temp != 1.0) c = pow(c, 1.0 / temp);   // :94
+                if (pass == 0) sum = MC_DADD(sum, c);
+                else {
+                    acc = MC_DADD(acc, c);
+                    if (c > 0.0) action = (int)ed[i].action;      // the last action with weight, should rounding leave acc <= target at the end
+                    if (acc > target) break;
+                }
+            }
+        }
+        if (temp == 0.0 && besti >= 0 && bestc > 0.0) action = (int)ed[besti].action;
+    }
+    action = w.shfl(action, 0);
+    return action;
+}
+
 // raw root statistics (tests, diagnostics): Nsa int32[406], Qsa double[406], Ps float[406], info int32[16]
 template <class W>
 SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* nsa, double* qsa, float* ps, int32_t* info) {

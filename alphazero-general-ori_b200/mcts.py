@@ -255,6 +255,20 @@ class MCTSArena:
         self.launches += 1
         return probs, q
 
+    def sample_moves(self, temp=1.0, episodes=None, actions=None, finished=None, counters=None):
+        """for every tree whose budget is spent: one action drawn from its visit distribution (getActionProb's tail + the caller's
+        np.random.choice, Coach.py:75-86) without materialising the probabilities -> (actions int16[T], -1 = still searching;
+        finished uint8[T]); counters int64[2] (optional) += (simulations of the finished trees, finished trees); episodes: the lanes'
+        episode counters (int32 / uint32 [T], part of the Philox key of the draw)"""
+        if actions is None:
+            actions = torch.empty(self.T, dtype=torch.int16, device=self.device)
+        if finished is None:
+            finished = torch.empty(self.T, dtype=torch.uint8, device=self.device)
+        nat.check(self._lib.spl_mcts_sample_moves(self._m, float(temp), _ptr(episodes), _ptr(actions), _ptr(finished), _ptr(counters),
+                                                  self._stream()))
+        self.launches += 1
+        return actions, finished
+
     def root_stats(self, want_arrays=True):
         """-> dict of device tensors: nsa int32[T,406], qsa float64[T,406], ps float32[T,406], and per-tree scalars"""
         T, A = self.T, nat.NUM_ACTIONS

@@ -165,8 +165,7 @@ class SelfPlayEngine:
         self.env.states(out=self.roots)
         self.arena.begin(self.roots, self.sims, self.flags)
         self.arena.select()
-        self.sims_completed = torch.zeros((), dtype=torch.int64, device=self.device)
-        self.moves_completed = torch.zeros((), dtype=torch.int64, device=self.device)
+        self._move_counters = torch.zeros(2, dtype=torch.int64, device=self.device)    # simulations, moves of the completed searches
         self._async = True
 
     def _assign_budgets(self, lanes):
@@ -214,6 +213,8 @@ class SelfPlayEngine:
             self._tick_tail(temp)
 
     def _tick_tail(self, temp):
+        if self.examples is None:
+            return self._tick_tail_fused(temp)
         st = self.arena.root_stats(want_arrays=False)
         fin = (st["sims_done"] >= self.sims) | (st["status"] != 0)
         probs, q = self.arena.policy(temp)
@@ -235,12 +236,36 @@ class SelfPlayEngine:
         self.env.reset(done8)
         self.arena.reset(done8)
         self.games_finished += done.sum()
-        self.sims_completed += torch.where(fin, st["sims_done"], torch.zeros_like(st["sims_done"])).sum()
-        self.moves_completed += fin.sum()
+        self._move_counters[0] += torch.where(fin, st["sims_done"], torch.zeros_like(st["sims_done"])).sum()
+        self._move_counters[1] += fin.sum()
         self._assign_budgets(fin)
         self.env.states(out=self.roots)
         self._fin8.copy_(fin)
         self.arena.begin(self.roots, self.sims, self.flags, self._fin8)
+
+    def _tick_tail_fused(self, temp):
+        """the same moves without materialising the policies (no examples are being recorded): spl_mcts_sample_moves draws every
+        finished lane's action from its visit counts on the device (Philox keyed by game / episode / ply) and counts the simulations"""
+        self.arena.sample_moves(temp, self.env.episodes, self.actions, self._fin8, self._move_counters)
+        fin = self._fin8.to(torch.bool)
+        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+        done = fin & (self.env.ended != 0).any(dim=1)
+        done8 = done.to(torch.uint8)
+        self.env.episodes += done.to(torch.int32)
+        self.env.reset(done8)
+        self.arena.reset(done8)
+        self.games_finished += done.sum()
+        self._assign_budgets(fin)
+        self.env.states(out=self.roots)
+        self.arena.begin(self.roots, self.sims, self.flags, self._fin8)
+
+    @property
+    def sims_completed(self):
+        return self._move_counters[0]
+
+    @property
+    def moves_completed(self):
+        return self._move_counters[1]
 
     def sims_in_flight(self):
         return self.arena.root_stats(want_arrays=False)["sims_done"].sum()

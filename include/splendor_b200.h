@@ -231,6 +231,14 @@ int  spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v,
                         uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
 /* getActionProb's tail: probs double[T][406], q double[T][n]; temp == 0 gives the one-hot of the FIRST most visited action */
 int  spl_mcts_policy(spl_mcts* m, double temp, double* probs, double* q, void* stream);
+/* Self-play with lanes that move on their own: for every tree whose budget is spent (simulations done >= budget, or a status bit
+ * set), getActionProb's tail and the caller's draw from it (Coach.py:75-86) in one launch, without materialising the 406
+ * probabilities: actions int16[T] = the action drawn with probability proportional to the (pruned, tempered) visit counts, -1 for
+ * a tree that is still searching; finished uint8[T]; counters (may be NULL) int64[2]: [0] += simulations of the finished trees,
+ * [1] += finished trees. The uniform comes from Philox keyed (seed, game, episode, root ply) like the environment's chance events:
+ * episodes uint32[T] = the lanes' episode counters (NULL: 0). temp == 0: the first most visited action. */
+int  spl_mcts_sample_moves(spl_mcts* m, double temp, const uint32_t* episodes, int16_t* actions, uint8_t* finished, long long* counters,
+                            void* stream);
 /* raw root statistics, any pointer may be NULL: nsa int32[T][406], qsa double[T][406] (-42 = unvisited), ps float[T][406],
  * info int32[T][16] = nodes, edges, root Ns, simulations done, network calls since reset, status bits | truncated searches << 8,
  *                     lossy resets * 65536 + cleanings, root Qs (float bits), then 4 floats (bits): the value vector the last

@@ -467,3 +467,47 @@ def test_selfplay_async_graph_replay_path():
     for i in range(0, T, 17):
         b = po.Board(n).set_state(boards[i])
         assert np.array_equal(b.valid_moves(0), valids[i].astype(bool))
+
+
+def test_sample_moves_follows_the_policy():
+    """spl_mcts_sample_moves = getActionProb's tail + the caller's np.random.choice (Coach.py:75-86) in one launch: over many
+    trees that hold the SAME search (same root, fixed network) but different game ids, the drawn actions follow the probabilities
+    spl_mcts_policy returns; unfinished trees give -1; temp 0 gives the most visited action; the counters add up; forced
+    playouts prune the same way"""
+    az = _azg()
+    n, T, sims = 2, 4096, 200
+    env = az.SplendorEnv(n, 1, seed=3)
+    env.reset(); env.rollout(20, rotate=True)
+    root = env.states()[0:1]
+    for forced in (0, 1):
+        ar = az.MCTSArena(n, T, node_cap=512, cpuct=1.5, fpu=0.1, seed=99)
+        roots = root.expand(T, -1, -1).contiguous()
+        simt = torch.full((T,), sims, dtype=torch.int32, device=ar.device)
+        simt[T // 2:] = sims + 50                                   # the second half will still be searching
+        flt = torch.full((T,), forced, dtype=torch.uint8, device=ar.device)
+        ar.begin(roots, simt, flt)
+        for _ in range(sims):
+            ar.wave(lambda s, v: ar.fixed_net(s, v))
+        ar.drain_nnet()
+        st = ar.root_stats(want_arrays=False)
+        assert int(st["sims_done"][: T // 2].min()) == sims
+        probs, _ = ar.policy(1.0)
+        counters = torch.zeros(2, dtype=torch.int64, device=ar.device)
+        episodes = torch.zeros(T, dtype=torch.int32, device=ar.device)
+        acts, fin = ar.sample_moves(1.0, episodes, counters=counters)
+        acts, fin = _np(acts).astype(np.int64), _np(fin).astype(bool)
+        assert fin[: T // 2].all() and not fin[T // 2:].any() and (acts[T // 2:] == -1).all()
+        assert [int(x) for x in counters.cpu()] == [sims * (T // 2), T // 2]
+        p = _np(probs[0])
+        assert (p[acts[: T // 2]] > 0).all()                        # only actions with weight are ever drawn
+        freq = np.bincount(acts[: T // 2], minlength=406) / (T // 2)
+        assert 0.5 * np.abs(freq - p).sum() < 0.06, 0.5 * np.abs(freq - p).sum()      # total variation, 2048 draws
+        a2, _ = ar.sample_moves(1.0, episodes)                      # same key -> same draws; another episode -> other draws
+        assert np.array_equal(_np(a2).astype(np.int64), acts)
+        a3, _ = ar.sample_moves(1.0, episodes + 1)
+        if p.max() < 0.8:                                           # (forced playouts can prune the policy down to one action)
+            assert (_np(a3).astype(np.int64)[: T // 2] != acts[: T // 2]).mean() > 0.2
+        a0, _ = ar.sample_moves(0.0, episodes)
+        nsa = _np(ar.root_stats()["nsa"][0])
+        if not forced:
+            assert (_np(a0).astype(np.int64)[: T // 2] == int(nsa.argmax())).all()
