@@ -1,16 +1,19 @@
 import sys, torch
 sys.path.insert(0, "/root/repo")
 import azg_b200 as azg
-n, T, sims = 2, 4096, 1600
+n = 2
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+sims = int(sys.argv[2]) if len(sys.argv) > 2 else 1600
+G = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 net = azg.FusedSplendorNNet(n, seed=1)
 cap = 8 * sims
-eng = azg.SelfPlayEngine(n, T, net, sims, seed=1, node_cap=cap, edge_cap=cap * 36, gc_reachable=True, graph_waves=128, max_levels=16, clean_every=0, tick_graph=True)
+eng = azg.SelfPlayEngine(n, T, net, sims, seed=1, node_cap=cap, edge_cap=cap * 36, gc_reachable=True, graph_waves=G, max_levels=16, clean_every=0, tick_graph=True)
 eng.env.rollout(24, rotate=True)
 eng.start_async()
-ticks_per_move = sims // 128
+ticks_per_move = max(1, sims // G)
 for mv in range(12):
     for _ in range(ticks_per_move):
-        eng.tick(128)
+        eng.tick(G)
     if mv % 4 == 3:
         st = eng.arena.root_stats(want_arrays=False)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -26,3 +29,10 @@ for _ in range(20):
     eng._tick_graph.replay()
 b.record(); torch.cuda.synchronize()
 print("tick tail graph replay ms", a.elapsed_time(b) / 20)
+
+# one graph replay of G waves
+a.record()
+for _ in range(5):
+    eng._graph.replay()
+b.record(); torch.cuda.synchronize()
+print("wave graph replay ms (%d waves)" % G, a.elapsed_time(b) / 5)
