@@ -59,6 +59,7 @@ class MCTSArena:
                            game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds), max_levels=int(max_levels))
         self.set_params()
         self.launches = 0
+        self.wave_nnet_launches = 3 if self.T <= 6144 else 4      # descent (+ rules step inside it up to 6144 trees), attach, network
         self._nn_pending, self._nn_dir = None, None
         self.reset()
 
@@ -138,7 +139,7 @@ class MCTSArena:
         self._nn_dir = dir_values
         nat.check(self._lib.spl_mcts_wave_nnet(self._m, C.c_void_p(net.blob_ptr), _ptr(pi), _ptr(v), _ptr(dir_values), _ptr(self.leaf_states),
                                                _ptr(self.leaf_valids), _ptr(self.leaf_flags), None, self._stream()))
-        self.launches += 4
+        self.launches += self.wave_nnet_launches
 
     def drain_nnet(self, dir_values=None):
         """after `wave_nnet`: back the pending network results up, so that the classic calls (select / expand / finish) can follow"""

@@ -344,7 +344,10 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     # kernels + the evaluator + expand; per tick / move the stats, policy, env step, resets, unpack and begin kernels
     per_wave = 3 * args.rounds + 1 + (1 if (args.fixed_net or args.nn_dtype == "fused") else 0)
     if args.async_moves:
-        own_launches_total = args.steps * ticks_per_step * (G * (per_wave - 1) + 8)     # expansion and descent share a launch
+        # per wave: descent (with the expansion, and the rules step up to 6144 trees), attach, network; per tick: sample_moves, env step,
+        # two resets, unpack, begin
+        in_wave = eng.arena.wave_nnet_launches if eng.overlap_nnet else per_wave - 1
+        own_launches_total = args.steps * ticks_per_step * (G * in_wave + 6)
     else:
         own_launches_total = args.steps * ((ticks_per_step * G + eng.extra_waves // max(1, W + args.steps)) * per_wave + 10)
 
@@ -436,7 +439,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     line["e2e"] = {"value": world * T * sims * ke / float(t.item()), "unit": UNIT_MCTS, "h2d_bytes_per_step": h2d // ke, "d2h_bytes_per_step": d2h // ke,
                    "call": "MCTSArena.get_action_prob_batch(host boards) -> host probs/q, then SplendorGame.getNextStateBatch(host boards, actions)",
-                   "steps": ke, "waves_per_move": (ar.launches - launches0) / 4.0 / ke,
+                   "steps": ke, "waves_per_move": (ar.launches - launches0) / float(ar.wave_nnet_launches if eng.overlap_nnet else 5) / ke,
                    "note": "lock-step: every wave lasts as long as the deepest descent of any tree and the call returns when the slowest tree "
                            "has spent its budget (its ~1600 sequential simulations bound the call from below)"}
     if world > 1:

@@ -220,7 +220,8 @@ int  spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double*
  * of a search: network -> expand_select -> network -> ...) */
 int  spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const double* dir_values, int8_t* leaf_states,
                             uint8_t* leaf_valids, uint8_t* leaf_flags, int32_t* counters, void* stream);
-/* The steady-state wave with the fused evaluator (spl_nnet_*) inside, four launches:
+/* The steady-state wave with the fused evaluator (spl_nnet_*) inside, three launches (four beyond 6144 trees, where the rules
+ * step is a kernel of its own):
  *     expansion of the previous wave's leaves from pi / v + next descent -> rules -> { attach  ||  network -> pi, v }
  * The network starts as soon as the child states exist (it reads them where the rules kernel left them) and runs on an
  * internal side stream next to the attach kernel; the call joins it back into `stream` (CUDA-graph capturable). pi float[T][406]
