@@ -475,7 +475,7 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     arena fits (tree pools scale with the budget), same kernels, same network"""
     n, T, sims = args.players, args.wide_trees, args.wide_sims
     net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
-    cap = 8 * sims
+    cap = 16 * sims     # short budgets: roomy pools are cheap (107 GB at 65,536 trees) and keep the cleaning off the path (+4 % measured)
     G = min(args.wide_tick_waves, args.graph_waves) if args.graph_waves > 0 else args.wide_tick_waves      # short budgets: look for finished lanes often
     eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
                              gc_reachable=args.gc == "reachable", graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds,

@@ -36,3 +36,12 @@ for _ in range(5):
     eng._graph.replay()
 b.record(); torch.cuda.synchronize()
 print("wave graph replay ms (%d waves)" % G, a.elapsed_time(b) / 5)
+# steady state, tick by tick: the waves and the move logic timed separately
+tw = tt = 0.0
+K = 40
+for _ in range(K):
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(); eng._run_waves(G); e1.record(); eng._tick_graph.replay(); e2.record()
+    torch.cuda.synchronize()
+    tw += e0.elapsed_time(e1); tt += e1.elapsed_time(e2)
+print("steady state per tick: waves %.3f ms (%.1f us per wave), move logic %.3f ms" % (tw / K, 1e3 * tw / K / G, tt / K))
