@@ -27,7 +27,7 @@ EXPORTS = [
     "spl_state_rows", "spl_state_bytes", "spl_lanes_padded", "spl_planes_bytes", "spl_mask_planes_bytes",
     "spl_pack", "spl_unpack", "spl_mask_unpack", "spl_reset_philox", "spl_reset_explicit", "spl_step", "spl_rollout",
     "spl_scores", "spl_symmetries",
-    "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
+    "spl_mcts_record_bytes", "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_set_episodes", "spl_mcts_pool_stats", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
     "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_wave_nnet", "spl_mcts_debug_profile", "spl_mcts_policy", "spl_mcts_sample_moves", "spl_mcts_root_stats", "spl_mcts_fixed_net",
     "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_nnet_debug_cta_times", "spl_umma_selftest",
 ]
@@ -121,9 +121,13 @@ def lib():
         L.spl_rollout.argtypes = [vp, C.POINTER(RolloutArgs), vp]
         L.spl_scores.argtypes = [vp, vp, ci, vp, vp, vp]
         L.spl_symmetries.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
-        L.spl_mcts_arena_bytes.argtypes = [ci, ci, ci, ci]
+        L.spl_mcts_record_bytes.argtypes = [ci, ci]
+        L.spl_mcts_record_bytes.restype = C.c_size_t
+        L.spl_mcts_arena_bytes.argtypes = [ci, ci, ci, C.c_size_t]
         L.spl_mcts_arena_bytes.restype = C.c_size_t
-        L.spl_mcts_create.argtypes = [vp, ci, ci, ci, vp, C.c_size_t, C.POINTER(vp)]
+        L.spl_mcts_create.argtypes = [vp, ci, ci, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]
+        L.spl_mcts_set_episodes.argtypes = [vp, vp]
+        L.spl_mcts_pool_stats.argtypes = [vp, vp, vp]
         L.spl_mcts_destroy.argtypes = [vp]
         L.spl_mcts_destroy.restype = None
         L.spl_mcts_set_params.argtypes = [vp, C.POINTER(MctsParams)]

@@ -24,7 +24,8 @@ struct spl_mcts {
     spl_ctx* ctx;
     MctsArena A;
     MctsSearchParams P;
-    int edge_reserve, gc_reachable, rounds, max_levels;
+    int gc_reachable, rounds, max_levels;
+    const uint32_t* episodes;    // the lanes' episode counters (device, may be NULL): part of the Philox key of the on-device Dirichlet sampler
     int rules_tpw;               // trees per warp of the rules kernel
     int pdl;                     // spl_mcts_wave_nnet: descent and network as programmatic dependent launches on one stream
     int fuse_rules;              // spl_mcts_wave_nnet: rules step inside the descent kernel (no launch boundary) instead of mcts_rules_kernel
@@ -58,14 +59,14 @@ __device__ __forceinline__ WarpScratch warp_scratch(int warp) {
 template <int N>
 __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSearchParams P, const int8_t* roots, const int32_t* sims,
                                                              const uint8_t* move_flags, const uint8_t* tree_select, const double* dir,
-                                                             int edge_reserve, int gc_reachable) {
+                                                             const uint32_t* episodes, int gc_reachable) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);
     if (t >= A.n_trees) return;
     if (tree_select && !tree_select[t]) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
-    mcts_begin_tree<N>(w, A, t, P, roots + (size_t)t * MctsLay<N>::S, sims[t], move_flags ? (uint32_t)move_flags[t] : 0u, edge_reserve,
-                       gc_reachable, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.st, sc.words, sc.dwords);
+    mcts_begin_tree<N>(w, A, t, P, roots + (size_t)t * MctsLay<N>::S, sims[t], move_flags ? (uint32_t)move_flags[t] : 0u, gc_reachable,
+                       dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, episodes ? episodes[t] : 0u, sc.st, sc.words, sc.dwords);
 }
 
 template <int N>
@@ -98,14 +99,15 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     const int t0 = (blockIdx.x * RW + warp) * TPW, t = t0 + lane;
     int8_t* wsm = tile_smem + (size_t)warp * TPW * STRIDE;
     bool pending = false;
-    int parent = 0, action = 0;
+    uint32_t parent = 0u;
+    int action = 0;
     if (lane < TPW && t < A.n_trees) {
         const MctsTree* T = A.trees + t;
         const int pe = T->pend_edge;
-        if (pe >= 0 && T->leaf < 0) {
+        if (pe >= 0 && T->leaf == 0u) {
             pending = true;
             parent = T->pend_parent;
-            action = (int)A.edges[(size_t)t * A.ecap + pe].action;
+            action = (int)mcts_edges(A, parent, pe >> 16).ca[pe & 0xFFFF].action;
         }
     }
     const uint32_t pmask = __ballot_sync(0xffffffffu, pending);
@@ -113,9 +115,9 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     if (t0 < A.n_trees) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
 #pragma unroll
     for (int j = 0; j < TPW; j++) {
-        const int par = __shfl_sync(0xffffffffu, parent, j);
+        const uint32_t par = __shfl_sync(0xffffffffu, parent, j);
         if ((pmask >> j) & 1u) {
-            const int8_t* src = A.states + ((size_t)(t0 + j) * A.cap + par) * A.sp;
+            const int8_t* src = mcts_state(A, par);
             for (int i = lane; i < CH; i += 32) {
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + j * STRIDE + 16 * i);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
@@ -223,9 +225,9 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     constexpr int CH = MctsLay<N>::SP / 16;
     const MctsTree* T = A.trees + t;
     const int pe = T->pend_edge;
-    if (pe < 0 || T->leaf >= 0) return;
-    const int action = (int)A.edges[(size_t)t * A.ecap + pe].action;
-    const int8_t* src = A.states + ((size_t)t * A.cap + T->pend_parent) * A.sp;
+    if (pe < 0 || T->leaf != 0u) return;
+    const int action = (int)mcts_edges(A, T->pend_parent, pe >> 16).ca[pe & 0xFFFF].action;
+    const int8_t* src = mcts_state(A, T->pend_parent);
     for (int i = lane; i < CH; i += 32) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + 16 * i);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
@@ -345,11 +347,20 @@ __global__ void __launch_bounds__(MW * 32) mcts_stats_kernel(MctsArena A, int32_
                          ps ? ps + (size_t)t * SPL_ACTIONS : nullptr, info ? info + (size_t)t * 16 : nullptr);
 }
 
-__global__ void __launch_bounds__(MW * 32) mcts_clean_kernel(MctsArena A, int max_nodes, int max_edges, int gc_reachable) {
+__global__ void __launch_bounds__(MW * 32) mcts_clean_kernel(MctsArena A, int max_nodes, int gc_reachable) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
-    mcts_clean_tree(w, A, t, max_nodes, max_edges, gc_reachable);
+    mcts_clean_tree(w, A, t, max_nodes, gc_reachable);
+}
+
+// every page of the pool into the free ring (page 0 is never handed out: record offset 0 means "none")
+__global__ void mcts_pool_init_kernel(MctsArena A) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.n_pool_pages) A.fq_slots[i] = i + 1u < A.n_pool_pages ? i + 1u : 0u;
+    if (i == 0u) {
+        A.fq_ctl[0] = 0; A.fq_ctl[1] = (int32_t)A.n_pool_pages - 1; A.fq_ctl[2] = (int32_t)A.n_pool_pages - 1; A.fq_ctl[3] = (int32_t)A.n_pool_pages - 1;
+    }
 }
 
 __global__ void __launch_bounds__(MW * 32) mcts_reset_kernel(MctsArena A, const uint8_t* tree_select) {
@@ -357,6 +368,10 @@ __global__ void __launch_bounds__(MW * 32) mcts_reset_kernel(MctsArena A, const 
     if (t >= A.n_trees) return;
     if (tree_select && !tree_select[t]) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
+    if (!tree_select) {   // a full reset re-fills the free ring afterwards (mcts_pool_init_kernel): nothing to push page by page
+        if (w.lane == 0) A.trees[t].n_pages = 0;
+        __syncwarp();
+    }
     mcts_clear_tree(w, A, t);
     if (w.lane == 0 && !tree_select) { A.trees[t].nn_calls = 0; A.trees[t].resets = 0; A.trees[t].compactions = 0; A.trees[t].truncated = 0; }   // a full reset also clears the statistics
 }
@@ -377,19 +392,30 @@ __global__ void __launch_bounds__(MW * 32) mcts_fixed_net_kernel(const int8_t* s
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ArenaPlan {
-    int sp, hcap, max_depth;
-    size_t off_states, off_nodes, off_edges, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, off_lsrc, total;
+    int sp, hcap, max_depth, max_pages;
+    uint32_t n_pool_pages;
+    size_t off_pool, off_fq, off_ctl, off_tpages, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, off_lsrc, total;
 };
-static ArenaPlan plan_arena(int n, int T, int cap, int ecap) {
+static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes) {
     ArenaPlan p;
     p.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
     p.hcap = 64;
-    while (p.hcap < 2 * cap) p.hcap *= 2;
+    while (p.hcap < 2 * node_limit) p.hcap *= 2;
     p.max_depth = 62 * n + 8;
+    const size_t page_bytes = (size_t)MCTS_PAGE_UNITS * MCTS_UNIT;
+    // at least one page per tree in flight plus the reserved page 0
+    size_t pages = (pool_bytes + page_bytes - 1) / page_bytes;
+    if (pages < (size_t)T + 8) pages = (size_t)T + 8;
+    p.n_pool_pages = (uint32_t)pages;
+    // per-tree page list: room for node_limit records of 40 edges, twice (the copy of a compaction)
+    size_t half = ((size_t)node_limit * (size_t)(32 + p.sp + 24 * 40) + page_bytes - 1) / page_bytes + 2;
+    if (half > pages) half = pages;
+    p.max_pages = (int)(2 * half);
     size_t o = 0;
-    p.off_states = o; o = align_up(o + (size_t)T * cap * p.sp, 256);
-    p.off_nodes = o;  o = align_up(o + (size_t)T * cap * sizeof(MctsNode), 256);
-    p.off_edges = o;  o = align_up(o + (size_t)T * ecap * sizeof(MctsEdge), 256);
+    p.off_pool = o;   o = align_up(o + pages * page_bytes, 256);
+    p.off_fq = o;     o = align_up(o + pages * 4, 256);
+    p.off_ctl = o;    o = align_up(o + 64, 256);
+    p.off_tpages = o; o = align_up(o + (size_t)T * p.max_pages * 4, 256);
     p.off_htab = o;   o = align_up(o + (size_t)T * p.hcap * 4, 256);
     p.off_trees = o;  o = align_up(o + (size_t)T * sizeof(MctsTree), 256);
     p.off_path = o;   o = align_up(o + (size_t)T * p.max_depth * 8, 256);
@@ -410,25 +436,34 @@ static ArenaPlan plan_arena(int n, int T, int cap, int ecap) {
 
 extern "C" {
 
-size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_cap, int edge_cap) {
-    if (n_players < 2 || n_players > 4 || n_trees <= 0 || node_cap <= 0 || edge_cap <= 0) return 0;
-    return plan_arena(n_players, n_trees, node_cap, edge_cap).total;
+size_t spl_mcts_record_bytes(int n_players, int n_edges) {
+    if (n_players < 2 || n_players > 4 || n_edges < 0) return 0;
+    const int sp = (7 * (32 + 10 * n_players + n_players * n_players) + 15) / 16 * 16;
+    return (size_t)(32 + sp + 24 * n_edges + 31) / 32 * 32;
 }
 
-int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void* arena, size_t arena_bytes, spl_mcts** out) {
-    if (!ctx || !out || !arena || n_trees <= 0 || node_cap < 4 || edge_cap < 4) return spl_fail_(SPL_E_ARG, "spl_mcts_create: bad argument");
-    if (node_cap > (1 << 24)) return spl_fail_(SPL_E_ARG, "spl_mcts_create: node_cap too large");
+size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes) {
+    if (n_players < 2 || n_players > 4 || n_trees <= 0 || node_limit <= 0) return 0;
+    return plan_arena(n_players, n_trees, node_limit, pool_bytes).total;
+}
+
+int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, void* arena, size_t arena_bytes, spl_mcts** out) {
+    if (!ctx || !out || !arena || n_trees <= 0 || node_limit < 4) return spl_fail_(SPL_E_ARG, "spl_mcts_create: bad argument");
+    if (node_limit > (1 << 24)) return spl_fail_(SPL_E_ARG, "spl_mcts_create: node_limit too large");
     if (((uintptr_t)arena & 255u) != 0) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena must be 256-byte aligned");
-    const ArenaPlan p = plan_arena(ctx->n, n_trees, node_cap, edge_cap);
+    const ArenaPlan p = plan_arena(ctx->n, n_trees, node_limit, pool_bytes);
     if (arena_bytes < p.total) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena smaller than spl_mcts_arena_bytes");
-    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsEdge) == 32 && sizeof(MctsTree) == 96, "arena record sizes");
+    if ((size_t)p.n_pool_pages * MCTS_PAGE_UNITS > 0xFFFFFFFFull) return spl_fail_(SPL_E_ARG, "spl_mcts_create: pool larger than 128 GB");
+    static_assert(sizeof(MctsNode) == 32 && sizeof(MctsPN) == 8 && sizeof(MctsCA) == 8 && sizeof(MctsTree) == 192, "arena record sizes");
     spl_mcts* m = new spl_mcts;
     m->ctx = ctx;
     char* base = (char*)arena;
-    m->A.n_trees = n_trees; m->A.cap = node_cap; m->A.ecap = edge_cap; m->A.hcap = p.hcap; m->A.sp = p.sp; m->A.max_depth = p.max_depth;
-    m->A.states = (int8_t*)(base + p.off_states);
-    m->A.nodes = (MctsNode*)(base + p.off_nodes);
-    m->A.edges = (MctsEdge*)(base + p.off_edges);
+    m->A.n_trees = n_trees; m->A.node_limit = node_limit; m->A.hcap = p.hcap; m->A.sp = p.sp; m->A.max_depth = p.max_depth;
+    m->A.max_pages = p.max_pages; m->A.n_pool_pages = p.n_pool_pages;
+    m->A.pool = (uint8_t*)(base + p.off_pool);
+    m->A.fq_slots = (uint32_t*)(base + p.off_fq);
+    m->A.fq_ctl = (int32_t*)(base + p.off_ctl);
+    m->A.tree_pages = (uint32_t*)(base + p.off_tpages);
     m->A.htab = (uint32_t*)(base + p.off_htab);
     m->A.trees = (MctsTree*)(base + p.off_trees);
     m->A.path = (uint32_t*)(base + p.off_path);
@@ -440,7 +475,8 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
     m->A.prof = nullptr;
     m->P.cpuct = 1.0; m->P.fpu = 0.0; m->P.temperature0 = 1.0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules = ctx->rules;
-    m->edge_reserve = 32; m->gc_reachable = 0; m->rounds = 1; m->max_levels = 1 << 20;
+    m->gc_reachable = 0; m->rounds = 1; m->max_levels = 1 << 20;
+    m->episodes = nullptr;
     m->rules_tpw = 8;
     if (const char* e = getenv("SPL_MCTS_RULES_TPW")) {   // tuning hook (4, 8 or 16)
         const int v = atoi(e);
@@ -461,7 +497,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void*
         return spl_fail_(SPL_E_CUDA, "spl_mcts_create: stream / event creation failed");
     }
     *out = m;
-    return SPL_OK;
+    return SPL_OK;   // the caller resets the arena (spl_mcts_reset with tree_select == NULL) before the first begin
 }
 
 void spl_mcts_destroy(spl_mcts* m) {
@@ -474,10 +510,10 @@ void spl_mcts_destroy(spl_mcts* m) {
 
 int spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p) {
     if (!m || !p) return spl_fail_(SPL_E_ARG, "spl_mcts_set_params: null argument");
-    if (!(p->temperature0 > 0.0) || !(p->dirichlet_alpha > 0.0) || p->edge_reserve < 1) return spl_fail_(SPL_E_ARG, "spl_mcts_set_params: bad value");
+    if (!(p->temperature0 > 0.0) || !(p->dirichlet_alpha > 0.0)) return spl_fail_(SPL_E_ARG, "spl_mcts_set_params: bad value");
     m->P.cpuct = p->cpuct; m->P.fpu = p->fpu; m->P.temperature0 = p->temperature0; m->P.dirichlet_alpha = p->dirichlet_alpha;
     m->P.seed = p->seed; m->P.game_base = p->game_base;
-    m->edge_reserve = p->edge_reserve; m->gc_reachable = p->gc_reachable ? 1 : 0;
+    m->gc_reachable = p->gc_reachable ? 1 : 0;
     m->rounds = p->rounds < 1 ? 1 : (p->rounds > 8 ? 8 : p->rounds);
     m->max_levels = p->max_levels < 1 ? (1 << 20) : p->max_levels;
     return SPL_OK;
@@ -486,6 +522,7 @@ int spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p) {
 int spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream) {
     ENTER_M(m);
     mcts_reset_kernel<<<grid, MW * 32, 0, st>>>(m->A, tree_select);
+    if (!tree_select) mcts_pool_init_kernel<<<(m->A.n_pool_pages + 255) / 256, 256, 0, st>>>(m->A);
     CU(cudaGetLastError());
     return SPL_OK;
 }
@@ -493,8 +530,7 @@ int spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream) {
 int spl_mcts_clean(spl_mcts* m, int fill_percent, void* stream) {
     ENTER_M(m);
     if (fill_percent < 0 || fill_percent > 100) return spl_fail_(SPL_E_ARG, "spl_mcts_clean: bad argument");
-    mcts_clean_kernel<<<grid, MW * 32, 0, st>>>(m->A, (int)((long long)m->A.cap * fill_percent / 100), (int)((long long)m->A.ecap * fill_percent / 100),
-                                                m->gc_reachable);
+    mcts_clean_kernel<<<grid, MW * 32, 0, st>>>(m->A, (int)((long long)m->A.node_limit * fill_percent / 100), m->gc_reachable);
     CU(cudaGetLastError());
     return SPL_OK;
 }
@@ -504,7 +540,7 @@ int spl_mcts_begin(spl_mcts* m, const int8_t* roots, const int32_t* sims, const 
     ENTER_M(m);
     if (!roots || !sims) return spl_fail_(SPL_E_ARG, "spl_mcts_begin: bad argument");
     m->P.rules = m->ctx->rules;
-    DISPATCH_N(m->ctx->n, mcts_begin_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, roots, sims, move_flags, tree_select, dir_values, m->edge_reserve, m->gc_reachable));
+    DISPATCH_N(m->ctx->n, mcts_begin_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, roots, sims, move_flags, tree_select, dir_values, m->episodes, m->gc_reachable));
     CU(cudaGetLastError());
     return SPL_OK;
 }
@@ -622,6 +658,23 @@ int spl_mcts_root_stats(spl_mcts* m, int32_t* nsa, double* qsa, float* ps, int32
     ENTER_M(m);
     mcts_stats_kernel<<<grid, MW * 32, 0, st>>>(m->A, nsa, qsa, ps, info);
     CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_mcts_set_episodes(spl_mcts* m, const uint32_t* episodes) {
+    if (!m) return spl_fail_(SPL_E_ARG, "null mcts handle");
+    m->episodes = episodes;
+    return SPL_OK;
+}
+
+int spl_mcts_pool_stats(spl_mcts* m, int32_t* out4, void* stream) {   /* host buffer: pages in the pool, free now, fewest free so far, bytes per page */
+    ENTER_M(m);
+    (void)grid;
+    if (!out4) return spl_fail_(SPL_E_ARG, "spl_mcts_pool_stats: bad argument");
+    int32_t ctl[4];
+    CU(cudaMemcpyAsync(ctl, m->A.fq_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out4[0] = (int32_t)m->A.n_pool_pages - 1; out4[1] = ctl[2]; out4[2] = ctl[3]; out4[3] = (int32_t)(MCTS_PAGE_UNITS * MCTS_UNIT);
     return SPL_OK;
 }
 

@@ -12,10 +12,13 @@
 //   mcts_policy_tree   <- getActionProb's tail :61-97 (counts, policy-target pruning, temperature)
 //
 // One tree = one game lane = one warp. The reference's `nodes_data` dictionary (exact state bytes -> node, a DAG with
-// transpositions that persists across moves) becomes a per-tree node pool + open-addressing hash table keyed by a
-// 64-bit state hash with a full-state compare. Nodes are either TERMINAL (Es stored), NEEDS_NN (legal edges allocated,
-// waiting for the network) or EXPANDED. Edges are sparse (only legal actions, in action order) and cache the child node
-// index, so an inner traversal touches no rules code at all.
+// transpositions that persists across moves) becomes a per-tree open-addressing hash table (64-bit state hash + full-state
+// compare) over variable-size node RECORDS that all trees allocate from ONE shared pool of 32 KB pages: a tree holds what
+// it needs at the moment (a few hundred nodes after a card was revealed, tens of thousands in a long line without reveals)
+// instead of a worst-case slab. A record = header + the reference's state bytes + the node's sparse edges (legal actions
+// only, in action order, structure-of-arrays: Q[k] | {P, N}[k] | {child, action, child's edge count}[k]), so one pointer
+// names a node and its header and edges arrive in one round trip. Nodes are TERMINAL (Es stored), NEEDS_NN (edges
+// allocated, waiting for the network) or EXPANDED. An inner traversal touches no rules code at all.
 //
 // Numerics follow the reference exactly: Ps float32, Qsa float64 running mean, Qs float32, Nsa/Ns integers, the -42
 // "unvisited" sentinel, strict > in the arg-max (lowest action wins ties), forced-playout early return. All
@@ -68,6 +71,16 @@ struct MctsWarp {
         return v;
     }
     __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ int scan_excl(int v, int& total) const {   // exclusive prefix sum over the lanes
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        return incl - v;
+    }
     // arg-max, lowest index wins ties; idx < 0 = none. Three warp reductions (REDUX) on an order-preserving integer image of the
     // double instead of five shuffle rounds: max of the high words, max of the low words among those, min index among those.
     // u + 0.0 maps -0.0 to +0.0 so that equal doubles have equal images (no NaNs occur).
@@ -99,61 +112,75 @@ struct MctsWarp {
     uint64_t sum64(uint64_t v) const { return v; }
     double sumd_tree(double v) const { return v; }
     int shfl(int v, int) const { return v; }
+    int scan_excl(int v, int& total) const { total = v; return 0; }
     void best(double&, int&) const {}
     void sqrt2(double a, double b, double& ra, double& rb) const { ra = MC_DSQRT(a); rb = MC_DSQRT(b); }
 };
 #endif
+
 
 // ------------------------------------------------------------------------------------------
 // arena layout (all in caller-owned HBM)
 // ------------------------------------------------------------------------------------------
 enum { MCTS_NODE_TERMINAL = 1, MCTS_NODE_NEEDS_NN = 2, MCTS_NODE_EXPANDED = 3 };
 enum { MCTS_F_FORCED = 1u, MCTS_F_NOISE = 2u };                       // per-move flags (getActionProb :54-58)
-enum { MCTS_S_OVERFLOW_NODES = 1u, MCTS_S_OVERFLOW_EDGES = 2u, MCTS_S_PROTOCOL = 4u };   // sticky status bits
+enum { MCTS_S_OVERFLOW_NODES = 1u, MCTS_S_OVERFLOW_POOL = 2u, MCTS_S_PROTOCOL = 4u };   // sticky status bits
 
-struct MctsNode {   // 32 B
+#define MCTS_UNIT 32u            // the pool is addressed in 32-byte units: a 32-bit record offset spans 128 GB
+#define MCTS_PAGE_UNITS 1024u    // 32 KB pages; the largest record (4 players, 406 edges: 10.4 KB) fits
+
+struct MctsNode {   // 32 B record header
     uint64_t hash;
     uint8_t ply, kind;
     uint16_t n_edges;
-    uint32_t edge_off;
+    uint32_t fwd;   // 0 outside a compaction; during one: the record's new offset (old copy) / the next record of the lane's chain (new copy)
     union {
-        struct { int32_t Ns; float Qs; uint32_t pad[2]; } x;   // EXPANDED / NEEDS_NN
-        float es[4];                                          // TERMINAL: getGameEnded vector
+        struct { int32_t Ns; float Qs; uint32_t hint; uint32_t pad; } x;   // EXPANDED / NEEDS_NN; hint: see mcts_descend_tree
+        float es[4];                                                       // TERMINAL: getGameEnded vector
     } u;
 };
-struct MctsEdge {   // 32 B
+struct MctsPN { float P; int32_t N; };                                     // Ps[a], Nsa
+struct MctsCA { uint32_t child; uint16_t action; uint16_t child_ne; };     // child record (0 = not linked yet), action, the child's edge count
+struct MctsEdgeV {   // one edge in registers
     double Q;        // Qsa (float64, -42 = unvisited)
-    float P;         // Ps[a]
-    int32_t N;       // Nsa
-    uint32_t child;  // node index + 1 (0 = not linked yet)
-    uint16_t action;
-    uint16_t child_ne;    // the child's edge count and first edge, copied here when the edge is linked: the descent then
-    uint32_t child_eoff;  // fetches the child's header and its edges in ONE round trip instead of two dependent ones
-    uint32_t pad;
+    float P;
+    int32_t N;
+    uint32_t child;
+    uint16_t action, child_ne;
 };
-struct MctsTree {   // 96 B
-    int32_t n_nodes, n_edges, root, leaf;
+struct MctsTree {   // 192 B
+    int32_t n_nodes, n_edges;          // records / edges this tree holds
+    uint32_t root, leaf;               // record offsets, 0 = none
     int32_t sims_done, sims_target, path_len;
     uint32_t flags, status;
     int32_t nn_calls, resets, compactions;
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
-    int32_t truncated; // searches cut short because a pool filled up mid-move (the next begin makes room again)
+    int32_t truncated; // searches cut short because the tree hit its node limit or the pool ran dry mid-move
     int32_t depth_sum; // sum of path lengths of the simulations since the last reset (diagnostics)
     // state of the simulation in flight (it survives between the kernels of a wave):
-    int32_t cur;         // >= 0: continue the descent at this node with path_len edges already recorded; -1: start at the root
-    int32_t pend_edge;   // >= 0: the descent stopped at this (absolute) edge, whose child state is being computed / attached
-    int32_t pend_parent; // node index of that edge's parent
-    int32_t spec_hits;   // diagnostics: levels of the descents that started from the early-fetched child (see mcts_descend_tree)
-    int32_t pad[2];
+    uint32_t cur;         // != 0: continue the descent at this node with path_len edges already recorded; 0: start at the root
+    int32_t pend_edge;    // >= 0: the descent stopped at this edge of pend_parent (position | edge count << 16), whose child state is being computed / attached
+    uint32_t pend_parent;
+    int32_t spec_hits;    // diagnostics: levels of the descents that started from the early-fetched child (see mcts_descend_tree)
+    // storage
+    int32_t n_pages;      // pages owned: tree_pages[t][0 .. n_pages)
+    uint32_t bump, page_end;   // next free unit / end of the page being filled
+    int32_t n_dropped;    // nodes an exact cleaning dropped since the last reset: n_nodes + n_dropped = size of the reference's dictionary
+    uint32_t episode;     // the lane's episode counter at the last begin (Philox key of the on-device Dirichlet sampler)
+    uint8_t deck[15];     // the deck bitmasks (rows 26 / 28 / 30, five colours each) every node of a homogeneous tree carries
+    uint8_t hetero;       // 1: nodes with different decks may be present (roots that do not follow each other in one game)
+    int32_t pad[17];
 };
 struct MctsArena {
-    int n_trees, cap, ecap, hcap, sp, max_depth;
-    int8_t* states;    // [T][cap][sp]   node states, the reference's int8[R,7] bytes + zero padding to 16
-    MctsNode* nodes;   // [T][cap]
-    MctsEdge* edges;   // [T][ecap]
-    uint32_t* htab;    // [T][hcap]      node index + 1, linear probing
-    MctsTree* trees;   // [T]
-    uint32_t* path;    // [T][max_depth][2]  (node, absolute edge index) of the current simulation
+    int n_trees, node_limit, hcap, sp, max_depth, max_pages;
+    uint32_t n_pool_pages;
+    uint8_t* pool;          // [n_pool_pages][32 KB]   node records of all trees (page 0 is never handed out: offset 0 = none)
+    uint32_t* fq_slots;     // [n_pool_pages]          ring of free pages (0 = empty slot)
+    int32_t* fq_ctl;        // [0] head ticket, [1] tail ticket, [2] free pages, [3] fewest free pages seen (diagnostics)
+    uint32_t* tree_pages;   // [T][max_pages]          pages of every tree; the upper half is room for the copy of a compaction
+    uint32_t* htab;         // [T][hcap]               record offsets, linear probing
+    MctsTree* trees;        // [T]
+    uint32_t* path;         // [T][max_depth][2]  (record, edge position | edge count << 16) of the current simulation
     // staging between the rules kernel and the attach kernel (the child state of every tree's pending edge)
     int8_t* stage_state;   // [T][sp]
     uint32_t* stage_mask;  // [13][T]
@@ -186,6 +213,37 @@ struct AosAcc {   // the reference's own array order: cell (row, col) = byte 7*r
     SPL_M int get(int row, int col) const { return p[7 * row + col]; }
     SPL_M void set(int row, int col, int v) { p[7 * row + col] = (int8_t)v; }
 };
+
+// record accessors: [MctsNode 32][state sp][Q double[k]][MctsPN[k]][MctsCA[k]], padded to a multiple of 32 bytes
+SPL_D uint8_t* mcts_ptr(const MctsArena& A, uint32_t rec) { return A.pool + (size_t)rec * MCTS_UNIT; }
+SPL_D MctsNode* mcts_node(const MctsArena& A, uint32_t rec) { return reinterpret_cast<MctsNode*>(mcts_ptr(A, rec)); }
+SPL_D int8_t* mcts_state(const MctsArena& A, uint32_t rec) { return reinterpret_cast<int8_t*>(mcts_ptr(A, rec) + 32); }
+SPL_D uint32_t mcts_rec_units(const MctsArena& A, int k) { return (uint32_t)(32 + A.sp + 24 * k + 31) / MCTS_UNIT; }
+struct MctsEdges {   // the three edge arrays of one record
+    double* Q;
+    MctsPN* pn;
+    MctsCA* ca;
+    SPL_M MctsEdgeV load(int i) const {
+        MctsEdgeV e;
+        const MctsPN p = pn[i];
+        const MctsCA c = ca[i];
+        e.Q = Q[i]; e.P = p.P; e.N = p.N; e.child = c.child; e.action = c.action; e.child_ne = c.child_ne;
+        return e;
+    }
+};
+SPL_D MctsEdges mcts_edges(const MctsArena& A, uint32_t rec, int k) {
+    uint8_t* b = mcts_ptr(A, rec) + 32 + A.sp;
+    MctsEdges e;
+    e.Q = reinterpret_cast<double*>(b);
+    e.pn = reinterpret_cast<MctsPN*>(b + 8 * (size_t)k);
+    e.ca = reinterpret_cast<MctsCA*>(b + 16 * (size_t)k);
+    return e;
+}
+SPL_D MctsEdgeV mcts_edge_none() {
+    MctsEdgeV e;
+    e.Q = MCTS_UNVISITED; e.P = 0.f; e.N = 0; e.child = 0u; e.action = 0; e.child_ne = 0;
+    return e;
+}
 
 SPL_D uint64_t mcts_mix64(uint64_t x) {
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
@@ -221,71 +279,136 @@ SPL_D bool mcts_equal16(const W& w, const void* a, const void* b, int bytes) {
     return w.ballot(diff) == 0u;
 }
 
-// nodes_data.get(s) :120
+// ------------------------------------------------------------------------------------------
+// the shared page pool: a ring of free pages with tickets. A pop takes a ticket and then the page in that slot (the push
+// that owns the slot may still be in flight: the pop waits for it); a push fills slots first and publishes the count last.
+// ------------------------------------------------------------------------------------------
+SPL_D uint32_t mcts_page_pop(const MctsArena& A) {   // one thread; 0 = the pool is dry
+#ifdef __CUDACC__
+    const int a = atomicSub(&A.fq_ctl[2], 1);
+    if (a <= 0) { atomicAdd(&A.fq_ctl[2], 1); return 0u; }
+    atomicMin(&A.fq_ctl[3], a - 1);
+    const uint32_t ticket = atomicAdd(reinterpret_cast<unsigned int*>(&A.fq_ctl[0]), 1u);
+    unsigned int* slot = A.fq_slots + ticket % A.n_pool_pages;
+    uint32_t p;
+    while ((p = atomicExch(slot, 0u)) == 0u) {}
+    return p;
+#else
+    if (A.fq_ctl[2] <= 0) return 0u;
+    A.fq_ctl[2] -= 1;
+    if (A.fq_ctl[2] < A.fq_ctl[3]) A.fq_ctl[3] = A.fq_ctl[2];
+    const uint32_t ticket = (uint32_t)A.fq_ctl[0]++;
+    uint32_t* slot = A.fq_slots + ticket % A.n_pool_pages;
+    const uint32_t p = *slot;
+    *slot = 0u;
+    return p;
+#endif
+}
 template <class W>
-SPL_D int mcts_lookup(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h) {
+SPL_D void mcts_pages_push(const W& w, const MctsArena& A, const uint32_t* pages, int n) {   // whole warp
+    if (n <= 0) return;
+    uint32_t base = 0u;
+#ifdef __CUDACC__
+    if (w.lane == 0) base = atomicAdd(reinterpret_cast<unsigned int*>(&A.fq_ctl[1]), (unsigned int)n);
+    base = (uint32_t)w.shfl((int)base, 0);
+    for (int i = w.lane; i < n; i += W::W) atomicExch(A.fq_slots + (base + (uint32_t)i) % A.n_pool_pages, pages[i]);
+    __threadfence();
+    w.sync();
+    if (w.lane == 0) atomicAdd(&A.fq_ctl[2], n);
+#else
+    base = (uint32_t)A.fq_ctl[1];
+    A.fq_ctl[1] += n;
+    for (int i = 0; i < n; i++) A.fq_slots[(base + (uint32_t)i) % A.n_pool_pages] = pages[i];
+    A.fq_ctl[2] += n;
+#endif
+    w.sync();
+}
+
+// room for a record of `units` in tree t (lane 0 allocates, every lane gets the offset); 0 = no room (status bit set).
+// Pages beyond max_pages / 2 are only handed to the copy of a compaction (`for_copy`).
+template <class W>
+SPL_D uint32_t mcts_alloc(const W& w, const MctsArena& A, int t, uint32_t units, bool for_copy = false) {
+    MctsTree* T = A.trees + t;
+    uint32_t off = 0u;
+    if (w.lane == 0) {
+        uint32_t bump = T->bump;
+        if (bump == 0u || bump + units > T->page_end) {
+            bump = 0u;
+            if (T->n_pages < (for_copy ? A.max_pages : A.max_pages / 2)) {
+                const uint32_t p = mcts_page_pop(A);
+                if (p) {
+                    A.tree_pages[(size_t)t * A.max_pages + T->n_pages] = p;
+                    T->n_pages += 1;
+                    bump = p * MCTS_PAGE_UNITS;
+                    T->page_end = bump + MCTS_PAGE_UNITS;
+                }
+            }
+        }
+        if (bump) { off = bump; T->bump = bump + units; }
+        else if (!for_copy) T->status |= MCTS_S_OVERFLOW_POOL;
+    }
+    off = (uint32_t)w.shfl((int)off, 0);
+    return off;
+}
+
+// nodes_data.get(s) :120 -> record offset or 0
+template <class W>
+SPL_D uint32_t mcts_lookup(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h) {
     const uint32_t* tab = A.htab + (size_t)t * A.hcap;
-    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
     uint32_t slot = (uint32_t)h & (uint32_t)(A.hcap - 1);
     for (;;) {
         const uint32_t e = tab[slot];
-        if (e == 0u) return -1;
-        const int idx = (int)e - 1;
-        if (nodes[idx].hash == h && mcts_equal16(w, A.states + ((size_t)t * A.cap + idx) * A.sp, st, A.sp)) return idx;
+        if (e == 0u) return 0u;
+        if (mcts_node(A, e)->hash == h && mcts_equal16(w, mcts_state(A, e), st, A.sp)) return e;
         slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
     }
 }
 
 template <class W>
-SPL_D void mcts_table_insert(const W& w, const MctsArena& A, int t, int idx, uint64_t h) {
+SPL_D void mcts_table_insert(const W& w, const MctsArena& A, int t, uint32_t rec, uint64_t h) {
     if (w.lane == 0) {
         uint32_t* tab = A.htab + (size_t)t * A.hcap;
         uint32_t slot = (uint32_t)h & (uint32_t)(A.hcap - 1);
         while (tab[slot] != 0u) slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
-        tab[slot] = (uint32_t)idx + 1u;
+        tab[slot] = rec;
     }
     w.sync();
 }
 
 // New node for the state `st` (sp bytes, zero padded) whose end-of-game vector / legal mask are already known:
 // stores the bytes, allocates one edge per legal action (in action order), links it into the hash table.
-// m: the 13 mask words at m[i * mstride]; es: N floats (used when ended). Returns the node index or -1 on pool overflow.
+// m: the 13 mask words at m[i * mstride]; es: N floats (used when ended). Returns the record or 0 (no room: status bit set).
 template <int N, class W>
-SPL_D int mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h, bool ended, const float* es,
-                          const uint32_t* m, int mstride) {
+SPL_D uint32_t mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h, bool ended, const float* es,
+                               const uint32_t* m, int mstride) {
     MctsTree* T = A.trees + t;
-    const int idx = T->n_nodes;
-    if (idx >= A.cap) {
+    if (T->n_nodes >= A.node_limit) {
         if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_NODES;
         w.sync();
-        return -1;
+        return 0u;
     }
     int k = 0;
     if (!ended)
         for (int i = 0; i < SPL_MASK_WORDS; i++) k += SPL_POPC(m[i * mstride]);
-    const int e0 = T->n_edges;
-    if (!ended && e0 + k > A.ecap) {
-        if (w.lane == 0) T->status |= MCTS_S_OVERFLOW_EDGES;
-        w.sync();
-        return -1;
-    }
-    MctsNode* nd = A.nodes + (size_t)t * A.cap + idx;
+    const uint32_t rec = mcts_alloc(w, A, t, mcts_rec_units(A, k));
+    if (rec == 0u) { w.sync(); return 0u; }
+    MctsNode* nd = mcts_node(A, rec);
     if (w.lane == 0) {
         nd->hash = h;
         nd->ply = (uint8_t)st[6];
         nd->n_edges = (uint16_t)k;
-        nd->edge_off = (uint32_t)e0;
+        nd->fwd = 0u;
         if (ended) {
             nd->kind = MCTS_NODE_TERMINAL;
             for (int i = 0; i < 4; i++) nd->u.es[i] = i < N ? es[i] : 0.f;
         } else {
             nd->kind = MCTS_NODE_NEEDS_NN;
-            nd->u.x.Ns = 0; nd->u.x.Qs = 0.f; nd->u.x.pad[0] = nd->u.x.pad[1] = 0u;
+            nd->u.x.Ns = 0; nd->u.x.Qs = 0.f; nd->u.x.hint = 0u; nd->u.x.pad = 0u;
         }
     }
-    mcts_copy16(w, A.states + ((size_t)t * A.cap + idx) * A.sp, st, A.sp);
+    mcts_copy16(w, mcts_state(A, rec), st, A.sp);
     if (!ended) {   // edges in action order: word i of the mask owns a contiguous run
-        MctsEdge* ed = A.edges + (size_t)t * A.ecap + e0;
+        const MctsEdges ed = mcts_edges(A, rec, k);
         for (int i = w.lane; i < SPL_MASK_WORDS; i += W::W) {
             int off = 0;
             for (int j = 0; j < i; j++) off += SPL_POPC(m[j * mstride]);
@@ -293,19 +416,20 @@ SPL_D int mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* s
             while (bits) {
                 const int b = SPL_FFS(bits) - 1;
                 bits &= bits - 1u;
-                MctsEdge e;
-                e.Q = MCTS_UNVISITED; e.P = 0.f; e.N = 0; e.child = 0u; e.action = (uint16_t)(32 * i + b); e.child_ne = 0; e.child_eoff = 0u; e.pad = 0u;
-                ed[off++] = e;
+                MctsPN pn; pn.P = 0.f; pn.N = 0;
+                MctsCA ca; ca.child = 0u; ca.action = (uint16_t)(32 * i + b); ca.child_ne = 0;
+                ed.Q[off] = MCTS_UNVISITED; ed.pn[off] = pn; ed.ca[off] = ca;
+                off++;
             }
         }
     }
     w.sync();
     if (w.lane == 0) {
-        T->n_nodes = idx + 1;
-        if (!ended) T->n_edges = e0 + k;
+        T->n_nodes += 1;
+        T->n_edges += k;
     }
-    mcts_table_insert(w, A, t, idx, h);
-    return idx;
+    mcts_table_insert(w, A, t, rec, h);
+    return rec;
 }
 
 // getGameEnded (:124) and, for a live position, getValidMoves (:136) of a canonical state, as one thread's work
@@ -332,7 +456,7 @@ SPL_D bool mcts_rules_core(S& s, int action, SplRules rules, float* es, uint32_t
 // root creation at the start of a move (one per move per tree: lane 0 evaluates the state, the warp stores it)
 // `scratch` = 24 uint32 of per-warp scratch.
 template <int N, class W>
-SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
+SPL_D uint32_t mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
     if (w.lane == 0) {
         AosAcc s{st};
         float es[N];
@@ -343,23 +467,25 @@ SPL_D int mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSear
     w.sync();
     float es[N];
     for (int i = 0; i < N; i++) memcpy(&es[i], &scratch[16 + i], 4);
-    const int idx = mcts_store_node<N>(w, A, t, st, h, scratch[13] != 0u, es, scratch, 1);
+    const uint32_t rec = mcts_store_node<N>(w, A, t, st, h, scratch[13] != 0u, es, scratch, 1);
     w.sync();
-    return idx;
+    return rec;
 }
 
 // ------------------------------------------------------------------------------------------
 // root softmax + Dirichlet noise (softmax :244-250, applyDirNoise :180-186, normalise :239-242)
 // ------------------------------------------------------------------------------------------
-// Marsaglia-Tsang gamma(alpha,1) for the on-device Dirichlet sampler (production; parity runs inject the vector)
+// Marsaglia-Tsang gamma(alpha,1) for the on-device Dirichlet sampler (production; parity runs inject the vector).
+// Philox key (seed), counter (game, episode, root ply, 16 + 128 * edge rank + 2 * attempt [+ 1]): fresh noise for every move of every
+// episode of every lane (rng.dirichlet per move, :181); streams 0..5 of the same (game, episode, ply) belong to the env and the move sampler.
 SPL_D double mcts_u01(uint32_t a, uint32_t b) { return ((double)(((uint64_t)a << 21) ^ (uint64_t)(b >> 11)) + 0.5) * (1.0 / 9007199254740992.0); }
-SPL_D double mcts_gamma(double alpha, uint64_t seed, uint32_t game, uint32_t ply, uint32_t k) {
+SPL_D double mcts_gamma(double alpha, uint64_t seed, uint32_t game, uint32_t episode, uint32_t ply, uint32_t k) {
     const double a1 = alpha < 1.0 ? alpha + 1.0 : alpha;
     const double d = a1 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
     double g = d;
     for (uint32_t attempt = 0; attempt < 64u; attempt++) {
-        const SplPhilox r0 = spl_philox(seed, game, ply, k * 128u + 2u * attempt, 4);
-        const SplPhilox r1 = spl_philox(seed, game, ply, k * 128u + 2u * attempt + 1u, 4);
+        const SplPhilox r0 = spl_philox(seed, game, episode, ply, 16u + k * 128u + 2u * attempt);
+        const SplPhilox r1 = spl_philox(seed, game, episode, ply, 16u + k * 128u + 2u * attempt + 1u);
         const double u1 = mcts_u01(r0.v[0], r0.v[1]), u2 = mcts_u01(r0.v[2], r0.v[3]), u3 = mcts_u01(r1.v[0], r1.v[1]);
         const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
         double v = 1.0 + c * x;
@@ -377,7 +503,7 @@ SPL_D double mcts_gamma(double alpha, uint64_t seed, uint32_t game, uint32_t ply
 // Ps <- normalise(0.75 * softmax(Ps, T0) + 0.25 * Dir) on the node's edges. dir (may be NULL): the vector
 // rng.dirichlet returned, one value per legal action in action order.
 template <class W>
-SPL_D void mcts_root_noise(const W& w, MctsEdge* ed, int k, const MctsSearchParams& P, const double* dir, uint32_t game, uint32_t ply,
+SPL_D void mcts_root_noise(const W& w, MctsPN* ed, int k, const MctsSearchParams& P, const double* dir, uint32_t game, uint32_t episode, uint32_t ply,
                            double* dscratch /* >= 2 doubles per warp */) {
     if (P.temperature0 != 1.0) {   // Ps ** (1/T) in float64, normalised, back to float32 (softmax :247-250)
         const double inv_t = 1.0 / P.temperature0;
@@ -394,11 +520,11 @@ SPL_D void mcts_root_noise(const W& w, MctsEdge* ed, int k, const MctsSearchPara
     double gsum = 1.0;
     if (!dir) {   // Dirichlet(alpha) = iid gamma(alpha) / their sum; the gammas are recomputed below (counter-based)
         double part = 0.0;
-        for (int i = w.lane; i < k; i += W::W) part = MC_DADD(part, mcts_gamma(P.dirichlet_alpha, P.seed, game, ply, (uint32_t)i));
+        for (int i = w.lane; i < k; i += W::W) part = MC_DADD(part, mcts_gamma(P.dirichlet_alpha, P.seed, game, episode, ply, (uint32_t)i));
         gsum = w.sumd_tree(part);
     }
     for (int i = w.lane; i < k; i += W::W) {
-        const double dv = dir ? dir[i] : MC_DDIV(mcts_gamma(P.dirichlet_alpha, P.seed, game, ply, (uint32_t)i), gsum);
+        const double dv = dir ? dir[i] : MC_DDIV(mcts_gamma(P.dirichlet_alpha, P.seed, game, episode, ply, (uint32_t)i), gsum);
         ed[i].P = (float)MC_DADD((double)MC_FMUL(0.75f, ed[i].P), MC_DMUL(0.25, dv));
     }
     w.sync();
@@ -418,15 +544,15 @@ SPL_D void mcts_root_noise(const W& w, MctsEdge* ed, int k, const MctsSearchPara
 // returns the edge position inside the node
 // ------------------------------------------------------------------------------------------
 template <class W>
-SPL_D int mcts_pick(const W& w, const MctsEdge* ed, const MctsEdge& first, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced,
-                    int n_iter) {   // `first` = ed[lane], fetched by the caller together with the node header
+SPL_D int mcts_pick(const W& w, const MctsEdges& ed, const MctsEdgeV& first, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced,
+                    int n_iter) {   // `first` = edge [lane], fetched by the caller together with the node header
     const double fpu_init = P.fpu > 0.0 ? MC_DADD((double)Qs, -P.fpu) : P.fpu;   // :202
     double sq_ns, sq_ns_eps;
     w.sqrt2((double)Ns, MC_DADD((double)Ns, MCTS_EPS), sq_ns, sq_ns_eps);
     double best_u = 0.0;
     int best_i = -1, forced_i = 0x7fffffff;
     for (int i = w.lane; i < k; i += W::W) {
-        const MctsEdge e = i == w.lane ? first : ed[i];
+        const MctsEdgeV e = i == w.lane ? first : ed.load(i);
         if (forced && forced_i == 0x7fffffff) {   // :207-208 - the first legal action short of its forced visits wins outright
             const long long quota = (long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)n_iter));
             if ((long long)e.N < quota) forced_i = i;
@@ -460,16 +586,17 @@ SPL_D float mcts_vsel(const float* v, int i) {
 }
 template <int N, class W>
 SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const float* v) {
-    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
     const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
     for (int d = w.lane; d < depth; d += W::W) {
         const float v0 = mcts_vsel<N>(v, ((d - depth) % N + N) % N);
-        MctsNode* nd = nodes + path[2 * d];
-        MctsEdge* e = edges + path[2 * d + 1];
-        e->Q = MC_DDIV(MC_DADD(MC_DMUL((double)e->N, e->Q), (double)v0), (double)(e->N + 1));                               // :171
+        const uint32_t rec = path[2 * d], pe = path[2 * d + 1];
+        MctsNode* nd = mcts_node(A, rec);
+        const MctsEdges ed = mcts_edges(A, rec, (int)(pe >> 16));
+        const int pos = (int)(pe & 0xFFFFu);
+        const MctsPN pn = ed.pn[pos];
+        ed.Q[pos] = MC_DDIV(MC_DADD(MC_DMUL((double)pn.N, ed.Q[pos]), (double)v0), (double)(pn.N + 1));                      // :171
         nd->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nd->u.x.Ns + 1), nd->u.x.Qs), v0), (float)(nd->u.x.Ns + 2));          // :172
-        e->N += 1;
+        ed.pn[pos].N = pn.N + 1;
         nd->u.x.Ns += 1;
     }
     if (w.lane == 0) {
@@ -482,21 +609,22 @@ SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const f
 
 // hands a node that waits for the network to the leaf row of its tree (:136-138)
 template <int N, class W>
-SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
+SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
                           bool rows = true) {   // rows = false: the staging row of the rules kernel already holds this very state and mask
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
     if (rows) {
-        const MctsNode* nd = A.nodes + (size_t)t * A.cap + node;
-        const int8_t* src = A.states + ((size_t)t * A.cap + node) * A.sp;
+        const MctsNode* nd = mcts_node(A, node);
+        const int8_t* src = mcts_state(A, node);
         for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
         for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
         w.sync();
-        const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
-        for (int i = w.lane; i < (int)nd->n_edges; i += W::W) leaf_valid[ed[i].action] = 1;
+        const int k = (int)nd->n_edges;
+        const MctsEdges ed = mcts_edges(A, node, k);
+        for (int i = w.lane; i < k; i += W::W) leaf_valid[ed.ca[i].action] = 1;
         if (w.lane == 0) A.leaf_src[t] = 0;
     }
-    if (w.lane == 0) { T->leaf = node; T->path_len = depth; T->sims_done = sims_done; T->cur = -1; T->pend_edge = -1; }
+    if (w.lane == 0) { T->leaf = node; T->path_len = depth; T->sims_done = sims_done; T->cur = 0u; T->pend_edge = -1; }
     w.sync();
 }
 
@@ -515,38 +643,37 @@ template <int N, class W>
 SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int max_terminal, int max_levels,
                             int8_t* leaf_state, uint8_t* leaf_valid) {
     MctsTree* T = A.trees + t;
-    if (T->leaf >= 0) return 1;
+    if (T->leaf != 0u) return 1;
     if (T->pend_edge >= 0) return 2;
     if (T->status != 0u) return 0;
-    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
-    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    const uint32_t root = T->root;
     int sims_done = T->sims_done;
     const int target = T->sims_target;
+    if (root == 0u || sims_done >= target) return 0;
+    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
     const uint32_t flags = T->flags;
-    const int root = T->root;
-    int cur = T->cur, depth = cur >= 0 ? T->path_len : 0;
-    if (cur < 0) cur = root;
-    // where the edges of `cur` are expected: known from the parent's edge, or from the node header at the start of a walk
-    uint32_t eoff = nodes[cur].edge_off;
-    int ne = nodes[cur].kind == MCTS_NODE_TERMINAL ? 0 : (int)nodes[cur].n_edges;
+    uint32_t cur = T->cur;
+    int depth = cur != 0u ? T->path_len : 0;
+    if (cur == 0u) cur = root;
+    // the edge count of `cur`: known from the parent's edge, or from the node header at the start of a walk
+    int ne = mcts_node(A, cur)->kind == MCTS_NODE_TERMINAL ? 0 : (int)mcts_node(A, cur)->n_edges;
     // The child the PREVIOUS visit of a node chose is fetched (header + edges) while this visit is still computing its pick: the
     // search tends to walk the same line again, and then the next level starts without a memory round trip. The hint lives in
     // a spare word of the node header (edge position + 1); it never influences a result, only what is loaded early.
     bool have_spec = false;
-    MctsEdge spec_first;
+    MctsEdgeV spec_first = mcts_edge_none();
     MctsNode spec_nd;
     while (sims_done < target) {
         for (;;) {
-            const MctsEdge* ed = edges + eoff;
-            MctsEdge first;                                  // header and first 32 edges: one round trip
+            const MctsEdges ed = mcts_edges(A, cur, ne);
+            MctsEdgeV first;                                  // header and first 32 edges: one round trip
             MctsNode nd;
             if (have_spec) {
                 first = spec_first; nd = spec_nd;
             } else {
-                first.Q = MCTS_UNVISITED; first.P = 0.f; first.N = 0; first.child = 0u; first.action = 0; first.child_ne = 0; first.child_eoff = 0u; first.pad = 0u;
-                if (w.lane < ne) first = ed[w.lane];
-                nd = nodes[cur];
+                first = mcts_edge_none();
+                if (w.lane < ne) first = ed.load(w.lane);
+                nd = *mcts_node(A, cur);
             }
             have_spec = false;
             const int kind = nd.kind;
@@ -556,22 +683,18 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             }
             if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
             int hp = -1;
-            const int hint = (int)nd.u.x.pad[0] - 1;
+            const int hint = (int)nd.u.x.hint - 1;
 #ifdef __CUDACC__
             if (hint >= 0 && hint < 32 && hint < (int)nd.n_edges) {
                 const uint32_t hchild = __shfl_sync(0xffffffffu, first.child, hint);
-                const uint32_t heoff = __shfl_sync(0xffffffffu, first.child_eoff, hint);
                 const int hne = __shfl_sync(0xffffffffu, (int)first.child_ne, hint);
                 if (hchild != 0u) {
                     hp = hint;
-                    spec_first.Q = MCTS_UNVISITED; spec_first.P = 0.f; spec_first.N = 0; spec_first.child = 0u; spec_first.action = 0;
-                    spec_first.child_ne = 0; spec_first.child_eoff = 0u; spec_first.pad = 0u;
-                    if (w.lane < hne) spec_first = edges[heoff + w.lane];
-                    spec_nd = nodes[hchild - 1u];
+                    spec_first = mcts_edge_none();
+                    if (w.lane < hne) spec_first = mcts_edges(A, hchild, hne).load(w.lane);
+                    spec_nd = *mcts_node(A, hchild);
                 }
             }
-#endif
-#ifdef __CUDACC__
             long long prof_t0 = 0;
             if (A.prof) prof_t0 = clock64();
 #endif
@@ -580,38 +703,37 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             if (A.prof && w.lane == 0) { A.prof[(size_t)t * 16 + 6] += clock64() - prof_t0; A.prof[(size_t)t * 16 + 7] += 1; }   // diagnostics: cycles inside the pick, levels
 #endif
             if (w.lane == 0) {
-                path[2 * depth] = (uint32_t)cur; path[2 * depth + 1] = nd.edge_off + (uint32_t)ei;
-                if (ei != hint) nodes[cur].u.x.pad[0] = (uint32_t)ei + 1u;
+                path[2 * depth] = cur; path[2 * depth + 1] = (uint32_t)ei | ((uint32_t)nd.n_edges << 16);
+                if (ei != hint) mcts_node(A, cur)->u.x.hint = (uint32_t)ei + 1u;
             }
             depth++;
-            uint32_t child, child_eoff;
+            uint32_t child;
             int child_ne;
 #ifdef __CUDACC__
             if (ei < 32) {
                 child = __shfl_sync(0xffffffffu, first.child, ei);
-                child_eoff = __shfl_sync(0xffffffffu, first.child_eoff, ei);
                 child_ne = __shfl_sync(0xffffffffu, (int)first.child_ne, ei);
             } else
 #endif
             {
-                const MctsEdge sel = ed[ei];
-                child = sel.child; child_eoff = sel.child_eoff; child_ne = (int)sel.child_ne;
+                const MctsCA sel = ed.ca[ei];
+                child = sel.child; child_ne = (int)sel.child_ne;
             }
             if (child != 0u && --max_levels <= 0) {   // yield: a very deep path finishes in the next call instead of holding up the wave
-                if (w.lane == 0) { T->cur = (int)child - 1; T->path_len = depth; T->sims_done = sims_done; }
+                if (w.lane == 0) { T->cur = child; T->path_len = depth; T->sims_done = sims_done; }
                 w.sync();
                 return 3;
             }
             if (child == 0u) {   // first traversal of this edge
                 if (w.lane == 0) {
-                    T->pend_edge = (int32_t)(nd.edge_off + (uint32_t)ei); T->pend_parent = cur;
-                    T->path_len = depth; T->sims_done = sims_done; T->cur = -1;
+                    T->pend_edge = (int32_t)((uint32_t)ei | ((uint32_t)nd.n_edges << 16)); T->pend_parent = cur;
+                    T->path_len = depth; T->sims_done = sims_done; T->cur = 0u;
                 }
                 w.sync();
                 return 2;
             }
-            cur = (int)child - 1;
-            eoff = child_eoff; ne = child_ne;
+            cur = child;
+            ne = child_ne;
             have_spec = ei == hp;
 #ifdef __CUDACC__
             if (have_spec && w.lane == 0) atomicAdd(&T->spec_hits, 1);
@@ -620,20 +742,20 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
         {   // terminal: return Es up the path
             float v[N];
 #pragma unroll
-            for (int i = 0; i < N; i++) v[i] = nodes[cur].u.es[i];
+            for (int i = 0; i < N; i++) v[i] = mcts_node(A, cur)->u.es[i];
             mcts_backup<N>(w, A, t, depth, v);
         }
         w.sync();
         sims_done++;
         cur = root; depth = 0;
-        eoff = nodes[root].edge_off; ne = nodes[root].kind == MCTS_NODE_TERMINAL ? 0 : (int)nodes[root].n_edges;
+        ne = mcts_node(A, root)->kind == MCTS_NODE_TERMINAL ? 0 : (int)mcts_node(A, root)->n_edges;
         if (--max_terminal <= 0 && sims_done < target) {
-            if (w.lane == 0) { T->sims_done = sims_done; T->cur = -1; T->path_len = 0; }
+            if (w.lane == 0) { T->sims_done = sims_done; T->cur = 0u; T->path_len = 0; }
             w.sync();
             return 3;
         }
     }
-    if (w.lane == 0) { T->sims_done = sims_done; T->cur = -1; T->path_len = 0; }
+    if (w.lane == 0) { T->sims_done = sims_done; T->cur = 0u; T->path_len = 0; }
     w.sync();
     return 0;
 }
@@ -646,37 +768,36 @@ SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSear
                            const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid, bool emit_rows = true) {
     MctsTree* T = A.trees + t;
     const int pe = T->pend_edge;
-    if (pe < 0) return T->leaf >= 0 ? 1 : 0;
+    if (pe < 0) return T->leaf != 0u ? 1 : 0;
     const uint64_t h = mcts_hash(w, st, A.sp);
-    int idx = mcts_lookup(w, A, t, st, h);
-    if (idx < 0) idx = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
-    if (idx < 0) {   // pool overflow: the search of this tree stops here (status bit set)
-        if (w.lane == 0) { T->pend_edge = -1; T->cur = -1; T->path_len = 0; }
+    uint32_t rec = mcts_lookup(w, A, t, st, h);
+    if (rec == 0u) rec = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
+    if (rec == 0u) {   // no room: the search of this tree stops here (status bit set)
+        if (w.lane == 0) { T->pend_edge = -1; T->cur = 0u; T->path_len = 0; }
         w.sync();
         return 0;
     }
-    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
+    const MctsNode* cn = mcts_node(A, rec);
+    const int kind = cn->kind;
     if (w.lane == 0) {
-        MctsEdge* e = A.edges + (size_t)t * A.ecap + pe;
-        e->child = (uint32_t)idx + 1u;
-        e->child_eoff = nodes[idx].edge_off;
-        e->child_ne = nodes[idx].kind == MCTS_NODE_TERMINAL ? (uint16_t)0 : nodes[idx].n_edges;
+        MctsCA* e = mcts_edges(A, T->pend_parent, pe >> 16).ca + (pe & 0xFFFF);
+        e->child = rec;
+        e->child_ne = kind == MCTS_NODE_TERMINAL ? (uint16_t)0 : cn->n_edges;
     }
     w.sync();
-    const int kind = nodes[idx].kind;
     const int depth = T->path_len, sims_done = T->sims_done;
     if (kind == MCTS_NODE_NEEDS_NN) {
-        mcts_emit_leaf<N>(w, A, t, idx, depth, sims_done, leaf_state, leaf_valid, emit_rows);
+        mcts_emit_leaf<N>(w, A, t, rec, depth, sims_done, leaf_state, leaf_valid, emit_rows);
         return 1;
     }
     if (kind == MCTS_NODE_TERMINAL) {
         float v[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) v[i] = nodes[idx].u.es[i];
+        for (int i = 0; i < N; i++) v[i] = cn->u.es[i];
         mcts_backup<N>(w, A, t, depth, v);
-        if (w.lane == 0) { T->sims_done = sims_done + 1; T->pend_edge = -1; T->cur = -1; T->path_len = 0; }
+        if (w.lane == 0) { T->sims_done = sims_done + 1; T->pend_edge = -1; T->cur = 0u; T->path_len = 0; }
     } else {   // an expanded node reached through a new edge: keep descending from it
-        if (w.lane == 0) { T->pend_edge = -1; T->cur = idx; }
+        if (w.lane == 0) { T->pend_edge = -1; T->cur = rec; }
     }
     w.sync();
     return 0;
@@ -687,9 +808,9 @@ template <int N, class W>
 SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const float* pi, const float* vin,
                             const double* dir, double* dscratch) {
     MctsTree* T = A.trees + t;
-    const int leaf = T->leaf;
-    if (leaf < 0) return;
-    MctsNode* nd = A.nodes + (size_t)t * A.cap + leaf;
+    const uint32_t leaf = T->leaf;
+    if (leaf == 0u) return;
+    MctsNode* nd = mcts_node(A, leaf);
 #ifdef __CUDACC__
     {
         // The common case in three rounds of loads instead of seven dependent ones: (1) the leaf's header, the value vector and
@@ -701,25 +822,26 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
         const MctsNode hdr = *nd;
         const int k = hdr.n_edges;
         if (!noise && k <= 32 && depth <= 32) {
-            MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-            MctsEdge* edges = A.edges + (size_t)t * A.ecap;
             const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
             float v[N];
 #pragma unroll
             for (int i = 0; i < N; i++) v[i] = vin[i];
             uint32_t pn = 0u, pe = 0u;
             if (w.lane < depth) { pn = path[2 * w.lane]; pe = path[2 * w.lane + 1]; }
-            MctsEdge* ed = edges + hdr.edge_off;
+            const MctsEdges ed = mcts_edges(A, leaf, k);
             int act = 0;
-            if (w.lane < k) act = ed[w.lane].action;
+            if (w.lane < k) act = ed.ca[w.lane].action;
             int eN = 0, nNs = 0;
             double eQ = 0.0;
             float nQs = 0.f;
-            if (w.lane < depth) { eN = edges[pe].N; eQ = edges[pe].Q; nNs = nodes[pn].u.x.Ns; nQs = nodes[pn].u.x.Qs; }
+            MctsNode* pnode = mcts_node(A, pn);
+            const MctsEdges ped = mcts_edges(A, pn, (int)(pe >> 16));
+            const int ppos = (int)(pe & 0xFFFFu);
+            if (w.lane < depth) { eN = ped.pn[ppos].N; eQ = ped.Q[ppos]; nNs = pnode->u.x.Ns; nQs = pnode->u.x.Qs; }
             float p = w.lane < k ? pi[act] : 0.f;
             float s = 0.f;
             for (int i = 0; i < k; i++) s = MC_FADD(s, __shfl_sync(0xffffffffu, p, i));
-            if (w.lane < k) ed[w.lane].P = MC_FDIV(p, s);
+            if (w.lane < k) ed.pn[w.lane].P = MC_FDIV(p, s);
             if (w.lane == 0) {
                 nd->u.x.Ns = 0;
                 nd->u.x.Qs = v[0];   // :147
@@ -727,17 +849,17 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
             }
             if (w.lane < depth) {
                 const float v0 = mcts_vsel<N>(v, ((w.lane - depth) % N + N) % N);
-                edges[pe].Q = MC_DDIV(MC_DADD(MC_DMUL((double)eN, eQ), (double)v0), (double)(eN + 1));                 // :171
-                nodes[pn].u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nNs + 1), nQs), v0), (float)(nNs + 2));             // :172
-                edges[pe].N = eN + 1;
-                nodes[pn].u.x.Ns = nNs + 1;
+                ped.Q[ppos] = MC_DDIV(MC_DADD(MC_DMUL((double)eN, eQ), (double)v0), (double)(eN + 1));                 // :171
+                pnode->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nNs + 1), nQs), v0), (float)(nNs + 2));               // :172
+                ped.pn[ppos].N = eN + 1;
+                pnode->u.x.Ns = nNs + 1;
             }
             if (w.lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? mcts_vsel<N>(v, ((i - depth) % N + N) % N) : 0.f;
                 T->depth_sum += depth;
                 T->sims_done += 1;
-                T->leaf = -1; T->cur = -1; T->pend_edge = -1; T->path_len = 0;
+                T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->path_len = 0;
                 T->nn_calls += 1;
             }
             w.sync();
@@ -745,21 +867,21 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
         }
     }
 #endif
-    MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
     const int k = nd->n_edges;
-    for (int i = w.lane; i < k; i += W::W) ed[i].P = pi[ed[i].action];
+    const MctsEdges ed = mcts_edges(A, leaf, k);
+    for (int i = w.lane; i < k; i += W::W) ed.pn[i].P = pi[ed.ca[i].action];
     w.sync();
     if (leaf == T->root && T->sims_done == 0 && (T->flags & MCTS_F_NOISE)) {   // :141-143
-        mcts_root_noise(w, ed, k, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
+        mcts_root_noise(w, ed.pn, k, P, dir, P.game_base + (uint32_t)t, T->episode, (uint32_t)nd->ply, dscratch);
     } else {                                                                      // normalise :144
         if (w.lane == 0) {
             float s = 0.f;
-            for (int i = 0; i < k; i++) s = MC_FADD(s, ed[i].P);
+            for (int i = 0; i < k; i++) s = MC_FADD(s, ed.pn[i].P);
             reinterpret_cast<float*>(dscratch)[0] = s;
         }
         w.sync();
         const float s = reinterpret_cast<float*>(dscratch)[0];
-        for (int i = w.lane; i < k; i += W::W) ed[i].P = MC_FDIV(ed[i].P, s);
+        for (int i = w.lane; i < k; i += W::W) ed.pn[i].P = MC_FDIV(ed.pn[i].P, s);
         w.sync();
     }
     float v[N];
@@ -775,368 +897,330 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
     w.sync();
     if (w.lane == 0) {
         T->sims_done += 1;
-        T->leaf = -1; T->cur = -1; T->pend_edge = -1; T->path_len = 0;
+        T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->path_len = 0;
         T->nn_calls += 1;
     }
     w.sync();
 }
 
 // ------------------------------------------------------------------------------------------
-// start of a move: find or create the root; make room first if the pools could run out
+// cleaning. What the reference's dictionary holds but no later search of the same game can look up again:
+//   * nodes below the root's ply (every key carries its ply; the reference's own cleaning :80-85 relies on the same fact), and
+//   * nodes whose deck rows differ from the root's: moves inside the tree are deterministic (make_move(..., deterministic=True),
+//     :228) and never touch the decks (SplendorLogicNumba.py:445-450,529-532), so every state a search from this root or from
+//     any later root of the game looks up carries a deck that is a subset of the root's; a node with a card in its deck
+//     that the root's deck no longer has can never be equal to one of them.
+// Dropping those is result-neutral ("exact"). A real move that reveals a card therefore retires the whole tree at the next
+// begin in O(pages) - no copying -, and within a line of moves without reveals the tree simply grows in the shared pool.
+// When a tree reaches its node limit the survivors are COPIED into fresh pages (every copy independent: lane per record,
+// forwarding pointers in the old headers), the hash table is rebuilt and the old pages go back to the pool.
 // ------------------------------------------------------------------------------------------
-// re-bases the simulation in flight after the nodes moved: remap[old] = new index + 1, nodes[] already at their new places;
-// path edge entries were made node-relative beforehand (mcts_path_make_relative)
-template <class W>
-SPL_D int mcts_path_make_relative(const W& w, const MctsArena& A, int t, int* pend_rel) {
-    MctsTree* T = A.trees + t;
-    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-    const bool in_flight = T->leaf >= 0 || T->cur >= 0 || T->pend_edge >= 0;
-    const int plen = in_flight ? T->path_len : 0;
-    for (int d = w.lane; d < plen; d += W::W) path[2 * d + 1] -= nodes[path[2 * d]].edge_off;
-    *pend_rel = T->pend_edge >= 0 ? T->pend_edge - (int)nodes[T->pend_parent].edge_off : -1;
-    w.sync();
-    return plen;
+SPL_D void mcts_deck_of(const int8_t* st, uint8_t* deck15) {
+    for (int tier = 0; tier < 3; tier++)
+        for (int c = 0; c < 5; c++) deck15[5 * tier + c] = (uint8_t)st[7 * (26 + 2 * tier) + c];
 }
-template <class W>
-SPL_D void mcts_rebase_in_flight(const W& w, const MctsArena& A, int t, const uint32_t* remap, int plen, int pend_rel) {
-    MctsTree* T = A.trees + t;
-    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-    for (int d = w.lane; d < plen; d += W::W) {
-        const uint32_t nn = remap[path[2 * d]] - 1u;
-        path[2 * d] = nn;
-        path[2 * d + 1] += nodes[nn].edge_off;
-    }
-    if (w.lane == 0) {
-        if (T->root >= 0) T->root = (int)remap[T->root] - 1;       // (-1 if the root itself was dropped: begin re-creates it)
-        if (T->leaf >= 0) T->leaf = (int)remap[T->leaf] - 1;
-        if (T->cur >= 0) T->cur = (int)remap[T->cur] - 1;
-        if (pend_rel >= 0) {
-            T->pend_parent = (int)remap[T->pend_parent] - 1;
-            T->pend_edge = (int)nodes[T->pend_parent].edge_off + pend_rel;
-        }
-    }
-    w.sync();
+SPL_D bool mcts_deck_subset(const int8_t* st, const uint8_t* deck15) {   // every card still in the deck of `st` is still in deck15
+    bool ok = true;
+    for (int tier = 0; tier < 3; tier++)
+        for (int c = 0; c < 5; c++) ok &= ((uint8_t)st[7 * (26 + 2 * tier) + c] & ~deck15[5 * tier + c]) == 0;
+    return ok;
 }
 
-// hash table from scratch for nodes [0, n): the lanes insert concurrently (compare-and-swap on the slots)
+// gives every page of the tree back and empties its table; statistics and the simulation in flight are the caller's business
 template <class W>
-SPL_D void mcts_rebuild_table(const W& w, const MctsArena& A, int t, int n) {
+SPL_D void mcts_release_storage(const W& w, const MctsArena& A, int t) {
+    MctsTree* T = A.trees + t;
     uint32_t* tab = A.htab + (size_t)t * A.hcap;
-    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    for (int i = w.lane; i < A.hcap; i += W::W) tab[i] = 0u;
+    mcts_pages_push(w, A, A.tree_pages + (size_t)t * A.max_pages, T->n_pages);
+    uint4* t4 = reinterpret_cast<uint4*>(tab);
+    uint4 z; z.x = z.y = z.z = z.w = 0u;
+    for (int i = w.lane; i < A.hcap / 4; i += W::W) t4[i] = z;
     w.sync();
-    for (int i = w.lane; i < n; i += W::W) {
-        uint32_t slot = (uint32_t)nodes[i].hash & (uint32_t)(A.hcap - 1);
-        for (;;) {
-#ifdef __CUDACC__
-            if (atomicCAS(&tab[slot], 0u, (uint32_t)i + 1u) == 0u) break;
-#else
-            if (tab[slot] == 0u) { tab[slot] = (uint32_t)i + 1u; break; }
-#endif
-            slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
-        }
-    }
+    if (w.lane == 0) { T->n_pages = 0; T->bump = 0u; T->page_end = 0u; T->n_nodes = 0; T->n_edges = 0; }
     w.sync();
-}
-
-// In-place compaction keeping nodes with ply >= min_ply. A node below the root's ply can never be looked up again
-// (every key carries its ply), so this is result-neutral - the reference's own cleaning (:80-85) relies on the same
-// fact. Node indices and edge offsets both grow in creation order, so every block only moves towards the front.
-template <class W>
-SPL_D void mcts_compact(const W& w, const MctsArena& A, int t, int min_ply, bool use_marks) {
-    MctsTree* T = A.trees + t;
-    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
-    uint32_t* remap = A.htab + (size_t)t * A.hcap;   // the table is rebuilt below; hcap >= 2 cap
-    int8_t* states = A.states + (size_t)t * A.cap * A.sp;
-    const int n_old = T->n_nodes;
-    int n_new = 0;
-    for (int base = 0; base < n_old; base += W::W) {
-        const int i = base + w.lane;
-        const bool live = i < n_old && (use_marks ? remap[i] != 0u : (int)nodes[i].ply >= min_ply);
-        const uint32_t b = w.ballot(live);
-        if (i < n_old) remap[i] = live ? (uint32_t)(n_new + SPL_POPC(b & w.lanemask_lt())) + 1u : 0u;
-        n_new += SPL_POPC(b);
-    }
-    w.sync();
-    // a simulation may be in flight (the periodic cleaning runs between waves): its references into the pools - root,
-    // cur, leaf, the pending edge and the recorded path - are re-based with the nodes. Edge references become
-    // (node, position inside the node) while the blocks move.
-    int pend_rel;
-    const int plen = mcts_path_make_relative(w, A, t, &pend_rel);
-    int e_new = 0;
-    for (int i = 0; i < n_old; i++) {
-        const uint32_t r = remap[i];
-        if (r == 0u) continue;
-        const int j = (int)r - 1;
-        MctsNode nd = nodes[i];
-        const int ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
-        const int off = (int)nd.edge_off;
-        for (int c = 0; c < ne; c += W::W) {   // chunk-wise: read, sync, write (destination never passes the source)
-            const int k = c + w.lane;
-            MctsEdge e;
-            if (k < ne) {
-                e = edges[off + k];
-                if (e.child) e.child = remap[e.child - 1u];
-            }
-            w.sync();
-            if (k < ne) edges[e_new + k] = e;
-            w.sync();
-        }
-        if (j != i) {
-            for (int c = 0; c < A.sp / 16; c += W::W) {
-                const int k = c + w.lane;
-                uint4 x;
-                if (k < A.sp / 16) x = reinterpret_cast<const uint4*>(states + (size_t)i * A.sp)[k];
-                w.sync();
-                if (k < A.sp / 16) reinterpret_cast<uint4*>(states + (size_t)j * A.sp)[k] = x;
-            }
-        }
-        w.sync();
-        if (w.lane == 0) {
-            if (nd.kind != MCTS_NODE_TERMINAL) nd.edge_off = (uint32_t)e_new;
-            nodes[j] = nd;
-        }
-        e_new += ne;
-        w.sync();
-    }
-    for (int k = w.lane; k < e_new; k += W::W) {   // the children moved too: refresh the edge ranges cached in the edges
-        MctsEdge* e = edges + k;
-        if (e->child) e->child_eoff = nodes[e->child - 1u].edge_off;
-    }
-    w.sync();
-    mcts_rebase_in_flight(w, A, t, remap, plen, pend_rel);
-    mcts_rebuild_table(w, A, t, n_new);
-    if (w.lane == 0) {
-        T->n_nodes = n_new;
-        T->n_edges = e_new;
-        T->compactions += 1;
-    }
-    w.sync();
-}
-
-// numbers (in the hash-table region, which the compaction rebuilds anyway) every node reachable from `root` through
-// linked edges in breadth-first order: mark[old index] = position + 1, queue[position] = old index; returns the count.
-// Frontier nodes are expanded 32 at a time, one lane per node, edge position by edge position, so the numbering is
-// deterministic. Tighter than the ply rule, but it also drops nodes that a not-yet-linked edge could still transpose into.
-template <class W>
-SPL_D int mcts_mark_reachable(const W& w, const MctsArena& A, int t, int root) {
-    MctsTree* T = A.trees + t;
-    const MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    const MctsEdge* edges = A.edges + (size_t)t * A.ecap;
-    uint32_t* mark = A.htab + (size_t)t * A.hcap;
-    uint32_t* queue = mark + A.cap;   // hcap >= 2 cap
-    const int n_old = T->n_nodes;
-    for (int i = w.lane; i < n_old; i += W::W) mark[i] = i == root ? 1u : 0u;
-    if (w.lane == 0) queue[0] = (uint32_t)root;
-    w.sync();
-    int head = 0, tail = 1;
-    while (head < tail) {
-        const int q = head + w.lane;
-        const int level_end = tail;          // nodes numbered so far; this pass expands queue[head .. min(head + W, tail))
-        int ne = 0;
-        uint32_t eoff = 0u;
-        if (q < level_end) {
-            const MctsNode nd = nodes[queue[q]];
-            ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
-            eoff = nd.edge_off;
-        }
-        int max_ne = ne;
-#ifdef __CUDACC__
-        max_ne = __reduce_max_sync(0xffffffffu, max_ne);
-#endif
-        for (int k = 0; k < max_ne; k++) {
-            bool fresh = false;
-            uint32_t child = 0u;
-            if (k < ne) {
-                child = edges[eoff + k].child;
-                if (child) {
-#ifdef __CUDACC__
-                    fresh = atomicCAS(&mark[child - 1u], 0u, 0xFFFFFFFFu) == 0u;
-#else
-                    fresh = mark[child - 1u] == 0u;
-                    if (fresh) mark[child - 1u] = 0xFFFFFFFFu;
-#endif
-                }
-            }
-            const uint32_t b = w.ballot(fresh);
-            if (fresh) {
-                const int pos = tail + SPL_POPC(b & w.lanemask_lt());
-                queue[pos] = child - 1u;
-                mark[child - 1u] = (uint32_t)pos + 1u;
-            }
-            tail += SPL_POPC(b);
-            w.sync();
-        }
-        head = level_end < head + W::W ? level_end : head + W::W;
-    }
-    w.sync();
-    return tail;
-}
-
-// Reachable cleaning, fast path: the reachable nodes (numbered breadth-first by mcts_mark_reachable, n_live of them) are
-// copied through the FREE TAIL of the pools - out to [n_old, n_old + n_live), then back to the front - so every copy is
-// independent: one lane per node, no ordering constraints (the in-place mcts_compact walks the nodes one by one).
-// New node index = breadth-first position; edge blocks follow in that order, so offsets still grow with the index.
-// Returns false (nothing changed) when the tails are too small; the caller then compacts in place.
-template <class W>
-SPL_D bool mcts_compact_reachable(const W& w, const MctsArena& A, int t, int n_live) {
-    MctsTree* T = A.trees + t;
-    MctsNode* nodes = A.nodes + (size_t)t * A.cap;
-    MctsEdge* edges = A.edges + (size_t)t * A.ecap;
-    uint32_t* mark = A.htab + (size_t)t * A.hcap;
-    const uint32_t* queue = mark + A.cap;
-    int8_t* states = A.states + (size_t)t * A.cap * A.sp;
-    const int n_old = T->n_nodes, e_old = T->n_edges;
-    if (n_old + n_live > A.cap) return false;
-    int live_edges = 0;
-    for (int q = w.lane; q < n_live; q += W::W) {
-        const MctsNode nd = nodes[queue[q]];
-        live_edges += nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
-    }
-    live_edges = w.sum(live_edges);
-    if (e_old + live_edges > A.ecap) return false;
-    int pend_rel;
-    const int plen = mcts_path_make_relative(w, A, t, &pend_rel);
-    // pass 1: out to the tails (headers with their new edge offsets, states, edges with re-numbered children)
-    int ebase = 0;
-    for (int base = 0; base < n_live; base += W::W) {
-        const int q = base + w.lane;
-        MctsNode nd;
-        int ne = 0, old = 0;
-        if (q < n_live) {
-            old = (int)queue[q];
-            nd = nodes[old];
-            ne = nd.kind == MCTS_NODE_TERMINAL ? 0 : (int)nd.n_edges;
-        }
-        int incl = ne;   // inclusive scan of the edge counts over the lanes
-#ifdef __CUDACC__
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (w.lane >= o) incl += v;
-        }
-#endif
-        const int new_off = ebase + incl - ne;
-        if (q < n_live) {
-            const uint32_t old_off = nd.edge_off;
-            if (nd.kind != MCTS_NODE_TERMINAL) nd.edge_off = (uint32_t)new_off;
-            nodes[n_old + q] = nd;
-            const uint4* s4 = reinterpret_cast<const uint4*>(states + (size_t)old * A.sp);
-            uint4* d4 = reinterpret_cast<uint4*>(states + (size_t)(n_old + q) * A.sp);
-            for (int k = 0; k < A.sp / 16; k++) d4[k] = s4[k];
-            for (int k = 0; k < ne; k++) {
-                MctsEdge e = edges[old_off + k];
-                if (e.child) e.child = mark[e.child - 1u];
-                edges[e_old + new_off + k] = e;
-            }
-        }
-#ifdef __CUDACC__
-        ebase += __shfl_sync(0xffffffffu, incl, 31);
-#else
-        ebase += incl;
-#endif
-        w.sync();
-    }
-    // pass 2: back to the front
-    for (int q = w.lane; q < n_live; q += W::W) {
-        nodes[q] = nodes[n_old + q];
-        const uint4* s4 = reinterpret_cast<const uint4*>(states + (size_t)(n_old + q) * A.sp);
-        uint4* d4 = reinterpret_cast<uint4*>(states + (size_t)q * A.sp);
-        for (int k = 0; k < A.sp / 16; k++) d4[k] = s4[k];
-    }
-    w.sync();
-    for (int k = w.lane; k < live_edges; k += W::W) {
-        MctsEdge e = edges[e_old + k];
-        if (e.child) e.child_eoff = nodes[e.child - 1u].edge_off;
-        edges[k] = e;
-    }
-    w.sync();
-    mcts_rebase_in_flight(w, A, t, mark, plen, pend_rel);
-    mcts_rebuild_table(w, A, t, n_live);
-    if (w.lane == 0) { T->n_nodes = n_live; T->n_edges = live_edges; T->compactions += 1; }
-    w.sync();
-    return true;
-}
-
-// reachable cleaning of tree t from `root`: fast path if the pools have room for it, in place otherwise
-template <class W>
-SPL_D void mcts_clean_reachable(const W& w, const MctsArena& A, int t, int root, bool in_place_only) {
-    const int n_live = mcts_mark_reachable(w, A, t, root);
-    if (in_place_only || !mcts_compact_reachable(w, A, t, n_live)) mcts_compact(w, A, t, 0, true);
-}
-
-// periodic cleaning between waves (any state of the search): trees whose pools are filled beyond the thresholds drop
-// what can no longer be used - nodes below the root's ply (exact) or everything the root does not reach (gc_reachable).
-// Every tree that needs it cleans in the SAME launch, so the serial per-tree work is paid once for all of them.
-template <class W>
-SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes, int max_edges, int gc_reachable) {
-    MctsTree* T = A.trees + t;
-    if (T->root < 0 || (T->n_nodes <= max_nodes && T->n_edges <= max_edges)) return;
-    if (gc_reachable) mcts_clean_reachable(w, A, t, T->root, gc_reachable == 2);
-    else mcts_compact(w, A, t, (int)A.nodes[(size_t)t * A.cap + T->root].ply, false);
 }
 
 template <class W>
 SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_all_search_trees :188-192 for one tree
-    uint32_t* tab = A.htab + (size_t)t * A.hcap;
-    for (int i = w.lane; i < A.hcap; i += W::W) tab[i] = 0u;
+    mcts_release_storage(w, A, t);
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
-        T->n_nodes = 0; T->n_edges = 0; T->root = -1; T->leaf = -1; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
-        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->spec_hits = 0; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
+        T->root = 0u; T->leaf = 0u; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
+        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->spec_hits = 0; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u;
+        T->n_dropped = 0; T->hetero = 0;
     }
     w.sync();
 }
 
-// root_state: the reference's int8[R,7] bytes. edge_reserve: edges budgeted per new node when deciding to clean.
-// gc_reachable = 0: cleaning keeps every node with ply >= the root's (exactly result-neutral, the parity mode);
-// gc_reachable = 1: keeps only what is reachable from the new root (production: far smaller pools; a node that only a
-// not-yet-linked edge transposes into is re-created instead of found, which the reference's dictionary would not do).
+// every node of the tree has become unreachable (the root's deck lost a card): an exact cleaning that copies nothing
+template <class W>
+SPL_D void mcts_retire_all(const W& w, const MctsArena& A, int t) {
+    MctsTree* T = A.trees + t;
+    const int n = T->n_nodes;
+    mcts_release_storage(w, A, t);
+    if (w.lane == 0) {
+        T->n_dropped += n; T->compactions += 1;
+        T->root = 0u; T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u; T->path_len = 0; T->hetero = 0;
+    }
+    w.sync();
+}
+
+// marks (fwd = 1) every node reachable from `root` through linked edges: a stack threaded through the fwd words of the
+// records themselves, one node popped at a time, its edges looked at by all lanes
+template <class W>
+SPL_D void mcts_mark_reachable(const W& w, const MctsArena& A, uint32_t root) {
+    if (w.lane == 0) mcts_node(A, root)->fwd = 1u;   // bottom of the stack: link = 1 = "marked, nothing below"
+    w.sync();
+    uint32_t head = root;
+    while (head != 1u) {
+        const uint32_t rec = head;
+        MctsNode* nd = mcts_node(A, rec);
+        head = nd->fwd;
+        const int k = nd->kind == MCTS_NODE_TERMINAL ? 0 : (int)nd->n_edges;
+        w.sync();
+        if (w.lane == 0) nd->fwd = 1u;
+        w.sync();
+        const MctsEdges ed = mcts_edges(A, rec, k);
+        for (int base = 0; base < k; base += W::W) {
+            const int i = base + w.lane;
+            uint32_t c = i < k ? ed.ca[i].child : 0u;
+            bool fresh = false;
+            if (c) {
+#ifdef __CUDACC__
+                fresh = atomicCAS(&mcts_node(A, c)->fwd, 0u, 1u) == 0u;   // two edges of a node may lead to the same child
+#else
+                fresh = mcts_node(A, c)->fwd == 0u;
+#endif
+            }
+            // the fresh children go on the stack in lane order: each links to the previous fresh one, the first to the old head
+            const uint32_t b = w.ballot(fresh);
+#ifdef __CUDACC__
+            if (b) {
+                const int prev_lane = 31 - __clz((int)(b & w.lanemask_lt()));       // -1 if none below
+                const uint32_t prev_c = __shfl_sync(0xffffffffu, c, prev_lane < 0 ? 0 : prev_lane);
+                if (fresh) mcts_node(A, c)->fwd = prev_lane < 0 ? head : prev_c;
+                head = __shfl_sync(0xffffffffu, c, 31 - __clz((int)b));
+            }
+#else
+            if (b) { mcts_node(A, c)->fwd = head; head = c; }
+#endif
+            w.sync();
+        }
+    }
+    w.sync();
+}
+
+// Copies the surviving records of tree t into fresh pages. use_marks: survivors = records with fwd != 0 (mcts_mark_reachable);
+// else the exact rule: ply >= min_ply and (check_deck: deck within deck15). The simulation in flight (root, cur, leaf, pending
+// edge, recorded path) is re-based. Returns false, with the tree unchanged, when the pool cannot supply the pages.
+template <class W>
+SPL_D bool mcts_compact(const W& w, const MctsArena& A, int t, bool use_marks, int min_ply, const uint8_t* deck15, bool check_deck) {
+    MctsTree* T = A.trees + t;
+    uint32_t* tab = A.htab + (size_t)t * A.hcap;
+    uint32_t* pages = A.tree_pages + (size_t)t * A.max_pages;
+    const int old_pages = T->n_pages, n_old = T->n_nodes;
+    const uint32_t old_bump = T->bump, old_end = T->page_end;
+    if (w.lane == 0) { T->bump = 0u; T->page_end = 0u; }   // the copy starts on a page of its own
+    w.sync();
+    uint32_t chain = 0u;   // the new records this lane made, linked through their fwd words
+    int n_live = 0, e_live = 0;
+    bool fail = false;
+    for (int base = 0; base < A.hcap && !fail; base += W::W) {
+        const int s = base + w.lane;
+        const uint32_t rec = s < A.hcap ? tab[s] : 0u;
+        bool live = false;
+        int k = 0;
+        if (rec) {
+            const MctsNode* nd = mcts_node(A, rec);
+            k = nd->kind == MCTS_NODE_TERMINAL ? 0 : (int)nd->n_edges;
+            if (use_marks) live = nd->fwd != 0u;
+            else live = (int)nd->ply >= min_ply && (!check_deck || mcts_deck_subset(mcts_state(A, rec), deck15));
+        }
+        const uint32_t lb = w.ballot(live);
+        if (lb == 0u) continue;
+        const uint32_t units = live ? mcts_rec_units(A, k) : 0u;
+        int total = 0;
+        const int excl = w.scan_excl((int)units, total);
+        uint32_t dst = 0u;
+        uint32_t cur_bump = T->bump, cur_end = T->page_end;
+        if (cur_bump != 0u && cur_bump + (uint32_t)total <= cur_end) {   // the whole batch fits on the current page
+            dst = cur_bump + (uint32_t)excl;
+            w.sync();
+            if (w.lane == 0) T->bump = cur_bump + (uint32_t)total;
+            w.sync();
+        } else {                                                       // page boundary: one record at a time, in lane order
+            for (int l = 0; l < W::W; l++) {
+                if (!((lb >> l) & 1u)) continue;
+                const uint32_t u = (uint32_t)w.shfl((int)units, l);
+                const uint32_t o = mcts_alloc(w, A, t, u, true);
+                if (o == 0u) { fail = true; break; }
+                if (w.lane == l) dst = o;
+            }
+        }
+        if (fail) break;
+        if (live) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(mcts_ptr(A, rec));
+            uint4* d4 = reinterpret_cast<uint4*>(mcts_ptr(A, dst));
+            const int n16 = (int)units * 2;
+            int i = 0;
+            for (; i + 4 <= n16; i += 4) {
+                const uint4 a = s4[i], b = s4[i + 1], c = s4[i + 2], d = s4[i + 3];
+                d4[i] = a; d4[i + 1] = b; d4[i + 2] = c; d4[i + 3] = d;
+            }
+            for (; i < n16; i++) d4[i] = s4[i];
+            mcts_node(A, rec)->fwd = dst;
+            mcts_node(A, dst)->fwd = chain;
+            chain = dst;
+            n_live += 1; e_live += k;
+        }
+    }
+    fail = w.ballot(fail) != 0u;
+    if (fail) {   // out of pages: give the copy back, forget the forwarding pointers
+        w.sync();
+        mcts_pages_push(w, A, pages + old_pages, T->n_pages - old_pages);
+        for (int s = w.lane; s < A.hcap; s += W::W) {
+            const uint32_t rec = tab[s];
+            if (rec) mcts_node(A, rec)->fwd = 0u;
+        }
+        w.sync();
+        if (w.lane == 0) { T->n_pages = old_pages; T->bump = old_bump; T->page_end = old_end; }
+        w.sync();
+        return false;
+    }
+    w.sync();
+    // the simulation in flight follows its nodes (a dropped node has fwd == 0)
+    {
+        uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+        const bool in_flight = T->leaf != 0u || T->cur != 0u || T->pend_edge >= 0;
+        const int plen = in_flight ? T->path_len : 0;
+        for (int d = w.lane; d < plen; d += W::W) path[2 * d] = mcts_node(A, path[2 * d])->fwd;
+        if (w.lane == 0) {
+            if (T->root) T->root = mcts_node(A, T->root)->fwd;     // (0 if the root itself was dropped: begin re-creates it)
+            if (T->leaf) T->leaf = mcts_node(A, T->leaf)->fwd;
+            if (T->cur) T->cur = mcts_node(A, T->cur)->fwd;
+            if (T->pend_edge >= 0) T->pend_parent = mcts_node(A, T->pend_parent)->fwd;
+        }
+        w.sync();
+    }
+    // new table; every lane walks the records it copied: children follow the forwarding pointers of the old copies
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(tab);
+        uint4 z; z.x = z.y = z.z = z.w = 0u;
+        for (int i = w.lane; i < A.hcap / 4; i += W::W) t4[i] = z;
+    }
+    w.sync();
+    for (uint32_t rec = chain; rec != 0u;) {
+        MctsNode* nd = mcts_node(A, rec);
+        const uint32_t next = nd->fwd;
+        nd->fwd = 0u;
+        const int k = nd->kind == MCTS_NODE_TERMINAL ? 0 : (int)nd->n_edges;
+        MctsCA* ca = mcts_edges(A, rec, k).ca;
+        for (int e = 0; e < k; e++) {
+            const uint32_t c = ca[e].child;
+            if (c) ca[e].child = mcts_node(A, c)->fwd;
+        }
+        uint32_t slot = (uint32_t)nd->hash & (uint32_t)(A.hcap - 1);
+        for (;;) {
+#ifdef __CUDACC__
+            if (atomicCAS(&tab[slot], 0u, rec) == 0u) break;
+#else
+            if (tab[slot] == 0u) { tab[slot] = rec; break; }
+#endif
+            slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
+        }
+        rec = next;
+    }
+    w.sync();
+    // the old pages go back to the pool; the new ones move to the front of the tree's page list
+    mcts_pages_push(w, A, pages, old_pages);
+    const int new_pages = T->n_pages - old_pages;
+    for (int base = 0; base < new_pages; base += W::W) {
+        const int i = base + w.lane;
+        uint32_t p = 0u;
+        if (i < new_pages) p = pages[old_pages + i];
+        w.sync();
+        if (i < new_pages) pages[i] = p;
+        w.sync();
+    }
+    n_live = w.sum(n_live); e_live = w.sum(e_live);
+    if (w.lane == 0) {
+        T->n_pages = new_pages;
+        if (!use_marks) T->n_dropped += n_old - n_live;
+        T->n_nodes = n_live; T->n_edges = e_live;
+        T->compactions += 1;
+    }
+    w.sync();
+    return true;
+}
+
+// periodic cleaning between waves (any state of the search): trees that hold more than max_nodes nodes drop what can no
+// longer be used - per the exact rule, or everything the root does not reach (gc_reachable)
+template <class W>
+SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes, int gc_reachable) {
+    MctsTree* T = A.trees + t;
+    if (T->root == 0u || T->n_nodes <= max_nodes) return;
+    if (gc_reachable) {
+        mcts_mark_reachable(w, A, T->root);
+        mcts_compact(w, A, t, true, 0, nullptr, false);
+    } else {
+        uint8_t deck[15];
+        mcts_deck_of(mcts_state(A, T->root), deck);
+        mcts_compact(w, A, t, false, (int)mcts_node(A, T->root)->ply, deck, T->hetero != 0);
+    }
+}
+
+// root_state: the reference's int8[R,7] bytes.
+// gc_reachable = 0: cleaning is exact (see above); gc_reachable = 1: a tree that reaches its node limit keeps only what the new
+// root reaches (a node that only a not-yet-linked edge transposes into is re-created instead of found, which the reference's
+// dictionary would not do).
 template <int N, class W>
 SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* root_state, int sims_target,
-                           uint32_t flags, int edge_reserve, int gc_reachable, const double* dir, int8_t* st, uint32_t* scratch, double* dscratch) {
+                           uint32_t flags, int gc_reachable, const double* dir, uint32_t episode, int8_t* st, uint32_t* scratch, double* dscratch) {
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
     for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
     w.sync();
     const int root_ply = (int)(uint8_t)st[6];
     const uint64_t h = mcts_hash(w, st, A.sp);
-    // room for this move: one node per simulation and, per node, the larger of the configured reserve and 1.5 x this
-    // tree's own average number of legal moves
-    const int avg = T->n_nodes > 16 ? (T->n_edges + T->n_nodes - 1) / T->n_nodes : 0;
-    const int per_node = edge_reserve > avg + avg / 2 ? edge_reserve : avg + avg / 2;
-    const int need_nodes = sims_target + 2, need_edges = (sims_target + 2) * per_node;
-    const uint32_t overflowed = T->status & (MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_EDGES);
-    if (overflowed || T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
-        bool cleared = false;
+    uint8_t deck[15];
+    mcts_deck_of(st, deck);
+    if (T->n_nodes > 0 && !T->hetero) {
+        bool same = true, subset = true;
+        for (int i = 0; i < 15; i++) { same &= deck[i] == T->deck[i]; subset &= (deck[i] & ~T->deck[i]) == 0; }
+        if (!same) {
+            if (subset) mcts_retire_all(w, A, t);          // a card was revealed since the tree's nodes were made
+            else { if (w.lane == 0) T->hetero = 1; w.sync(); }   // not a later position of the same game: keep everything
+        }
+    }
+    const int need_nodes = sims_target + 2;
+    const uint32_t overflowed = T->status & (MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_POOL);
+    if (overflowed || T->n_nodes + need_nodes > A.node_limit) {
         if (gc_reachable) {
-            const int old_root = mcts_lookup(w, A, t, st, h);
-            if (old_root >= 0) {
-                mcts_clean_reachable(w, A, t, old_root, gc_reachable == 2);
-            } else {   // a root the tree has never seen (a card was revealed): nothing of the old tree can be reached
+            const uint32_t old_root = mcts_lookup(w, A, t, st, h);
+            if (old_root) {
+                mcts_mark_reachable(w, A, old_root);
+                mcts_compact(w, A, t, true, 0, nullptr, false);
+            } else {   // a root the tree has never seen: nothing of the old tree can be reached
                 const int resets = T->resets;
                 mcts_clear_tree(w, A, t);
                 if (w.lane == 0) T->resets = resets;
                 w.sync();
-                cleared = true;
             }
         } else {
-            mcts_compact(w, A, t, root_ply, false);
-            if (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap) {
+            mcts_compact(w, A, t, false, root_ply, deck, T->hetero != 0);
+            if (T->n_nodes + need_nodes > A.node_limit) {
                 // the exact cleaning did not free enough: fall back to the reachable set of the new root (counted as lossy:
                 // nodes that only a not-yet-linked edge could transpose into are dropped)
-                const int old_root = mcts_lookup(w, A, t, st, h);
-                if (old_root >= 0) {
-                    mcts_clean_reachable(w, A, t, old_root, false);
+                const uint32_t old_root = mcts_lookup(w, A, t, st, h);
+                if (old_root) {
+                    mcts_mark_reachable(w, A, old_root);
+                    mcts_compact(w, A, t, true, 0, nullptr, false);
                     if (w.lane == 0) T->resets += 1;
                     w.sync();
                 }
             }
         }
-        if (!cleared && (T->n_nodes + need_nodes > A.cap || T->n_edges + need_edges > A.ecap)) {   // still no room: forget the tree (counted)
+        if (T->n_nodes + need_nodes > A.node_limit) {   // still no room: forget the tree (counted)
             const int resets = T->resets;
             mcts_clear_tree(w, A, t);
             if (w.lane == 0) T->resets = resets + 1;
@@ -1144,23 +1228,27 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
         }
         if (w.lane == 0) {
             if (overflowed) T->truncated += 1;
-            T->status &= ~(uint32_t)(MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_EDGES);
+            T->status &= ~(uint32_t)(MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_POOL);
         }
         w.sync();
     }
-    int idx = mcts_lookup(w, A, t, st, h);
-    if (idx < 0) idx = mcts_create_node<N>(w, A, t, P, st, h, scratch);
+    if (T->n_nodes == 0) {   // an empty tree takes the deck of its first root
+        if (w.lane == 0) { for (int i = 0; i < 15; i++) T->deck[i] = deck[i]; T->hetero = 0; }
+        w.sync();
+    }
+    uint32_t rec = mcts_lookup(w, A, t, st, h);
+    if (rec == 0u) rec = mcts_create_node<N>(w, A, t, P, st, h, scratch);
     if (w.lane == 0) {
-        T->root = idx; T->leaf = -1; T->sims_done = 0; T->sims_target = idx < 0 ? 0 : sims_target; T->path_len = 0;
-        T->flags = flags; T->cur = -1; T->pend_edge = -1; T->pend_parent = -1;
+        T->root = rec; T->leaf = 0u; T->sims_done = 0; T->sims_target = rec == 0u ? 0 : sims_target; T->path_len = 0;
+        T->flags = flags; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u; T->episode = episode;
     }
     w.sync();
     // a root the tree already expanded gets the noise on its stored Ps before the first simulation picks (:150-154);
     // a new root gets it when its network row arrives (mcts_expand_tree)
-    if (idx >= 0 && sims_target > 0 && (flags & MCTS_F_NOISE)) {
-        MctsNode* nd = A.nodes + (size_t)t * A.cap + idx;
+    if (rec != 0u && sims_target > 0 && (flags & MCTS_F_NOISE)) {
+        const MctsNode* nd = mcts_node(A, rec);
         if (nd->kind == MCTS_NODE_EXPANDED)
-            mcts_root_noise(w, A.edges + (size_t)t * A.ecap + nd->edge_off, (int)nd->n_edges, P, dir, P.game_base + (uint32_t)t, (uint32_t)nd->ply, dscratch);
+            mcts_root_noise(w, mcts_edges(A, rec, (int)nd->n_edges).pn, (int)nd->n_edges, P, dir, P.game_base + (uint32_t)t, episode, (uint32_t)nd->ply, dscratch);
     }
 }
 
@@ -1173,24 +1261,25 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
     const MctsTree* T = A.trees + t;
     for (int a = w.lane; a < SPL_ACTIONS; a += W::W) probs[a] = 0.0;
     w.sync();
-    if (T->root < 0) return;
-    const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+    if (T->root == 0u) return;
+    const MctsNode* nd = mcts_node(A, T->root);
     if (nd->kind != MCTS_NODE_EXPANDED) return;
-    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
     const int k = nd->n_edges;
+    const MctsEdges ed = mcts_edges(A, T->root, k);
     const bool forced = (T->flags & MCTS_F_FORCED) != 0u;
     if (w.lane == 0) {
         const float qs = nd->u.x.Qs;
         for (int p = 0; p < N; p++) q[p] = p == 0 ? (double)qs : (double)MC_FDIV(-qs, (float)(N - 1));   // :65-66
         int best = 0;
-        for (int i = 0; i < k; i++) best = ed[i].N > best ? ed[i].N : best;
+        for (int i = 0; i < k; i++) best = ed.pn[i].N > best ? ed.pn[i].N : best;
         double sum = 0.0;
         int besti = -1;
         double bestc = -1.0;
         for (int i = 0; i < k; i++) {
-            double c = (double)ed[i].N;
+            const MctsPN e = ed.pn[i];
+            double c = (double)e.N;
             if (forced) {   // policy target pruning :69-74
-                if (ed[i].N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)ed[i].P), (double)T->sims_target));
+                if (e.N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)T->sims_target));
                 c = c > 1.0 ? c : 0.0;
             }
             if (c > bestc) { bestc = c; besti = i; }
@@ -1198,12 +1287,12 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
                 c = temp == 1.0 ? c : pow(c, 1.0 / temp);   // :94
                 sum = MC_DADD(sum, c);
             }
-            probs[ed[i].action] = c;
+            probs[ed.ca[i].action] = c;
         }
         if (temp == 0.0) {   // :87-92
-            for (int i = 0; i < k; i++) probs[ed[i].action] = i == besti ? 1.0 : 0.0;
+            for (int i = 0; i < k; i++) probs[ed.ca[i].action] = i == besti ? 1.0 : 0.0;
         } else {
-            for (int i = 0; i < k; i++) probs[ed[i].action] = MC_DDIV(probs[ed[i].action], sum);   // :95-96
+            for (int i = 0; i < k; i++) probs[ed.ca[i].action] = MC_DDIV(probs[ed.ca[i].action], sum);   // :95-96
         }
     }
     (void)dscratch;
@@ -1218,18 +1307,18 @@ SPL_D void mcts_policy_tree(const W& w, const MctsArena& A, int t, double temp, 
 template <int N, class W>
 SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, double temp, uint32_t episode, bool* finished) {
     const MctsTree* T = A.trees + t;
-    const bool fin = T->root >= 0 && (T->sims_done >= T->sims_target || T->status != 0u);
+    const bool fin = T->root != 0u && (T->sims_done >= T->sims_target || T->status != 0u);
     *finished = fin;
     if (!fin) return -1;
-    const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+    const MctsNode* nd = mcts_node(A, T->root);
     if (nd->kind != MCTS_NODE_EXPANDED) return -1;
-    const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
     const int k = nd->n_edges;
+    const MctsEdges ed = mcts_edges(A, T->root, k);
     const bool forced = (T->flags & MCTS_F_FORCED) != 0u;
     int action = -1;
     if (w.lane == 0) {
         int best = 0;
-        for (int i = 0; i < k; i++) best = ed[i].N > best ? ed[i].N : best;
+        for (int i = 0; i < k; i++) best = ed.pn[i].N > best ? ed.pn[i].N : best;
         double sum = 0.0, bestc = -1.0;
         int besti = -1;
         for (int pass = 0; pass < 2; pass++) {      // pass 0: total weight, pass 1: the walk up to u * total
@@ -1240,9 +1329,10 @@ SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSear
                 target = MC_DMUL(mcts_u01(r.v[0], r.v[1]), sum);
             }
             for (int i = 0; i < k; i++) {
-                double c = (double)ed[i].N;
+                const MctsPN e = ed.pn[i];
+                double c = (double)e.N;
                 if (forced) {   // policy target pruning :69-74
-                    if (ed[i].N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)ed[i].P), (double)T->sims_target));
+                    if (e.N != best) c = c - (double)(long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)T->sims_target));
                     c = c > 1.0 ? c : 0.0;
                 }
                 if (pass == 0 && c > bestc) { bestc = c; besti = i; }
@@ -1250,12 +1340,12 @@ SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSear
                 if (pass == 0) sum = MC_DADD(sum, c);
                 else {
                     acc = MC_DADD(acc, c);
-                    if (c > 0.0) action = (int)ed[i].action;      // the last action with weight, should rounding leave acc <= target at the end
+                    if (c > 0.0) action = (int)ed.ca[i].action;      // the last action with weight, should rounding leave acc <= target at the end
                     if (acc > target) break;
                 }
             }
         }
-        if (temp == 0.0 && besti >= 0 && bestc > 0.0) action = (int)ed[besti].action;
+        if (temp == 0.0 && besti >= 0 && bestc > 0.0) action = (int)ed.ca[besti].action;
     }
     action = w.shfl(action, 0);
     return action;
@@ -1273,14 +1363,16 @@ SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* 
     w.sync();
     int ns = 0;
     float qs = 0.f;
-    if (T->root >= 0) {
-        const MctsNode* nd = A.nodes + (size_t)t * A.cap + T->root;
+    if (T->root != 0u) {
+        const MctsNode* nd = mcts_node(A, T->root);
         if (nd->kind == MCTS_NODE_EXPANDED) {
-            const MctsEdge* ed = A.edges + (size_t)t * A.ecap + nd->edge_off;
-            for (int i = w.lane; i < (int)nd->n_edges; i += W::W) {
-                if (nsa) nsa[ed[i].action] = ed[i].N;
-                if (qsa) qsa[ed[i].action] = ed[i].Q;
-                if (ps) ps[ed[i].action] = ed[i].P;
+            const int k = (int)nd->n_edges;
+            const MctsEdges ed = mcts_edges(A, T->root, k);
+            for (int i = w.lane; i < k; i += W::W) {
+                const int a = ed.ca[i].action;
+                if (nsa) nsa[a] = ed.pn[i].N;
+                if (qsa) qsa[a] = ed.Q[i];
+                if (ps) ps[a] = ed.pn[i].P;
             }
             ns = nd->u.x.Ns; qs = nd->u.x.Qs;
         }
@@ -1292,6 +1384,8 @@ SPL_D void mcts_root_stats_tree(const W& w, const MctsArena& A, int t, int32_t* 
         memcpy(&info[8], T->last_v, 16);
         info[12] = T->depth_sum;
         info[13] = T->spec_hits;
+        info[14] = T->n_dropped;     // nodes exact cleanings dropped: n_nodes + n_dropped = size of the reference's dictionary
+        info[15] = T->n_pages;
     }
     w.sync();
 }

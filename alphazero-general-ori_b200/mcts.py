@@ -30,21 +30,29 @@ def _ptr(t):
 class MCTSArena:
     def __init__(self, n_players, n_trees, node_cap, edge_cap=None, device=0, cpuct=1.0, fpu=0.0, temperature0=1.0,
                  dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, rounds=1, max_levels=0, token_limit=10,
-                 rule_flags=nat.RULES_DEFAULT):
+                 rule_flags=nat.RULES_DEFAULT, pool_nodes=None, pool_bytes=None):
+        """node_cap: the most nodes ONE tree may hold (its hash table is sized for it). The node records themselves come from a
+        page pool all trees share: `pool_nodes` records per tree on average (default node_cap, i.e. every tree can reach its
+        limit at once; production sizes it for the average tree - a tree is retired whenever a real move reveals a card) with
+        `edge_cap` edges per tree on average (default 24 per pooled node); or give `pool_bytes` directly."""
         if not torch.cuda.is_available():
             raise RuntimeError("MCTSArena needs a CUDA device (sm_100a); there is no CPU fallback")
         self.n, self.T = int(n_players), int(n_trees)
         self.R, self.S = rows(self.n), 7 * rows(self.n)
         self.device = torch.device("cuda", device)
         self.node_cap = int(node_cap)
-        self.edge_cap = int(edge_cap) if edge_cap else self.node_cap * 40
+        self.pool_nodes = int(pool_nodes) if pool_nodes else self.node_cap
+        self.edge_cap = int(edge_cap) if edge_cap else self.pool_nodes * 24
         self._lib = nat.lib()
         h = C.c_void_p()
         nat.check(self._lib.spl_ctx_create(self.n, token_limit, rule_flags, device, C.byref(h)))
         self._ctx = h
-        nbytes = self._lib.spl_mcts_arena_bytes(self.n, self.T, self.node_cap, self.edge_cap)
+        if pool_bytes is None:
+            pool_bytes = self.T * (self.pool_nodes * self._lib.spl_mcts_record_bytes(self.n, 0) + self.edge_cap * 24) + (2 * self.T + 64) * 32768
+        self.pool_bytes = int(pool_bytes)
+        nbytes = self._lib.spl_mcts_arena_bytes(self.n, self.T, self.node_cap, self.pool_bytes)
         with torch.cuda.device(self.device):
-            self.arena = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self.arena = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)      # spl_mcts_reset initialises what needs it
             off = (-self.arena.data_ptr()) % 256
             self._arena_ptr = self.arena.data_ptr() + off
             self.leaf_states = torch.zeros((self.T, self.R, 7), dtype=torch.int8, device=self.device)
@@ -52,7 +60,7 @@ class MCTSArena:
             self.leaf_flags = torch.zeros(self.T, dtype=torch.uint8, device=self.device)
             self.counters = torch.zeros(2, dtype=torch.int32, device=self.device)
         m = C.c_void_p()
-        nat.check(self._lib.spl_mcts_create(self._ctx, self.T, self.node_cap, self.edge_cap, C.c_void_p(self._arena_ptr), nbytes, C.byref(m)))
+        nat.check(self._lib.spl_mcts_create(self._ctx, self.T, self.node_cap, self.pool_bytes, C.c_void_p(self._arena_ptr), nbytes, C.byref(m)))
         self._m = m
         self.arena_bytes = nbytes
         self.params = dict(cpuct=cpuct, fpu=fpu, temperature0=temperature0, dirichlet_alpha=dirichlet_alpha, seed=seed,
@@ -79,6 +87,19 @@ class MCTSArena:
         self.params.update(kw)
         p = nat.MctsParams(**{k: self.params[k] for k, _ in nat.MctsParams._fields_})
         nat.check(self._lib.spl_mcts_set_params(self._m, C.byref(p)))
+
+    def set_episodes(self, episodes):
+        """the lanes' episode counters (int32 / uint32 [T] device tensor, read at every begin): part of the key of the on-device
+        Dirichlet sampler, so that every episode of a lane draws fresh root noise (the reference draws rng.dirichlet per move)"""
+        assert episodes is None or (episodes.is_cuda and episodes.numel() == self.T and episodes.element_size() == 4)
+        self._episodes = episodes
+        nat.check(self._lib.spl_mcts_set_episodes(self._m, _ptr(episodes)))
+
+    def pool_stats(self):
+        """-> dict(pages, free, min_free, page_bytes) of the shared page pool (host sync)"""
+        out = (C.c_int32 * 4)()
+        nat.check(self._lib.spl_mcts_pool_stats(self._m, out, self._stream()))
+        return dict(pages=int(out[0]), free=int(out[1]), min_free=int(out[2]), page_bytes=int(out[3]))
 
     def set_rules(self, token_limit=10, rule_flags=nat.RULES_DEFAULT):
         nat.check(self._lib.spl_ctx_set_rules(self._ctx, token_limit, rule_flags))
@@ -281,14 +302,15 @@ class MCTSArena:
         self.launches += 1
         return dict(nsa=nsa, qsa=qsa, ps=ps, nodes=info[:, 0], edges=info[:, 1], ns=info[:, 2], sims_done=info[:, 3],
                     nn_calls=info[:, 4], status=info[:, 5] & 0xFF, truncated=info[:, 5] >> 8, resets=info[:, 6] >> 16, cleanings=info[:, 6] & 0xFFFF,
-                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32), depth_sum=info[:, 12], spec_hits=info[:, 13])
+                    qs=info[:, 7].contiguous().view(torch.float32), last_v=info[:, 8:8 + self.n].contiguous().view(torch.float32), depth_sum=info[:, 12], spec_hits=info[:, 13],
+                    dropped=info[:, 14], pages=info[:, 15])
 
     def check_status(self):
         st = self.root_stats(want_arrays=False)["status"]
         bad = int(st.max().item())
         if bad:
-            raise nat.NativeError(f"MCTS arena: tree status bits {bad} (1 node pool full, 2 edge pool full, 4 protocol): "
-                                  f"raise node_cap/edge_cap (now {self.node_cap}/{self.edge_cap})")
+            raise nat.NativeError(f"MCTS arena: tree status bits {bad} (1 tree at its node limit, 2 shared page pool dry, 4 protocol): "
+                                  f"raise node_cap / the pool (now {self.node_cap} nodes per tree, {self.pool_bytes} pool bytes)")
 
 
 class MCTS:

@@ -24,7 +24,7 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None):
+                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None, pool_nodes=None):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -33,10 +33,13 @@ class SelfPlayEngine:
         self.evaluator = evaluator
         self.env = SplendorEnv(n_players, n_games, device=device, seed=seed, game_base=game_base)
         self.device = self.env.device
+        # node_cap: the most nodes one tree may hold (a line of ~node_cap / num_sims moves without a revealed card); the shared page
+        # pool is sized for the average tree, pool_nodes records per lane (default: node_cap, every tree at its limit at once)
         node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
         self.arena = MCTSArena(n_players, n_games, node_cap, edge_cap, device=device, cpuct=cpuct, fpu=fpu, temperature0=temperature0,
                                dirichlet_alpha=dirichlet_alpha, seed=seed, game_base=game_base, edge_reserve=edge_reserve,
-                               gc_reachable=gc_reachable, rounds=rounds, max_levels=max_levels)
+                               gc_reachable=gc_reachable, rounds=rounds, max_levels=max_levels, pool_nodes=pool_nodes)
+        self.arena.set_episodes(self.env.episodes)      # the on-device Dirichlet sampler is keyed (seed, game, episode, ply)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed) * 1000003 + int(game_base))
         self.sims = torch.empty(n_games, dtype=torch.int32, device=self.device)
@@ -106,16 +109,18 @@ class SelfPlayEngine:
         else:
             is_full = torch.rand(T, device=self.device, generator=self.gen) < self.prob_full
             max_sims = self.num_sims
-        self.sims.copy_(torch.where(is_full, self.num_sims, self.num_sims // self.ratio_full).to(torch.int32))
+        self.sims.copy_(torch.where(is_full, self.num_sims, max(1, self.num_sims // self.ratio_full)).to(torch.int32))
         fl = (nat.MCTS_MOVE_FORCED if self.forced else 0) | (nat.MCTS_MOVE_NOISE if self.noise else 0)
         self.flags.copy_(torch.where(is_full, fl, 0).to(torch.uint8))
         self.sims_total += self.sims.sum()
         self.env.states(out=self.roots)
-        self.arena.begin(self.roots, self.sims, self.flags)
         if self.graph_waves > 0 and self._graph is None:
-            # the warm-up waves of the capture must not eat into this move's budget: capture on a scratch move first
-            self._run_waves(0)
+            # the warm-up waves of the capture are real waves: run them on a scratch search and throw its trees away, so that
+            # the first move of every lane is exactly the reference's sequential search (no extra simulations, no second noise)
             self.arena.begin(self.roots, self.sims, self.flags)
+            self._run_waves(0)
+            self.arena.reset()
+        self.arena.begin(self.roots, self.sims, self.flags)
         self._run_waves(max_sims)
         chunk = None
         if self.graph_waves > 0:

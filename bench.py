@@ -47,8 +47,10 @@ def parse():
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
     ap.add_argument("--graph-waves", type=int, default=128, help="waves per CUDA-graph replay (0: plain launches)")
     ap.add_argument("--tick-waves", type=int, default=0, help="waves between two rounds of moves (0: --graph-waves, or 16 with plain launches)")
-    ap.add_argument("--gc", default="reachable", choices=["ply", "reachable"],
-                    help="tree cleaning: ply = exact (keeps every node that could still be looked up), reachable = only what the root reaches")
+    ap.add_argument("--gc", default="exact", choices=["exact", "reachable"],
+                    help="tree cleaning: exact = drops only nodes no later search can look up again (ply + deck rule; the parity-tested mode), "
+                         "reachable = a tree at its node limit keeps only what the root reaches")
+    ap.add_argument("--pool-nodes", type=int, default=0, help="node records per tree the shared page pool is sized for (0: 4 x sims)")
     ap.add_argument("--clean-moves", type=float, default=4.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
@@ -281,11 +283,13 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     else:
         net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16)
     reach = args.gc == "reachable"
-    cap = args.node_cap or 8 * sims
+    cap = args.node_cap or 20 * sims          # node limit of ONE tree: a line of ~20 moves without a revealed card
+    pool_nodes = args.pool_nodes or 4 * sims  # the shared page pool holds this many records per tree on average
     G0 = args.tick_waves or (args.graph_waves if args.graph_waves > 0 else 16)
-    clean_every = max(1, int(args.clean_moves * sims / G0)) if args.async_moves else 0
+    # exact mode: begin retires / cleans a tree when it has to; reachable mode: periodic cleaning of the over-full trees between waves
+    clean_every = max(1, int(args.clean_moves * sims / G0)) if (args.async_moves and reach) else 0
     eng = azg.SelfPlayEngine(n, T, None, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, node_cap=cap,
-                             edge_cap=cap * 36, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels,
+                             pool_nodes=pool_nodes, gc_reachable=reach, graph_waves=args.graph_waves, rounds=args.rounds, max_levels=args.max_levels,
                              clean_every=clean_every, clean_percent=45, overlap_nnet=None if args.overlap else False, tick_graph=True)
     if args.fixed_net:
         pi_buf = torch.empty((T, 406), dtype=torch.float32, device=dev); v_buf = torch.empty((T, n), dtype=torch.float32, device=dev)
@@ -338,6 +342,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     if not args.async_moves:
         assert sims_done == T * sims * args.steps
     st = eng.arena.root_stats(want_arrays=False)
+    pool = eng.arena.pool_stats()
     truncated_now = 0 if args.async_moves else int((st["sims_done"] < sims).sum())
     value = world * sims_done / (ms_total * 1e-3)
     # our own kernels inside the timed region (graph replays re-launch the captured ones): per wave 3 x rounds selection
@@ -402,13 +407,14 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
-                   "gc": args.gc, "node_cap": cap, "graph_waves": args.graph_waves, "waves_per_tick": G, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
+                   "gc": args.gc, "node_limit_per_tree": cap, "pool_nodes_per_tree": pool_nodes, "graph_waves": args.graph_waves, "waves_per_tick": G, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
                    "moves_completed": int(eng.moves_completed.item()) if args.async_moves else args.steps * T, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
         "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
-                       "mean_nodes": float(st["nodes"].float().mean()), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
+                       "mean_nodes": float(st["nodes"].float().mean()), "max_nodes": int(st["nodes"].max()),
+                       "pool_gb": pool["pages"] * pool["page_bytes"] / 1e9, "pool_peak_fill": 1.0 - pool["min_free"] / max(1, pool["pages"]), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
                        "early_fetch_hit_rate": float(st["spec_hits"].sum()) / max(1.0, float(st["depth_sum"].sum())),
                        "games_finished": int(eng.games_finished.item()), "network_rows_per_sim": float(st["nn_calls"].sum()) / max(1, sims_now())},
     }
@@ -475,11 +481,12 @@ def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
     arena fits (tree pools scale with the budget), same kernels, same network"""
     n, T, sims = args.players, args.wide_trees, args.wide_sims
     net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
-    cap = 16 * sims     # short budgets: roomy pools are cheap (107 GB at 65,536 trees) and keep the cleaning off the path (+4 % measured)
+    cap = 32 * sims
     G = min(args.wide_tick_waves, args.graph_waves) if args.graph_waves > 0 else args.wide_tick_waves      # short budgets: look for finished lanes often
-    eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, edge_cap=cap * 36,
-                             gc_reachable=args.gc == "reachable", graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds,
-                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if args.async_moves else 0, clean_percent=45,
+    reach = args.gc == "reachable"
+    eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=cap, pool_nodes=6 * sims,
+                             gc_reachable=reach, graph_waves=G if args.graph_waves > 0 else 0, rounds=args.rounds,
+                             max_levels=args.max_levels, clean_every=max(1, int(args.clean_moves * sims / G)) if (args.async_moves and reach) else 0, clean_percent=45,
                              tick_graph=True)
     eng.env.rollout(args.opening_plies, rotate=True)
     ticks = -(-sims // G)

@@ -151,7 +151,8 @@ int spl_symmetries(spl_ctx* ctx, const int8_t* aos, const float* pi, const uint8
  *
  * One tree per game lane, one warp per tree. The reference's `nodes_data` dictionary (exact state bytes -> node; a DAG
  * with transpositions that persists across moves until reset_all_search_trees, MCTS.py:36,119-120,188-192) is a per-tree
- * node pool + hash table inside one caller-owned device buffer. A move is searched in waves:
+ * hash table over node records that all trees allocate from one shared pool of 32 KB pages, inside one caller-owned
+ * device buffer. A move is searched in waves:
  *
  *     spl_mcts_begin                      root lookup / creation, tree cleaning            (getActionProb :45-58)
  *     repeat: spl_mcts_select             descend by PUCT to an unevaluated node           (search :99-166, :199-237)
@@ -167,39 +168,49 @@ typedef struct spl_mcts spl_mcts;
 #define SPL_MCTS_MOVE_FORCED 1u   /* forced playouts + policy-target pruning for this move (:56, :69-74) */
 #define SPL_MCTS_MOVE_NOISE 2u    /* root softmax + Dirichlet noise on the first simulation (:58, :141-143, :150-154) */
 
-/* tree status bits (low byte of info[5] of spl_mcts_root_stats). A pool that fills up mid-move stops that tree's search
- * early (the policy then reflects the simulations done so far); the next spl_mcts_begin makes room, clears the bit and
- * counts the event as a truncated search. */
-#define SPL_MCTS_ST_OVERFLOW_NODES 1
-#define SPL_MCTS_ST_OVERFLOW_EDGES 2
+/* tree status bits (low byte of info[5] of spl_mcts_root_stats). A tree that reaches its node limit, or a shared pool
+ * that runs dry, mid-move stops that tree's search early (the policy then reflects the simulations done so far); the
+ * next spl_mcts_begin makes room, clears the bit and counts the event as a truncated search. */
+#define SPL_MCTS_ST_OVERFLOW_NODES 1  /* the tree holds node_limit nodes */
+#define SPL_MCTS_ST_OVERFLOW_POOL 2   /* no free page left in the shared pool */
 #define SPL_MCTS_ST_PROTOCOL 4        /* select called while a leaf was still waiting for spl_mcts_expand */
 
 typedef struct {
     double   cpuct, fpu;        /* args.cpuct, args.fpu (pick_highest_UCB :199-213) */
     double   temperature0;      /* args.temperature[0]: root softmax before the noise (:141, :244-250) */
     double   dirichlet_alpha;   /* args.dirichletAlpha (:181); used by the on-device sampler when dir_values == NULL */
-    uint64_t seed;              /* Philox key of the on-device Dirichlet sampler, counter (game, root ply, action rank) */
+    uint64_t seed;              /* Philox key of the on-device Dirichlet sampler, counter (game, episode, root ply, 16 + 128 * action rank + draw) */
     uint32_t game_base;         /* game id of tree 0 */
-    int      edge_reserve;      /* edges budgeted per new node when deciding whether to clean before a move (default 32) */
-    int      gc_reachable;      /* 0: cleaning keeps every node with ply >= root ply - result-neutral, like the reference's
-                                   own cleaning :80-85 (default); 1: keeps only what the new root reaches (smaller pools) */
+    int      edge_reserve;      /* unused (kept for layout compatibility) */
+    int      gc_reachable;      /* 0: exact cleaning (default) - drops only nodes no later search of the game can look up again:
+                                   below the root's ply (like the reference's own cleaning :80-85) or holding a deck the root's
+                                   deck is not a subset of (moves inside the tree never reveal cards, :228); result-neutral.
+                                   1: a tree at its node limit keeps only what the new root reaches (not result-neutral) */
     int      rounds;            /* (descend, rules, attach) passes per selection wave (default 1): a descent that runs into
                                    a transposition or a terminal node continues in the next pass / wave; result-neutral */
     int      max_levels;        /* edges one descend call walks before it yields to the next wave (0: no limit); bounds the
                                    wave's latency by the typical, not the deepest, path; result-neutral */
 } spl_mcts_params;
 
-/* bytes of device memory an arena needs; node_cap / edge_cap are per tree */
-size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_cap, int edge_cap);
-/* MCTS.__init__ (:21-43): `arena` is caller-owned device memory of at least spl_mcts_arena_bytes, 256-byte aligned */
-int  spl_mcts_create(spl_ctx* ctx, int n_trees, int node_cap, int edge_cap, void* arena, size_t arena_bytes, spl_mcts** out);
+/* bytes of one node record with n_edges legal actions (header + state + 24 bytes per edge, rounded to 32): for sizing the pool */
+size_t spl_mcts_record_bytes(int n_players, int n_edges);
+/* bytes of device memory an arena needs. node_limit: most nodes ONE tree may hold (sizes its hash table); pool_bytes: the page
+ * pool all trees share - size it for the AVERAGE tree (a tree is retired whenever a real move reveals a card) */
+size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes);
+/* MCTS.__init__ (:21-43): `arena` is caller-owned device memory of at least spl_mcts_arena_bytes, 256-byte aligned.
+ * Call spl_mcts_reset(m, NULL, stream) once before the first spl_mcts_begin (it fills the ring of free pages). */
+int  spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, void* arena, size_t arena_bytes, spl_mcts** out);
+/* the lanes' episode counters (device uint32[T], read by spl_mcts_begin; may be NULL = 0): part of the key of the on-device
+ * Dirichlet sampler, so that every episode of a lane draws its own root noise */
+int  spl_mcts_set_episodes(spl_mcts* m, const uint32_t* episodes);
+/* out4 (HOST int32[4]): pages in the pool, free now, fewest free since the last full reset, bytes per page (synchronises) */
+int  spl_mcts_pool_stats(spl_mcts* m, int32_t* out4, void* stream);
 void spl_mcts_destroy(spl_mcts* m);
 int  spl_mcts_set_params(spl_mcts* m, const spl_mcts_params* p);
 /* reset_all_search_trees (:188-192); tree_select (may be NULL) restricts it to trees with a non-zero byte */
 int  spl_mcts_reset(spl_mcts* m, const uint8_t* tree_select, void* stream);
-/* cleaning between waves, in any state of the search: every tree whose node or edge pool is filled beyond fill_percent drops
- * what it can no longer use (per gc_reachable) and re-bases the simulation in flight. All trees that need it clean in the
- * same launch - the way to keep the serial per-tree compaction off the critical path of spl_mcts_begin. */
+/* cleaning between waves, in any state of the search: every tree that holds more than fill_percent of node_limit copies what
+ * it can still use (per gc_reachable) into fresh pages, gives the old ones back and re-bases the simulation in flight. */
 int  spl_mcts_clean(spl_mcts* m, int fill_percent, void* stream);
 /* start of getActionProb for every (selected) tree: roots int8[T][R*7] canonical boards, sims int32[T] simulation budget
  * (numMCTSSims or numMCTSSims // ratio_fullMCTS, :55), move_flags uint8[T] of SPL_MCTS_MOVE_* */

@@ -13,6 +13,7 @@ struct HsMcts {
     MctsArena A;
     MctsSearchParams P;
     int edge_reserve, gc_reachable;
+    uint32_t episode;
     int clean_every, clean_gc, clean_counter;   // test hook: clean in the middle of a search every N driver steps
     int8_t* leaf_state;
     uint8_t* leaf_valid;
@@ -22,28 +23,37 @@ struct HsMcts {
 template <int N>
 static void hm_step_rules(HsMcts* m, int8_t* st, bool* ended, float* es, uint32_t* mask) {
     const MctsTree& T = m->A.trees[0];
-    memcpy(st, m->A.states + (size_t)T.pend_parent * m->A.sp, m->A.sp);
+    memcpy(st, mcts_state(m->A, T.pend_parent), m->A.sp);
     AosAcc s{st};
-    *ended = mcts_rules_core<N>(s, (int)m->A.edges[T.pend_edge].action, m->P.rules, es, mask);
+    const int action = (int)mcts_edges(m->A, T.pend_parent, T.pend_edge >> 16).ca[T.pend_edge & 0xFFFF].action;
+    *ended = mcts_rules_core<N>(s, action, m->P.rules, es, mask);
 }
 
 extern "C" {
+// cap: node limit of the tree; pool_nodes: how many average-size records the page pool holds (0: cap)
 HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, double cpuct, double fpu, double temperature0, int edge_reserve, int gc_reachable) {
     HsMcts* m = (HsMcts*)calloc(1, sizeof *m);
     m->n = n;
     MctsArena& A = m->A;
-    A.n_trees = 1; A.cap = cap; A.ecap = ecap;
-    A.hcap = 1; while (A.hcap < 2 * cap) A.hcap *= 2;
+    A.n_trees = 1; A.node_limit = cap;
+    A.hcap = 64; while (A.hcap < 2 * cap) A.hcap *= 2;
     A.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
     A.max_depth = 62 * n + 8;
-    A.states = (int8_t*)aligned_alloc(16, (size_t)cap * A.sp);
-    A.nodes = (MctsNode*)calloc(cap, sizeof(MctsNode));
-    A.edges = (MctsEdge*)calloc(ecap, sizeof(MctsEdge));
-    A.htab = (uint32_t*)calloc(A.hcap, 4);
+    const size_t pool_bytes = (size_t)cap * (32 + A.sp) + (size_t)ecap * 24;
+    A.n_pool_pages = (uint32_t)(pool_bytes / (MCTS_PAGE_UNITS * MCTS_UNIT)) + 4;
+    A.max_pages = 2 * (int)A.n_pool_pages;
+    A.pool = (uint8_t*)aligned_alloc(256, (size_t)A.n_pool_pages * MCTS_PAGE_UNITS * MCTS_UNIT);
+    A.fq_slots = (uint32_t*)calloc(A.n_pool_pages, 4);
+    A.fq_ctl = (int32_t*)calloc(4, 4);
+    for (uint32_t p = 1; p < A.n_pool_pages; p++) A.fq_slots[p - 1] = p;
+    A.fq_ctl[0] = 0; A.fq_ctl[1] = (int32_t)A.n_pool_pages - 1; A.fq_ctl[2] = (int32_t)A.n_pool_pages - 1; A.fq_ctl[3] = A.fq_ctl[2];
+    A.tree_pages = (uint32_t*)calloc(A.max_pages, 4);
+    A.htab = (uint32_t*)aligned_alloc(16, (size_t)A.hcap * 4);
+    memset(A.htab, 0, (size_t)A.hcap * 4);
     A.trees = (MctsTree*)calloc(1, sizeof(MctsTree));
     A.path = (uint32_t*)calloc((size_t)A.max_depth * 2, 4);
     A.leaf_src = (uint8_t*)calloc(1, 1);
-    A.trees[0].root = -1; A.trees[0].leaf = -1;
+    A.trees[0].pend_edge = -1;
     m->P.cpuct = cpuct; m->P.fpu = fpu; m->P.temperature0 = temperature0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules.limit = limit; m->P.rules.flags = rule_flags;
     m->edge_reserve = edge_reserve; m->gc_reachable = gc_reachable;
@@ -54,9 +64,11 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     return m;
 }
 void hm_destroy(HsMcts* m) {
-    free(m->A.states); free(m->A.nodes); free(m->A.edges); free(m->A.htab); free(m->A.trees); free(m->A.path); free(m->A.leaf_src);
+    free(m->A.pool); free(m->A.fq_slots); free(m->A.fq_ctl); free(m->A.tree_pages); free(m->A.htab); free(m->A.trees); free(m->A.path); free(m->A.leaf_src);
     free(m->leaf_state); free(m->leaf_valid); free(m->pi); free(m->v); free(m);
 }
+int hm_free_pages(HsMcts* m) { return m->A.fq_ctl[2]; }
+int hm_total_pages(HsMcts* m) { return (int)m->A.n_pool_pages - 1; }
 void hm_reset(HsMcts* m) {
     MctsWarp w{0};
     mcts_clear_tree(w, m->A, 0);
@@ -68,15 +80,16 @@ static void hm_maybe_clean(HsMcts* m) {
     if (m->clean_every <= 0) return;
     if (++m->clean_counter % m->clean_every) return;
     MctsWarp w{0};
-    mcts_clean_tree(w, m->A, 0, 0, 0, m->clean_gc);      // thresholds 0: always compacts
+    mcts_clean_tree(w, m->A, 0, 0, m->clean_gc);      // threshold 0: always compacts
 }
+void hm_set_episode(HsMcts* m, uint32_t e) { m->episode = e; }
 void hm_set_clean(HsMcts* m, int every, int gc_reachable) { m->clean_every = every; m->clean_gc = gc_reachable; m->clean_counter = 0; }
 int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const double* dir) {
     MctsWarp w{0};
     alignas(16) int8_t st[640];
     uint32_t scratch[24];
     double dscratch[4];
-    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->edge_reserve, m->gc_reachable, dir, st, scratch, dscratch));
+    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->gc_reachable, dir, m->episode, st, scratch, dscratch));
     for (;;) {
         int r = 0;
         DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid));

@@ -109,6 +109,9 @@ def lib_mcts():
         L.hm_policy.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.hm_root_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.hm_set_clean.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hm_set_episode.argtypes = [C.c_void_p, C.c_uint32]
+        L.hm_free_pages.argtypes = [C.c_void_p]
+        L.hm_total_pages.argtypes = [C.c_void_p]
         L.hm_fixed_net.argtypes = [C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _lib_mcts = L
     return _lib_mcts
@@ -120,7 +123,8 @@ class TreeSim:
     def __init__(self, n, num_sims, cpuct=1.0, fpu=0.0, forced_playouts=False, dirichlet_noise=False, ratio_full=5,
                  temperature0=1.0, cap=4096, ecap=None, edge_reserve=32, gc_reachable=False, limit=10, flags=F_RESERVE | F_GIVEBACK | F_REFCOMPAT):
         self.n, self.num_sims, self.forced, self.noise, self.ratio = n, num_sims, forced_playouts, dirichlet_noise, ratio_full
-        self._h = lib_mcts().hm_create(n, cap, ecap or cap * 48, limit, flags, cpuct, fpu, temperature0, edge_reserve, int(gc_reachable))   # gc_reachable: 0 ply rule, 1 reachable, 2 reachable, in place only
+        # cap: node limit of the tree; the page pool holds cap records with ecap edges in all (default 48 per node)
+        self._h = lib_mcts().hm_create(n, cap, ecap or cap * 48, limit, flags, cpuct, fpu, temperature0, edge_reserve, int(gc_reachable))   # gc_reachable: 0 exact rule, 1 reachable
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -129,6 +133,13 @@ class TreeSim:
 
     def reset(self):
         lib_mcts().hm_reset(self._h)
+
+    def free_pages(self):
+        """(free, total) pages of the shared pool"""
+        return lib_mcts().hm_free_pages(self._h), lib_mcts().hm_total_pages(self._h)
+
+    def set_episode(self, e):
+        lib_mcts().hm_set_episode(self._h, int(e))
 
     def set_clean(self, every, gc_reachable=False):
         """test hook: run the between-waves cleaning every `every` driver steps, whatever the search is doing"""
@@ -145,7 +156,7 @@ class TreeSim:
         nsa = np.zeros(406, dtype=np.int32); qsa = np.zeros(406); ps = np.zeros(406, dtype=np.float32); info = np.zeros(16, dtype=np.int32)
         lib_mcts().hm_root_stats(self._h, _p(nsa, C.c_int32), _p(qsa, C.c_double), _p(ps, C.c_float), _p(info, C.c_int32))
         return dict(probs=probs, q=q, nsa=nsa.astype(np.int64), qsa=qsa, ps=ps, ns=int(info[2]), qs=info[7:8].view(np.float32)[0],
-                    nodes=int(info[0]), edges=int(info[1]), nn_calls=int(info[4]), status=status, truncated=int(info[5]) >> 8, resets=int(info[6]) >> 16,
+                    nodes=int(info[0]), edges=int(info[1]), dropped=int(info[14]), pages=int(info[15]), nn_calls=int(info[4]), status=status, truncated=int(info[5]) >> 8, resets=int(info[6]) >> 16,
                     compactions=int(info[6]) & 0xFFFF)
 
 
