@@ -81,11 +81,11 @@ class SplendorEnv:
         self.launches += 1
         self._keep = aos
 
-    def states(self, out=None):
+    def states(self, out=None, planes=None):
         """-> int8[L, R, 7] device tensor in the reference's layout"""
         if out is None:
             out = torch.empty((self.L, self.R, 7), dtype=torch.int8, device=self.device)
-        nat.check(self._lib.spl_unpack(self._ctx, _ptr(self.planes), _ptr(out), self.L, self._stream()))
+        nat.check(self._lib.spl_unpack(self._ctx, _ptr(self.planes if planes is None else planes), _ptr(out), self.L, self._stream()))
         self.launches += 1
         return out
 
@@ -125,15 +125,28 @@ class SplendorEnv:
         self.players.zero_()
 
     # ------------------------------------------------------------------ one ply for every lane
+    def canonical(self, out=None, players=None, ended_out=None):
+        """getCanonicalForm (SplendorGame.py:51-57) of every lane for its player to move (`players` uint8[L], default
+        self.players) WITHOUT touching the stored states: a scratch copy of the lane tiles is rotated and unpacked.
+        Also leaves getValidMoves(canonical, 0) in self.masks. For callers that keep the boards in the absolute seat order
+        like the reference's Coach / Arena do (with more than two players the reference's rotation is not equivariant -
+        SURVEY F7a -, so a board that is rotated after every move is not the board the reference would have)."""
+        if getattr(self, "_scratch", None) is None:
+            self._scratch = torch.empty_like(self.planes)
+        self._scratch.copy_(self.planes)
+        self.step(None, players=self.players if players is None else players, rotate=True, want_ended=ended_out is not None, want_status=False,
+                  planes=self._scratch, ended_out=ended_out)
+        return self.states(out, planes=self._scratch)
+
     def step(self, actions=None, players=None, player=0, chance="philox", reveals=None, rotate=False,
              auto_reset=False, store_state=True, want_mask=True, want_ended=True, want_next=False,
-             want_status=True, count=False):
+             want_status=True, count=False, planes=None, ended_out=None):
         """actions int16[L] (None / negative: query only). players uint8[L] or a single `player`.
         Returns nothing; results are in self.masks / self.ended / self.next_actions / self.status."""
         mode = {"det": nat.CHANCE_DETERMINISTIC, "deterministic": nat.CHANCE_DETERMINISTIC,
                 "replay": nat.CHANCE_REPLAY, "philox": nat.CHANCE_PHILOX}[chance]
         a = nat.StepArgs()
-        a.planes = self.planes.data_ptr(); a.n_lanes = self.L
+        a.planes = (self.planes if planes is None else planes).data_ptr(); a.n_lanes = self.L
         self._hold = (actions, players, reveals)
         a.actions = None if actions is None else actions.data_ptr()
         a.players = None if players is None else players.data_ptr()
@@ -143,7 +156,7 @@ class SplendorEnv:
         a.episodes = self.episodes.data_ptr()
         a.rotate = int(rotate); a.auto_reset = int(auto_reset); a.store_state = int(store_state)
         a.mask_out = self.masks.data_ptr() if want_mask else None
-        a.ended_out = self.ended.data_ptr() if want_ended else None
+        a.ended_out = (self.ended if ended_out is None else ended_out).data_ptr() if want_ended else None
         a.next_actions = self.next_actions.data_ptr() if want_next else None
         a.status_out = self.status.data_ptr() if want_status else None
         a.counters = self.counters.data_ptr() if count else None

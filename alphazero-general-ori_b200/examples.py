@@ -64,10 +64,11 @@ class ExampleBuffer:
         self.player[lanes, slot] = self.cur_player[sel]
         self.count += sel.to(torch.int64)
 
-    def advance(self, ended, scores, moved=None):
+    def advance(self, ended, scores, moved=None, absolute=False):
         """after the move: ended float32[T,n] (getGameEnded in the new canonical frame), scores int32[T,n] (getScore of
         the stored state, same frame). Finished lanes hand their examples over and start a new game at seat 0.
-        moved bool[T] (None = all): the lanes that actually made a move in this call."""
+        moved bool[T] (None = all): the lanes that actually made a move in this call.
+        absolute: ended / scores are in the absolute seat order (the boards are kept like Coach keeps them, Coach.py:86-98)."""
         n = self.n
         if moved is None:
             self.cur_player = (self.cur_player + 1) % n
@@ -75,13 +76,18 @@ class ExampleBuffer:
         else:
             self.cur_player = torch.where(moved, (self.cur_player + 1) % n, self.cur_player)
             done = moved & (ended != 0).any(dim=1)
+        return self.finish(done, ended, scores, absolute)
+
+    def finish(self, done, ended, scores, absolute=False):
+        """the lanes in `done` hand the examples of their game over (winner / score difference per Coach.py:89-98) and start anew"""
         if bool(done.any()):
             lanes = self._lane[done]
             cnt = self.count[lanes]
             m = torch.arange(self.M, device=self.device).view(1, -1) < cnt.view(-1, 1)          # [D, M]
             li = lanes.view(-1, 1).expand(-1, self.M)[m]
             si = torch.arange(self.M, device=self.device).view(1, -1).expand(lanes.numel(), -1)[m]
-            winner, scdiff = finalize_examples(self.player[li, si], ended[li], scores[li].to(torch.int32), self.cur_player[li])
+            c_final = torch.zeros_like(self.cur_player[li]) if absolute else self.cur_player[li]
+            winner, scdiff = finalize_examples(self.player[li, si], ended[li], scores[li].to(torch.int32), c_final)
             self.finished.append(dict(board=self.board[li, si].clone(), pi=self.pi[li, si].clone(), winner=winner, scdiff=scdiff,
                                       valids=self.valids[li, si].clone(), surprise=self.surprise[li, si].clone()))
             self.count[lanes] = 0
@@ -150,3 +156,43 @@ def to_coach_format(ex, compress=True):
              [float(x) for x in host["surprise"][i]])
         out.append(zlib.compress(pickle.dumps(t), level=1) if compress else t)
     return out
+
+
+def save_train_examples(history, folder, filename="checkpoint.examples"):
+    """Coach.saveTrainExamples (Coach.py:167-173): `history` = trainExamplesHistory, a list (one entry per iteration) of
+    lists / deques of examples in Coach's form (tuples, or their zlib+pickle bytes) -> pickle file the reference loads"""
+    import os
+    os.makedirs(folder, exist_ok=True)
+    path = os.path.join(folder, filename)
+    with open(path, "wb") as f:
+        pickle.dump(history, f)
+    return path
+
+
+def load_train_examples(path, no_compression=False, num_iters_history=None, maxlen_of_queue=None):
+    """Coach.loadTrainExamples (Coach.py:175-208): reads the pickled history, harmonises the compression of its items with
+    `no_compression` (tuples <-> zlib+pickle bytes) and applies the two trims (latest iterations, items per iteration)"""
+    with open(path, "rb") as f:
+        hist = pickle.load(f)
+    if hist and len(hist[0]) > 0:
+        is_tuple = type(hist[0][0]) is tuple
+        if is_tuple and not no_compression:
+            hist = [type(h)(zlib.compress(pickle.dumps(x), level=1) for x in h) for h in hist]
+        elif not is_tuple and no_compression:
+            hist = [type(h)(pickle.loads(zlib.decompress(x)) for x in h) for h in hist]
+    if num_iters_history is not None and len(hist) > num_iters_history:
+        hist = hist[-num_iters_history:]
+    if maxlen_of_queue is not None:
+        for h in hist:
+            while len(h) > maxlen_of_queue:
+                h.pop()
+    return hist
+
+
+def from_coach_format(items, device="cpu"):
+    """the inverse of to_coach_format: Coach's example tuples (or their zlib+pickle bytes) -> dict of tensors (FIELDS)"""
+    rows = [pickle.loads(zlib.decompress(x)) if isinstance(x, (bytes, bytearray)) else x for x in items]
+    if not rows:
+        raise ValueError("no examples")
+    f = lambda i, dt: torch.from_numpy(np.stack([np.asarray(r[i]) for r in rows]).astype(dt)).to(device)
+    return dict(board=f(0, np.int8), pi=f(1, np.float32), winner=f(2, np.float32), scdiff=f(3, np.int32), valids=f(4, np.uint8), surprise=f(5, np.float32))

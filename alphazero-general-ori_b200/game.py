@@ -208,6 +208,16 @@ class SplendorGame:
     def moveToString(self, move, current_player):
         return move_to_str(move)
 
+    def printBoard(self, numpy_board):
+        """SplendorGame.py:72-75 -> print_board (SplendorLogic.py:600-607): round and scores, nobles, the three tiers with their deck
+        sizes, the bank, then gems / cards / reserved cards of every player - the same content in plain text (no console colours)"""
+        print(board_to_text(np.asarray(numpy_board, dtype=np.int8), self.num_players, self))
+
+    def getNobleGemIDs(self, board):
+        """SplendorGame.py:77-80 prints the nobles rows of `board.nobles` and returns None"""
+        print("nobles: ", np.asarray(board.state if hasattr(board, "state") else board)[31:32 + self.num_players])
+        return None
+
     def disableReserve(self):
         self.board.ENABLE_ACTION_RESERVE = False
 
@@ -259,6 +269,42 @@ class SplendorGame:
 
 
 _COLORS = ["white", "blue", "green", "red", "black"]
+_SHORT = ["W", "U", "G", "R", "K", "gold"]
+
+
+def _card_text(cost, gain):
+    if int(gain[:5].sum()) == 0:
+        return "-"
+    col = _SHORT[int(np.flatnonzero(gain[:5] != 0)[0])]
+    price = " ".join(f"{int(cost[c])}{_SHORT[c]}" for c in range(5) if cost[c] != 0)
+    return f"[{col} {int(gain[6])}pt: {price}]"
+
+
+def board_to_text(state, n, game=None):
+    """the content of print_board (SplendorLogic.py:476-607) for a state in the reference's int8[R,7] layout"""
+    R0 = 32 + n
+    gems, nobles_p, cards, res = R0, R0 + n, R0 + 2 * n + n * n, R0 + 3 * n + n * n
+    lines = []
+    scores = [game.getScore(state, p) if game is not None else int(state[cards + p, 6]) for p in range(n)]
+    lines.append(f"Round {int(np.uint8(state[0, 6])) // n} (ply {int(np.uint8(state[0, 6]))})  scores: " + "  ".join(f"P{p}={scores[p]}" for p in range(n)))
+    nb = []
+    for i in range(n + 1):
+        row = state[31 + i]
+        nb.append("< empty >" if row[6] == 0 else "< %d points %s >" % (int(row[6]), " ".join(f"{int(row[c])}{_SHORT[c]}" for c in range(5) if row[c] != 0)))
+    lines.append("Nobles:  " + " ".join(nb))
+    for tier in (2, 1, 0):
+        deck = int(state[25 + 2 * tier, :5].sum())
+        cs = [_card_text(state[1 + 8 * tier + 2 * i], state[2 + 8 * tier + 2 * i]) for i in range(4)]
+        lines.append(f"Tier {tier} ({deck:2d} in deck): " + "  ".join(cs))
+    lines.append("Bank:    " + " ".join(f"{int(state[0, c])}{_SHORT[c]}" for c in range(6)))
+    for p in range(n):
+        g = state[gems + p]
+        own = [int(r[6]) for r in state[nobles_p + 3 * p: nobles_p + 3 * p + 3] if r[6] > 0]       # the reference reads a stride of 3 (:562)
+        rs = [_card_text(state[res + 6 * p + 2 * r], state[res + 6 * p + 2 * r + 1]) for r in range(3) if int(state[res + 6 * p + 2 * r].sum()) != 0]
+        lines.append(f"Player {p}: gems " + " ".join(f"{int(g[c])}{_SHORT[c]}" for c in range(6)) + f" (sum {int(g[:6].sum())})  cards " +
+                     " ".join(f"{int(state[cards + p, c])}{_SHORT[c]}" for c in range(5)) + (f"  nobles {own}" if own else "") +
+                     ("  reserved " + " ".join(rs) if rs else ""))
+    return "\n".join(lines)
 
 
 def move_to_str(move):

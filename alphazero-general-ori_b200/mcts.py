@@ -215,7 +215,7 @@ class MCTSArena:
         pi, v = evaluator(self.leaf_states, self.leaf_valids)
         self.expand(pi, v, dir_values)
 
-    def finish(self, evaluator, dir_values=None, chunk=None, max_extra=100000):
+    def finish(self, evaluator, dir_values=None, chunk=None, max_extra=100000):  # noqa: C901
         """waves until every tree has spent its budget. One host synchronisation per `chunk()` call (default: 8 waves);
         returns the number of extra waves."""
         extra = 0
@@ -336,8 +336,12 @@ class MCTS:
         temperature0 = 1.0
         if dirichlet_noise:
             temperature0 = float(args.temperature[0])
+        try:      # pit.py's args (utils.dotdict: a missing key raises KeyError, not AttributeError) carry no dirichletAlpha
+            alpha = float(args.dirichletAlpha or 0.3)
+        except (AttributeError, KeyError):
+            alpha = 0.3
         self._arena = MCTSArena(n, 1, node_cap or max(4096, 10 * sims), device=dev, cpuct=float(args.cpuct), fpu=float(args.fpu),
-                                temperature0=temperature0, dirichlet_alpha=float(getattr(args, "dirichletAlpha", 0.3) or 0.3),
+                                temperature0=temperature0, dirichlet_alpha=alpha,
                                 token_limit=limit, rule_flags=flags)
         self._dev = self._arena.device
         self._root = torch.zeros((1, self._arena.R, 7), dtype=torch.int8, device=self._dev)

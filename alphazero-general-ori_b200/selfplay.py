@@ -24,7 +24,8 @@ class SelfPlayEngine:
     def __init__(self, n_players, n_games, evaluator, num_sims, device=0, seed=0, game_base=0, cpuct=1.0, fpu=0.0,
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
-                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None, pool_nodes=None):
+                 max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None, pool_nodes=None,
+                 absolute=None):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -33,6 +34,11 @@ class SelfPlayEngine:
         self.evaluator = evaluator
         self.env = SplendorEnv(n_players, n_games, device=device, seed=seed, game_base=game_base)
         self.device = self.env.device
+        # How the boards are kept. Two players: always canonical (rotated after every move, one fused launch per move). More
+        # players: in the absolute seat order with a player-to-move per lane, like Coach / Arena keep them, and canonical copies
+        # are made for the search - the reference's rotation of the noble rows is not equivariant for n >= 3, so
+        # only this reproduces the boards, end-of-game checks and examples of the reference's callers.
+        self.absolute = (n_players > 2) if absolute is None else bool(absolute)
         # node_cap: the most nodes one tree may hold (a line of ~node_cap / num_sims moves without a revealed card); the shared page
         # pool is sized for the average tree, pool_nodes records per lane (default: node_cap, every tree at its limit at once)
         node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
@@ -72,7 +78,56 @@ class SelfPlayEngine:
         self.overlap_nnet = fused if self._overlap_req is None else (bool(self._overlap_req) and fused)
 
     # ------------------------------------------------------------------
+    def _roots(self):
+        """canonical boards of all lanes -> self.roots (Coach.py:73)"""
+        if not self.absolute:
+            return self.env.states(out=self.roots)
+        if not hasattr(self, "_ended_canon"):
+            self._ended_canon = torch.zeros((self.T, self.n), dtype=torch.float32, device=self.device)
+        self.env.canonical(self.roots, ended_out=self._ended_canon)
+        # With the reference's n >= 3 quirks the end-of-game check of a rotated board can disagree with the check of the board in
+        # seat order (get_score reads the noble rows with the wrong stride after a rotation, SURVEY F7a). The reference's Coach
+        # crashes there (the search of a finished position returns no visits); here such a game ends with the rotated board's result.
+        stuck = (self._ended_canon != 0).any(dim=1)
+        if self.examples is not None:
+            i = torch.arange(self.n, device=self.device).view(1, -1)
+            back = (i - self.env.players.view(-1, 1).to(torch.int64)) % self.n       # seat i sits at canonical index (i - p)
+            scores, _ = self.env.scores()
+            self.examples.finish(stuck, torch.gather(self._ended_canon, 1, back), scores, absolute=True)
+        self._restart(stuck)
+        self.env.canonical(self.roots)
+
+    def _valids(self):
+        """getValidMoves(canonical, 0) of all lanes (Coach.py:77)"""
+        if not self.absolute:
+            self.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
+        return self.env.valids()          # (absolute: left there by env.canonical)
+
+    def _move(self, chance="philox", reveals=None):
+        """the real move of every lane (self.actions, negative = none): getNextState + getGameEnded (Coach.py:86-88)"""
+        if self.absolute:
+            pl = self.env.players
+            self.env.step(self.actions, players=pl, chance=chance, reveals=reveals, rotate=False, auto_reset=False, want_mask=False,
+                          want_status=True, count=True)
+            st = self.env.status
+            pl.copy_(torch.where((self.actions >= 0) & (st >= 0), st, pl.to(torch.int32)).to(torch.uint8))
+        else:
+            self.env.step(self.actions, player=0, chance=chance, reveals=reveals, rotate=True, auto_reset=False, want_mask=False,
+                          want_status=False, count=True)
+
+    def _restart(self, done):
+        """finished lanes start their next game and forget their trees (Coach.py:67,122)"""
+        done8 = done.to(torch.uint8)
+        self.env.episodes += done.to(torch.int32)      # Philox key: game id, episode
+        self.env.reset(done8)
+        if self.absolute:
+            self.env.players.masked_fill_(done, 0)
+        self.arena.reset(done8)
+        self.games_finished += done.sum()
+
     def _wave(self):
+        if getattr(self, "_dir_values", None) is not None:      # parity runs: the Dirichlet vectors the caller supplies
+            return self.arena.wave(self.evaluator, self._dir_values)
         if getattr(self, "_async", False):
             if self.overlap_nnet:
                 self.arena.wave_nnet(self.evaluator)   # network next to the attach kernel (spl_mcts_wave_nnet)
@@ -100,10 +155,16 @@ class SelfPlayEngine:
         for _ in range((waves + self.graph_waves - 1) // self.graph_waves):
             self._graph.replay()
 
-    def search(self, temp=1.0):
-        """one getActionProb for every lane -> (probs float64[T,406], q float64[T,n], is_full bool[T])"""
+    def search(self, temp=1.0, is_full=None, dir_values=None):
+        """one getActionProb for every lane -> (probs float64[T,406], q float64[T,n], is_full bool[T]).
+        is_full bool[T] / dir_values float64[T,406] (optional): the playout-cap coins and the root Dirichlet vectors of a recorded
+        run instead of the engine's own draws (parity tests against Coach.executeEpisode)"""
         T = self.T
-        if self.prob_full >= 1.0:
+        self._dir_values = dir_values
+        if is_full is not None:
+            is_full = is_full.to(self.device, dtype=torch.bool)
+            max_sims = self.num_sims
+        elif self.prob_full >= 1.0:
             is_full = torch.ones(T, dtype=torch.bool, device=self.device)
             max_sims = self.num_sims
         else:
@@ -113,44 +174,49 @@ class SelfPlayEngine:
         fl = (nat.MCTS_MOVE_FORCED if self.forced else 0) | (nat.MCTS_MOVE_NOISE if self.noise else 0)
         self.flags.copy_(torch.where(is_full, fl, 0).to(torch.uint8))
         self.sims_total += self.sims.sum()
-        self.env.states(out=self.roots)
+        self._roots()
         if self.graph_waves > 0 and self._graph is None:
             # the warm-up waves of the capture are real waves: run them on a scratch search and throw its trees away, so that
             # the first move of every lane is exactly the reference's sequential search (no extra simulations, no second noise)
             self.arena.begin(self.roots, self.sims, self.flags)
             self._run_waves(0)
             self.arena.reset()
-        self.arena.begin(self.roots, self.sims, self.flags)
+        self.arena.begin(self.roots, self.sims, self.flags, None, dir_values)
         self._run_waves(max_sims)
         chunk = None
         if self.graph_waves > 0:
             def chunk():
                 self._graph.replay()
                 return self.graph_waves
-        self.extra_waves += self.arena.finish(self.evaluator, chunk=chunk)   # stragglers (descents that crossed transpositions / terminal nodes)
+        self.extra_waves += self.arena.finish(self.evaluator, dir_values, chunk=chunk)   # stragglers (descents that crossed transpositions / terminal nodes)
+        self._dir_values = None
         probs, q = self.arena.policy(temp)
         return probs, q, is_full
 
-    def play_move(self, temp=1.0):
+    def play_move(self, temp=1.0, is_full=None, dir_values=None, forced_actions=None, reveals=None):
         """search, sample an action per lane from the visit distribution, advance every game (finished lanes restart and
-        their trees are cleared). Returns (probs, q, is_full, ended float32[T,n])."""
-        probs, q, is_full = self.search(temp)
-        a = torch.multinomial(probs.to(torch.float32), 1, generator=self.gen).view(-1)
-        self.actions.copy_(a.to(torch.int16))
+        their trees are cleared). Returns (probs, q, is_full, ended float32[T,n]).
+        forced_actions int16[T] / reveals uint8[T] (colour*8+idx, 255 = nothing drawn): replay of a recorded game - the action
+        Coach picked and the card the reference revealed - instead of the engine's own sample and Philox reveal"""
+        probs, q, is_full = self.search(temp, is_full, dir_values)
+        if forced_actions is not None:
+            self.actions.copy_(forced_actions.to(self.device, dtype=torch.int16))
+        else:
+            a = torch.multinomial(probs.to(torch.float32), 1, generator=self.gen).view(-1)
+            self.actions.copy_(a.to(torch.int16))
         if self.examples is not None:   # Coach.py:76-80: the position, its policy target and legal mask, before the move
-            self.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
-            self.examples.record(self.roots, probs, self.env.valids(), q, is_full)
-        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+            self.examples.record(self.roots, probs, self._valids(), q, is_full)
+        if reveals is not None:
+            self._reveals = reveals.to(self.device, dtype=torch.uint8).contiguous()
+            self._move("replay", self._reveals)
+        else:
+            self._move()
         ended = self.env.ended
         done = (ended != 0).any(dim=1)
         if self.examples is not None:
             scores, _ = self.env.scores()
-            self.examples.advance(ended, scores)
-        done8 = done.to(torch.uint8)
-        self.env.episodes += done.to(torch.int32)      # finished lanes start their next game (Philox key: game id, episode)
-        self.env.reset(done8)
-        self.arena.reset(done8)                        # MCTS.reset_all_search_trees after every episode (Coach.py:122)
-        self.games_finished += done.sum()
+            self.examples.advance(ended, scores, absolute=self.absolute)
+        self._restart(done)
         self.moves += 1
         return probs, q, is_full, ended
 
@@ -167,7 +233,7 @@ class SelfPlayEngine:
     def start_async(self):
         T = self.T
         self._assign_budgets(torch.ones(T, dtype=torch.bool, device=self.device))
-        self.env.states(out=self.roots)
+        self._roots()
         self.arena.begin(self.roots, self.sims, self.flags)
         self.arena.select()
         self._move_counters = torch.zeros(2, dtype=torch.int64, device=self.device)    # simulations, moves of the completed searches
@@ -228,23 +294,18 @@ class SelfPlayEngine:
         a = torch.multinomial(p, 1, generator=self.gen).view(-1).to(torch.int16)
         self.actions.copy_(torch.where(fin, a, torch.full_like(a, -1)))
         if self.examples is not None:
-            self.env.step(None, player=0, store_state=False, want_ended=False, want_status=False)
-            self.examples.record(self.roots, probs, self.env.valids(), q, self._is_full & fin)
-        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+            self.examples.record(self.roots, probs, self._valids(), q, self._is_full & fin)
+        self._move()
         ended = self.env.ended
         done = fin & (ended != 0).any(dim=1)
         if self.examples is not None:
             scores, _ = self.env.scores()
-            self.examples.advance(ended, scores, moved=fin)
-        done8 = done.to(torch.uint8)
-        self.env.episodes += done.to(torch.int32)
-        self.env.reset(done8)
-        self.arena.reset(done8)
-        self.games_finished += done.sum()
+            self.examples.advance(ended, scores, moved=fin, absolute=self.absolute)
+        self._restart(done)
         self._move_counters[0] += torch.where(fin, st["sims_done"], torch.zeros_like(st["sims_done"])).sum()
         self._move_counters[1] += fin.sum()
         self._assign_budgets(fin)
-        self.env.states(out=self.roots)
+        self._roots()
         self._fin8.copy_(fin)
         self.arena.begin(self.roots, self.sims, self.flags, self._fin8)
 
@@ -253,15 +314,11 @@ class SelfPlayEngine:
         finished lane's action from its visit counts on the device (Philox keyed by game / episode / ply) and counts the simulations"""
         self.arena.sample_moves(temp, self.env.episodes, self.actions, self._fin8, self._move_counters)
         fin = self._fin8.to(torch.bool)
-        self.env.step(self.actions, player=0, chance="philox", rotate=True, auto_reset=False, want_mask=False, want_status=False, count=True)
+        self._move()
         done = fin & (self.env.ended != 0).any(dim=1)
-        done8 = done.to(torch.uint8)
-        self.env.episodes += done.to(torch.int32)
-        self.env.reset(done8)
-        self.arena.reset(done8)
-        self.games_finished += done.sum()
+        self._restart(done)
         self._assign_budgets(fin)
-        self.env.states(out=self.roots)
+        self._roots()
         self.arena.begin(self.roots, self.sims, self.flags, self._fin8)
 
     @property

@@ -22,7 +22,15 @@ and applies the mechanical patch list of SURVEY.md §8(c):
 Every hunk asserts that the text it replaces is present exactly once, so a changed
 reference fails loudly instead of silently producing a different oracle.
 
-Only oracle/refgen/gen_golden.py and tests marked `ref` use the result.
+  P7  (callers only) stubs for onnxruntime / coloredlogs / torchinfo, which Arena.py -> splendor/NNet.py ->
+      GenericNNetWrapper.py and main.py import but this image does not have
+
+Only oracle/refgen/gen_*.py and tests marked `ref` use the result.
+
+`build(out, callers=True)` also copies the CALLERS of the hot path (Arena.py, Coach.py and what they import), unmodified, so that
+tests can drive them over the reference's own Game / MCTS and over the B200 mirrors. The one place inside the repository a copy
+may go is the git-ignored oracle/_ref/ (it travels to the GPU box with gpurun, never into history): `python
+oracle/refgen/build_patched_ref.py --travel` builds oracle/_ref/pyref.
 """
 import os
 import shutil
@@ -33,6 +41,9 @@ OUT = os.environ.get("AZG_REF_OUT", "/tmp/azg_ref")
 
 ROOT_FILES = ["Game.py", "MCTS.py", "utils.py", "NeuralNet.py"]
 PKG_FILES = ["SplendorGame.py", "SplendorLogic.py", "SplendorLogicNumba.py", "SplendorNNet.py"]
+CALLER_ROOT_FILES = ["Arena.py", "Coach.py", "GenericNNetWrapper.py"]
+CALLER_PKG_FILES = ["NNet.py"]
+TRAVEL = os.path.realpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "_ref", "pyref"))
 
 
 def _sub_once(text, old, new, tag):
@@ -85,13 +96,20 @@ Style = _Blank(); Fore = _Blank(); Back = _Blank()
 '''
 
 
-def build(out=OUT, ref=REF):
+STUBS = {   # P7
+    "onnxruntime.py": '"""stub (P7): the ONNX path is not selected at HEAD (GenericNNetWrapper.py:25-29)"""\n',
+    "coloredlogs.py": '"""stub (P7)"""\ndef install(*a, **k):\n    pass\n',
+    "torchinfo.py": '"""stub (P7)"""\ndef summary(*a, **k):\n    return None\n',
+}
+
+
+def build(out=OUT, ref=REF, callers=False):
     if not os.path.isdir(ref):
         raise FileNotFoundError(ref)
     real_out = os.path.realpath(out)
     repo = os.path.realpath(os.path.join(os.path.dirname(__file__), "..", ".."))
-    if real_out.startswith(repo + os.sep):
-        raise RuntimeError("refusing to copy reference sources into the repo")
+    if real_out.startswith(repo + os.sep) and real_out != TRAVEL:
+        raise RuntimeError("refusing to copy reference sources into the repo (only the git-ignored oracle/_ref/pyref may hold a copy)")
     if os.path.isdir(out):
         shutil.rmtree(out)
     os.makedirs(os.path.join(out, "splendor"))
@@ -107,17 +125,40 @@ def build(out=OUT, ref=REF):
     open(os.path.join(out, "splendor", "__init__.py"), "w").close()
     with open(os.path.join(out, "colorama.py"), "w") as fh:
         fh.write(COLORAMA_STUB)
+    if callers:
+        for f in CALLER_ROOT_FILES:
+            shutil.copy(os.path.join(ref, f), os.path.join(out, f))
+        for f in CALLER_PKG_FILES:
+            shutil.copy(os.path.join(ref, f), os.path.join(out, "splendor", f))
+        for name, text in STUBS.items():
+            with open(os.path.join(out, name), "w") as fh:
+                fh.write(text)
     return out
 
 
-def import_ref(out=OUT):
+def import_ref(out=OUT, callers=False):
     """Build (if needed) and put the patched copy on sys.path."""
-    if not os.path.isfile(os.path.join(out, "splendor", "SplendorLogicNumba.py")):
-        build(out)
+    if not os.path.isfile(os.path.join(out, "splendor", "SplendorLogicNumba.py")) or (callers and not os.path.isfile(os.path.join(out, "Coach.py"))):
+        build(out, callers=callers)
     if out not in sys.path:
         sys.path.insert(0, out)
     return out
 
 
+def find_ref(callers=False):
+    """the patched copy that is available: built from /root/reference when that exists (build container), else the
+    travelling copy oracle/_ref/pyref (GPU box), else None"""
+    if os.path.isdir(REF):
+        return import_ref(callers=callers)
+    if os.path.isfile(os.path.join(TRAVEL, "Coach.py" if callers else os.path.join("splendor", "SplendorLogicNumba.py"))):
+        if TRAVEL not in sys.path:
+            sys.path.insert(0, TRAVEL)
+        return TRAVEL
+    return None
+
+
 if __name__ == "__main__":
-    print(build())
+    if "--travel" in sys.argv:
+        print(build(TRAVEL, callers=True))
+    else:
+        print(build(callers="--callers" in sys.argv))
