@@ -1314,7 +1314,7 @@ SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSear
     if (nd->kind != MCTS_NODE_EXPANDED) return -1;
     const int k = nd->n_edges;
     const MctsEdges ed = mcts_edges(A, T->root, k);
-    const bool forced = (T->flags & MCTS_F_FORCED) != 0u;
+    bool forced = (T->flags & MCTS_F_FORCED) != 0u;
     int action = -1;
     if (w.lane == 0) {
         int best = 0;
@@ -1324,6 +1324,12 @@ SPL_D int mcts_sample_tree(const W& w, const MctsArena& A, int t, const MctsSear
         for (int pass = 0; pass < 2; pass++) {      // pass 0: total weight, pass 1: the walk up to u * total
             double target = 0.0, acc = 0.0;
             if (pass == 1) {
+                if (forced && !(sum > 0.0) && best > 0) {
+                    // policy-target pruning left nothing (every visited move was visited once: `c > 1 else 0`, :73): the reference
+                    // divides by zero here and its caller's np.random.choice raises; the engine falls back to the raw counts
+                    forced = false; pass = -1; sum = 0.0; bestc = -1.0; besti = -1;
+                    continue;
+                }
                 if (temp == 0.0 || !(sum > 0.0)) break;
                 const SplPhilox r = spl_philox(P.seed, P.game_base + (uint32_t)t, episode, (uint32_t)nd->ply, 5);
                 target = MC_DMUL(mcts_u01(r.v[0], r.v[1]), sum);

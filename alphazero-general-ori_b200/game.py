@@ -242,17 +242,48 @@ class SplendorGame:
             self._batch_envs[n_lanes] = env
         return env
 
-    def getNextStateBatch(self, boards, player, actions, deterministic=False, canonical=True):
+    def getNextStateBatch(self, boards, player, actions, deterministic=False, canonical=True, packed_masks=False):
         """L games at once, host arrays in and out: boards int8[L,R,7], actions int[L], all moved by `player`.
         Returns (next boards int8[L,R,7] (rotated to the next player's canonical form when `canonical`),
         valid masks bool[L,406] for the player to move, end vectors float32[L,n]) =
-        getNextState + getCanonicalForm + getValidMoves + getGameEnded of the reference, per lane."""
+        getNextState + getCanonicalForm + getValidMoves + getGameEnded of the reference, per lane.
+        packed_masks: the masks come back as their 406 bits - uint32[L,13], bit a of word a // 32 = action a (52 bytes per game
+        instead of 406; `unpack_masks` expands them) - and the call runs as a pipeline of lane chunks on several streams, so that
+        the copies in both directions and the kernels overlap."""
         boards = np.ascontiguousarray(boards, dtype=np.int8)
         L = boards.shape[0]
+        if packed_masks:
+            pipe = self._pipe_for(L)
+            pipe.h_in.numpy()[...] = boards.reshape(L, -1)
+            pipe.h_act.numpy()[...] = np.asarray(actions, dtype=np.int16)
+            return pipe.step(int(player), deterministic, canonical)
         env = self._env_for(L)
         env._h_in.numpy()[...] = boards
         env._h_act.numpy()[...] = np.asarray(actions, dtype=np.int16)
         return self._step_pinned(env, player, deterministic, canonical)
+
+    def rolloutBatch(self, boards, plies):
+        """The loop of Arena.playGame with random players (Arena.py:99-160; SplendorPlayers.RandomPlayer) for L games and `plies` plies
+        per call: canonical boards int8[L,R,7] in; every game plays uniformly random legal moves with Philox reveals, finished games
+        restart; canonical boards out, plus (games finished, plies played). One host round trip per `plies` plies."""
+        boards = np.ascontiguousarray(boards, dtype=np.int8)
+        L = boards.shape[0]
+        pipe = self._pipe_for(L)
+        pipe.h_in.numpy()[...] = boards.reshape(L, -1)
+        return pipe.rollout(int(plies))
+
+    @staticmethod
+    def unpack_masks(words):
+        """uint32[L,13] mask words -> bool[L,406] as getValidMoves returns them"""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        return np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")[:, :nat.NUM_ACTIONS].astype(np.bool_)
+
+    def _pipe_for(self, n_lanes):
+        key = ("pipe", n_lanes)
+        pipe = self._batch_envs.get(key)
+        if pipe is None:
+            pipe = self._batch_envs[key] = _BatchPipe(self, n_lanes)
+        return pipe
 
     def _step_pinned(self, env, player, deterministic, canonical):
         env._d_in.copy_(env._h_in, non_blocking=True)
@@ -266,6 +297,82 @@ class SplendorGame:
         env._h_ended.copy_(env.ended, non_blocking=True)
         torch.cuda.current_stream(env.device).synchronize()
         return env._h_out.numpy(), env._h_valid.numpy().view(np.bool_), env._h_ended.numpy()
+
+
+class _BatchPipe:
+    """Host-buffer calls for L games as a pipeline: the lanes are cut into chunks (multiples of the 32-lane tile), every chunk has
+    its own stream and environment object; chunk c + 1 uploads while chunk c computes and chunk c - 1 downloads (PCIe is full
+    duplex). Pinned host buffers for the whole batch, reused from call to call."""
+
+    def __init__(self, game, n_lanes, chunks=None):
+        n = game.num_players
+        self.L, self.n = n_lanes, n
+        dev = torch.device("cuda", game._device)
+        C = chunks or max(1, min(8, n_lanes // 8192))
+        per = -(-n_lanes // C)
+        per = -(-per // 32) * 32
+        self.bounds = [(lo, min(n_lanes, lo + per)) for lo in range(0, n_lanes, per)]
+        S = 7 * rows(n)
+        self.h_in = torch.empty((n_lanes, S), dtype=torch.int8).pin_memory()
+        self.h_act = torch.empty(n_lanes, dtype=torch.int16).pin_memory()
+        self.h_out = torch.empty((n_lanes, rows(n), 7), dtype=torch.int8).pin_memory()
+        self.h_mask = torch.empty((n_lanes, nat.MASK_WORDS), dtype=torch.int32).pin_memory()
+        self.h_ended = torch.empty((n_lanes, n), dtype=torch.float32).pin_memory()
+        self.h_cnt = torch.zeros((len(self.bounds), 2), dtype=torch.int64).pin_memory()
+        self.parts = []
+        with torch.cuda.device(dev):
+            for lo, hi in self.bounds:
+                env = SplendorEnv(n, hi - lo, device=game._device, seed=game._seed, game_base=lo, token_limit=game.board.NUM_TOKEN_LIMIT,
+                                  rule_flags=game.board._flags)
+                d = dict(env=env, stream=torch.cuda.Stream(dev), lo=lo, hi=hi,
+                         d_in=torch.empty((hi - lo, S), dtype=torch.int8, device=dev), d_act=torch.empty(hi - lo, dtype=torch.int16, device=dev),
+                         d_out=torch.empty((hi - lo, rows(n), 7), dtype=torch.int8, device=dev),
+                         d_mask=torch.empty((hi - lo, nat.MASK_WORDS), dtype=torch.int32, device=dev))
+                self.parts.append(d)
+        self.device = dev
+
+    def step(self, player, deterministic, canonical):
+        cur = torch.cuda.current_stream(self.device)
+        for p in self.parts:
+            st, env, lo, hi = p["stream"], p["env"], p["lo"], p["hi"]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                p["d_in"].copy_(self.h_in[lo:hi], non_blocking=True)
+                p["d_act"].copy_(self.h_act[lo:hi], non_blocking=True)
+                env.set_states(p["d_in"])
+                env.step(p["d_act"], player=player, chance="det" if deterministic else "philox", rotate=canonical, want_status=False)
+                env.states(out=p["d_out"])
+                p["d_mask"].copy_(env.masks[:, : hi - lo].t())          # mask planes [13][lanes] -> words per game [lanes][13]
+                self.h_out[lo:hi].copy_(p["d_out"], non_blocking=True)
+                self.h_mask[lo:hi].copy_(p["d_mask"], non_blocking=True)
+                self.h_ended[lo:hi].copy_(env.ended, non_blocking=True)
+        for p in self.parts:
+            p["stream"].synchronize()
+        return self.h_out.numpy(), self.h_mask.numpy().view(np.uint32), self.h_ended.numpy()
+
+    def rollout(self, plies):
+        cur = torch.cuda.current_stream(self.device)
+        for i, p in enumerate(self.parts):
+            st, env, lo, hi = p["stream"], p["env"], p["lo"], p["hi"]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                p["d_in"].copy_(self.h_in[lo:hi], non_blocking=True)
+                env.set_states(p["d_in"])
+                env.counters.zero_()
+                env.rollout(plies, rotate=True)
+                env.states(out=p["d_out"])
+                self.h_out[lo:hi].copy_(p["d_out"], non_blocking=True)
+                self.h_cnt[i].copy_(env.counters, non_blocking=True)
+        for p in self.parts:
+            p["stream"].synchronize()
+        c = self.h_cnt.numpy().sum(0)
+        return self.h_out.numpy(), int(c[0]), int(c[1])
+
+    def bytes_per_call(self, rollout=False):
+        S = 7 * rows(self.n)
+        if rollout:
+            return self.L * S, self.L * S + 16 * len(self.parts)
+        return self.L * (S + 2), self.L * (S + 4 * nat.MASK_WORDS + 4 * self.n)
 
 
 _COLORS = ["white", "blue", "green", "red", "black"]

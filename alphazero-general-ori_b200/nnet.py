@@ -182,6 +182,45 @@ def pack_blob(n_players, sd):
     return torch.from_numpy(blob)
 
 
+def load_checkpoint_file(path, allow_pickle=False):
+    """a checkpoint of GenericNNetWrapper.save_checkpoint (:185-198): {'state_dict', 'full_model', **training args}. Only the
+    weights are needed, so the file is read with weights_only=True first; the reference also pickles the whole module
+    ('full_model'), which that mode refuses - then only the tensors of 'state_dict' are pulled out of the archive with an
+    unpickler that builds nothing but tensors and plain containers (unknown classes become inert placeholders).
+    allow_pickle=True: plain torch.load (executes whatever the file's pickle says; needs the reference package importable)."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        if allow_pickle:
+            return torch.load(path, map_location="cpu", weights_only=False)
+    import pickle
+
+    class _Inert:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            pass
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.startswith(("torch", "collections", "numpy")) or module == "builtins":
+                return super().find_class(module, name)
+            return _Inert
+
+    class _Pickle:
+        Unpickler = _Unpickler
+        load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
+        __name__ = "pickle"
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_Pickle)
+
+
+def state_dict_from_npz(path):
+    """the weights frozen by oracle/refgen/gen_genbu_golden.py (keys 'sd/<name>') -> dict of tensors"""
+    z = np.load(path)
+    return {str(k): torch.from_numpy(z["sd/" + str(k)]) for k in z["sd_keys"]}
+
+
 class FusedSplendorNNet:
     """The same evaluator as SplendorNNetB200 in ONE kernel launch (csrc/spl_nnet.cu): bf16 tensor-core products with
     fp32 accumulation, activations resident in shared memory. Output buffers are static per batch size (CUDA-graph safe)."""
@@ -265,10 +304,10 @@ class SplendorNNetB200:
                 raise ValueError(f"state_dict entry {k}: expected shape {shape}, got {tuple(sd[k].shape) if k in sd else None}")
         self.W = fold(sd, self.device, self.dtype)
 
-    def load_checkpoint(self, folder, filename):
+    def load_checkpoint(self, folder, filename, allow_pickle=False):
         """reads the 'state_dict' entry of a checkpoint written by GenericNNetWrapper.save_checkpoint (:185-198)"""
         import os
-        ck = torch.load(os.path.join(folder, filename), map_location="cpu", weights_only=False)
+        ck = load_checkpoint_file(os.path.join(folder, filename), allow_pickle=allow_pickle)
         self.load_state_dict(ck["state_dict"] if "state_dict" in ck else ck)
         return ck
 

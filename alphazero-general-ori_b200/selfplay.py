@@ -191,7 +191,16 @@ class SelfPlayEngine:
         self.extra_waves += self.arena.finish(self.evaluator, dir_values, chunk=chunk)   # stragglers (descents that crossed transpositions / terminal nodes)
         self._dir_values = None
         probs, q = self.arena.policy(temp)
-        return probs, q, is_full
+        return self._usable_policy(probs), q, is_full
+
+    def _usable_policy(self, probs):
+        """getActionProb divides by the sum of the (pruned) visit counts (MCTS.py:69-76,94-97). With forced playouts, few simulations
+        and many legal moves every move may have been visited once, the pruning (`c if c > 1 else 0`) then leaves nothing and the
+        reference returns NaNs that crash its caller's np.random.choice. The engine keeps such a lane going on the raw visit counts."""
+        bad = ~torch.isfinite(probs).all(dim=1) | ~(probs.sum(dim=1) > 0)
+        nsa = self.arena.root_stats()["nsa"].to(probs.dtype)
+        raw = nsa / nsa.sum(dim=1, keepdim=True).clamp_min(1.0)
+        return torch.where(bad.view(-1, 1), raw, probs)
 
     def play_move(self, temp=1.0, is_full=None, dir_values=None, forced_actions=None, reveals=None):
         """search, sample an action per lane from the visit distribution, advance every game (finished lanes restart and
@@ -289,6 +298,7 @@ class SelfPlayEngine:
         st = self.arena.root_stats(want_arrays=False)
         fin = (st["sims_done"] >= self.sims) | (st["status"] != 0)
         probs, q = self.arena.policy(temp)
+        probs = self._usable_policy(probs)
         p = probs.to(torch.float32)
         p = torch.where(fin.view(-1, 1) & (p.sum(dim=1, keepdim=True) > 0), p, torch.ones_like(p))
         a = torch.multinomial(p, 1, generator=self.gen).view(-1).to(torch.int16)

@@ -30,6 +30,7 @@ METRIC_MCTS, UNIT_MCTS = "splendor_mcts_sims_per_s", "sims/s"
 METRIC_ENV, UNIT_ENV = "splendor_env_steps_per_s", "steps/s"
 B_STEP = {2: 846, 3: 1060, 4: 1302}     # algorithmic bytes per env step: 2S + 52 + 2 + 4n
 B_SIM = {2: 4500, 3: 5300, 4: 6300}     # algorithmic bytes per simulation (d=4.83, m=20)
+NN_FLOPS_PER_LEAF = {2: 1.24e6, 3: 1.30e6, 4: 1.37e6}   # SplendorNNet forward, 2 x MACs (0.62 M MAC at n = 2; the first layer grows with R)
 
 
 def parse():
@@ -41,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="both", choices=["both", "mcts", "env"])
     ap.add_argument("--players", type=int, default=2)
     # MCTS (configs[1])
-    ap.add_argument("--trees", type=int, default=4096, help="parallel games (trees) per GPU")
+    ap.add_argument("--trees", type=int, default=18944, help="parallel games (trees) per GPU (18,944 = 148 SMs x 128: four full rounds of the 32-leaf evaluator CTAs)")
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
     ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
@@ -77,6 +78,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-mcts-worker", type=str, default="", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-ref-worker", type=str, default="", help=argparse.SUPPRESS)
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (config 2 with genbu.pt, configs[2], configs[3], float32 evaluator)")
     return ap.parse_args()
 
 
@@ -147,23 +150,86 @@ def cpu_mcts_worker(spec):
     print(json.dumps({"sims": done, "seconds": dt}), flush=True)
 
 
-def cpu_mcts(n, sims, moves, seed, fixed, procs=None):
+def reference_dir():
+    """the reference's own files (patched copy, oracle/refgen/build_patched_ref.py): built from /root/reference where that exists,
+    else the travelling copy oracle/_ref/pyref; None if neither is there"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refgen"))
+    try:
+        import build_patched_ref
+        return build_patched_ref.find_ref(callers=True)
+    except Exception:
+        return None
+
+
+def cpu_ref_worker(spec):
+    """one process = one core: the REFERENCE ITSELF - its MCTS.py, its Numba Board behind SplendorGame, its NNetWrapper.predict
+    (GenericNNetWrapper.py:141-168: torch CPU float32, batch 1, one thread) - playing `moves` moves of `sims` simulations"""
+    n, sims, moves, seed, idx, _ = [int(x) for x in spec.split(",")]
+    import warnings
+    warnings.filterwarnings("ignore")
+    t_jit = time.perf_counter()
+    if reference_dir() is None:
+        print(json.dumps({"unavailable": "no copy of the reference"}), flush=True)
+        return
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from MCTS import MCTS
+    from splendor.SplendorGame import SplendorGame
+    from splendor.NNet import NNetWrapper
+    from utils import dotdict
+    import azg_b200  # noqa: F401  (only for the weights both arms share)
+    from azg_b200 import nnet
+    game = SplendorGame(n)
+    net = NNetWrapper(game, dict(lr=0.001, dropout=0.3, epochs=1, batch_size=32, nn_version=1), use_exchange=True)
+    net.nnet.load_state_dict(nnet.random_state_dict(n, seed), strict=True)
+    args = dotdict(numMCTSSims=sims, prob_fullMCTS=1.0, ratio_fullMCTS=5, forced_playouts=False, cpuct=1.0, fpu=0.0, no_mem_optim=False)
+    mcts = MCTS(game, net, args)
+    rng = np.random.default_rng(seed + idx)
+    board, cur = game.getInitBoard(), 0
+    for _ in range(24):
+        canon = game.getCanonicalForm(board, cur)
+        v = game.getValidMoves(canon, 0)
+        board, cur = game.getNextState(board, cur, int(rng.choice(np.flatnonzero(v))))
+    mcts.args = dotdict(args, numMCTSSims=32)
+    mcts.getActionProb(game.getCanonicalForm(board, cur), temp=1, force_full_search=True)     # JIT warm-up of every njit helper
+    mcts.args = args
+    MCTS.reset_all_search_trees()
+    t_jit = time.perf_counter() - t_jit
+    done = 0
+    t0 = time.perf_counter()
+    for _ in range(moves):
+        if game.getGameEnded(board, cur).any():
+            board, cur = game.getInitBoard(), 0
+            MCTS.reset_all_search_trees()
+        canon = game.getCanonicalForm(board, cur)
+        pi, _, _ = mcts.getActionProb(canon, temp=1, force_full_search=True)
+        done += sims
+        board, cur = game.getNextState(board, cur, int(rng.choice(len(pi), p=np.array(pi) / np.sum(pi))))
+    dt = time.perf_counter() - t0
+    print(json.dumps({"sims": done, "seconds": dt, "jit_seconds": t_jit}), flush=True)
+
+
+def cpu_mcts(n, sims, moves, seed, fixed, procs=None, worker="--cpu-mcts-worker"):
     """-> (sims/s aggregate, cores, total sims, wall seconds) with one worker process per host core"""
     procs = procs or len(os.sched_getaffinity(0))
     env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
-    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-mcts-worker", f"{n},{sims},{moves},{seed},{i},{int(fixed)}"],
+    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), worker, f"{n},{sims},{moves},{seed},{i},{int(fixed)}"],
                            stdout=subprocess.PIPE, env=env, text=True) for i in range(procs)]
     tot, rate, worst = 0, 0.0, 0.0
     for p in ps:
         out, _ = p.communicate()
         r = json.loads(out.strip().splitlines()[-1])
+        if "unavailable" in r:
+            return None
         tot += r["sims"]; rate += r["sims"] / r["seconds"]; worst = max(worst, r["seconds"])
     return rate, procs, tot, worst
 
 
 def workload_mcts(args):
     net = "fixed stand-in network" if args.fixed_net else "SplendorNNet (random-init)"
-    return (f"configs[1]: {args.players}p self-play, {args.sims} MCTS sims/move with {net}, {args.trees} parallel games per GPU")
+    return (f"configs[1]: {args.players}p self-play, {args.sims} MCTS sims/move with {net}, {args.trees} parallel games per GPU "
+            f"(the metric's '64k games' = 65,536 games over 4 or more GPUs; exact tree cleaning)")
 
 
 def workload_env(args):
@@ -186,22 +252,30 @@ def run_reference(args):
         for _ in range(args.steps):
             v, cores, g, plies, dt = cpu_rollouts(n, args.seed, per_step)
             tot += plies; tdt += dt; games += g
+        kind = "port"
         value, metric, unit, wl = tot / tdt, METRIC_ENV, UNIT_ENV, workload_env(args)
         sample = f"{games} whole random {n}p games (oracle port of the SplendorLogicNumba rules, C -O2), {cores} threads"
     else:
-        # step = one move (getActionProb) per worker; bounded: sims per move scaled so that K+W moves stay within minutes
-        sims = min(args.sims, 400)
-        moves = max(1, args.steps) * 10            # a step of this arm = 10 moves per worker (about 1 s of CPU work)
-        rate, cores, tot, tdt = cpu_mcts(n, sims, moves, args.seed, args.fixed_net)
+        # step = one move (getActionProb, the full budget) per worker process, one process per host core
+        sims = args.sims
+        moves = max(1, args.steps)
+        res, kind = None, "reference"
+        if reference_dir() is not None:
+            res = cpu_mcts(n, sims, moves, args.seed, args.fixed_net, worker="--cpu-ref-worker")
+        if res is None:
+            kind = "port"
+            res = cpu_mcts(n, sims, moves, args.seed, args.fixed_net)
+        rate, cores, tot, tdt = res
         value, metric, unit, wl = rate, METRIC_MCTS, UNIT_MCTS, workload_mcts(args)
-        sample = (f"{cores} processes x {moves} moves ({args.steps} steps of 10 moves) x {sims} sims/move = {tot} simulations (C port of MCTS.py + per-leaf torch-CPU "
-                  f"float32 SplendorNNet predict, 1 thread each; {sims} instead of {args.sims} sims/move to bound the run)")
+        what = ("the reference's own MCTS.py + Numba Board + NNetWrapper.predict (torch CPU float32, batch 1)" if kind == "reference" else
+                "C port of MCTS.py + per-leaf torch-CPU float32 SplendorNNet predict")
+        sample = f"{cores} processes x {moves} moves x {sims} sims/move = {tot} simulations ({what}, 1 thread each, JIT / warm-up move excluded)"
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tdt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64/f32 tree statistics, f32 network" if metric == METRIC_MCTS else "int8", "data": "synthetic",
         "config": {"workload": wl, "players": n},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind if args.workload != "env" else "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -341,10 +415,14 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     sims_done = sims_now() - sims0
     if not args.async_moves:
         assert sims_done == T * sims * args.steps
+    sims_all = torch.tensor([sims_done], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(sims_all, op=dist.ReduceOp.SUM)       # what every rank really simulated, not world x rank 0
+    sims_all = int(sims_all.item())
     st = eng.arena.root_stats(want_arrays=False)
     pool = eng.arena.pool_stats()
     truncated_now = 0 if args.async_moves else int((st["sims_done"] < sims).sum())
-    value = world * sims_done / (ms_total * 1e-3)
+    value = sims_all / (ms_total * 1e-3)
     # our own kernels inside the timed region (graph replays re-launch the captured ones): per wave 3 x rounds selection
     # kernels + the evaluator + expand; per tick / move the stats, policy, env step, resets, unpack and begin kernels
     per_wave = 3 * args.rounds + 1 + (1 if (args.fixed_net or args.nn_dtype == "fused") else 0)
@@ -401,17 +479,24 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
                 "wave_breakdown_ms": {"selection (descend+rules+attach kernels x rounds)": sel, "network_forward": nnt, "mcts_expand_kernel": exp,
                                       "whole wave, network next to the attach kernel (plain launches)": ovl}}
 
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1409.8))
+    nn_tflops = NN_FLOPS_PER_LEAF[n] * T / (nnt * 1e-3) / 1e12
+    roofline_nn = {"bound": "tensor", "achieved": nn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": nn_tflops / bf16_peak, "traffic": None,
+                   "kernel": "nnet_forward_kernel (one launch = the whole SplendorNNet forward for every tree's leaf)", "avg_launch_ms": nnt,
+                   "flops_per_leaf": NN_FLOPS_PER_LEAF[n], "leaves_per_launch": T, "leaves_per_s": T / (nnt * 1e-3),
+                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a long step)" if peaks else "fallback 1409.8 TFLOP/s"}
+    nn_name = {"fused": "bf16 network (bf16 x bf16 -> fp32 accumulate, tensor cores)", "bf16": "bf16 network (torch)", "fp32": "f32 network (torch)"}[args.nn_dtype]
     line = {
         "metric": METRIC_MCTS, "value": value, "unit": UNIT_MCTS, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": f"f64/f32 tree statistics, {args.nn_dtype} network", "data": "synthetic",
+        "dtype": f"f64/f32 tree statistics, {nn_name}", "data": "synthetic",
         "config": {"workload": workload_mcts(args), "players": n, "trees_per_gpu": T, "sims_per_move": sims, "cpuct": 1.0, "fpu": 0.0,
                    "network": "fixed" if args.fixed_net else f"SplendorNNet random-init seed {args.seed} ({args.nn_dtype}, tf32 off)",
                    "gc": args.gc, "node_limit_per_tree": cap, "pool_nodes_per_tree": pool_nodes, "graph_waves": args.graph_waves, "waves_per_tick": G, "rounds_per_wave": args.rounds, "max_levels_per_descend": args.max_levels, "async_moves": bool(args.async_moves), "network_overlaps_attach": bool(eng.overlap_nnet),
                    "moves_completed": int(eng.moves_completed.item()) if args.async_moves else args.steps * T, "extra_waves": eng.extra_waves, "opening_plies": args.opening_plies,
                    "parallelism": f"games sharded dp{world}, no collective on the path",
                    "l2": f"inputs larger than L2: tree arena {eng.arena.arena_bytes / 1e9:.1f} GB per GPU vs 126 MB L2"},
-        "roofline": roofline, "gpu_launches": own_launches_total, "wall_s": wall,
+        "roofline": roofline, "roofline_network": roofline_nn, "gpu_launches": own_launches_total, "wall_s": wall,
         "tree_stats": {"truncated_searches": int(st["truncated"].sum()) + truncated_now, "lossy_resets": int(st["resets"].sum()), "cleanings": int(st["cleanings"].sum()),
                        "mean_nodes": float(st["nodes"].float().mean()), "max_nodes": int(st["nodes"].max()),
                        "pool_gb": pool["pages"] * pool["page_bytes"] / 1e9, "pool_peak_fill": 1.0 - pool["min_free"] / max(1, pool["pages"]), "mean_path_length": float(st["depth_sum"].sum()) / max(1.0, float(sims_now())), "mean_edges_per_node": float(st["edges"].sum()) / max(1.0, float(st["nodes"].sum())),
@@ -474,6 +559,98 @@ def check_example_exchange(args, torch, dist, azg, world, rank, local):
     dist.all_reduce(cnt)
     return {"examples_local_rank0": local_n, "examples_gathered": total, "sum_of_local_counts": int(cnt.item()),
             "identical_on_all_ranks": bool(torch.equal(lo, hi)), "backend": "nccl"}
+
+
+# ----------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, each as a nested block of the JSON line
+# ----------------------------------------------------------------------------------------------
+def _timed_async(eng, torch, dist, world, dev, barrier, G, ticks, steps, warm=2):
+    """`steps` x `ticks` ticks of G waves of an asynchronous self-play engine -> (simulations of all ranks, ms max over ranks)"""
+    def sims_now():
+        return int(eng.sims_completed.item()) + int(eng.sims_in_flight().item())
+    for _ in range(warm * ticks):
+        eng.tick(G)
+    barrier()
+    s0 = sims_now()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps * ticks):
+        eng.tick(G)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    done = torch.tensor([sims_now() - s0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(done, op=dist.ReduceOp.SUM)
+    return int(done.item()), float(t.item())
+
+
+def bench_config2_genbu(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """SURVEY config 2 as the reference runs it (main.py:111-117 defaults): the shipped checkpoint genbu.pt as the network, 4096 lanes,
+    1600 sims for a full search, playout-cap randomisation (prob_fullMCTS 0.25, ratio 5), Dirichlet noise alpha 0.2 after a root
+    softmax with temperature 1.25, forced playouts + policy-target pruning; exact cleaning"""
+    path = os.path.join(ROOT, "tests", "golden", "genbu_n2.npz")
+    if args.players != 2 or not os.path.isfile(path):
+        return {"skipped": "genbu.pt is a 2-player network"}
+    T, sims, G = 4096, args.sims, args.graph_waves or 16
+    net = azg.FusedSplendorNNet(2, state_dict=azg.nnet.state_dict_from_npz(path), device=local)
+    eng = azg.SelfPlayEngine(2, T, net, sims, device=local, seed=args.seed, game_base=rank * T, cpuct=1.0, fpu=0.0, prob_full=0.25, ratio_full=5,
+                             forced_playouts=True, dirichlet_noise=True, dirichlet_alpha=0.2, temperature0=1.25, node_cap=20 * sims,
+                             pool_nodes=4 * sims, graph_waves=args.graph_waves, max_levels=args.max_levels, tick_graph=True)
+    eng.env.rollout(args.opening_plies, rotate=True)
+    eng.start_async()
+    ticks = -(-sims // G)
+    done, ms = _timed_async(eng, torch, dist, world, dev, barrier, G, ticks, steps=3)
+    st = eng.arena.root_stats(want_arrays=False)
+    return {"value": done / (ms * 1e-3), "unit": UNIT_MCTS, "workload": "SURVEY config 2: genbu.pt weights, 4096 lanes per GPU, 1600 / 320 sims per move "
+            "(prob_fullMCTS 0.25, ratio 5), dirichletAlpha 0.2, temperature[0] 1.25, forced playouts, cpuct 1.0, fpu 0", "trees_per_gpu": T,
+            "moves_completed": int(eng.moves_completed.item()), "games_finished": int(eng.games_finished.item()), "ms": ms,
+            "truncated_searches": int(st["truncated"].sum()), "lossy_resets": int(st["resets"].sum())}
+
+
+def bench_fp32_network(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """the same search with the float32 evaluator (torch kernels, tf32 off): what the bf16 tensor-core kernel buys"""
+    n, T, sims, G = args.players, 4096, args.sims, 16
+    net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32)
+    eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=20 * sims, pool_nodes=4 * sims,
+                             graph_waves=0, max_levels=args.max_levels, tick_graph=False)
+    eng.env.rollout(args.opening_plies, rotate=True)
+    eng.start_async()
+    done, ms = _timed_async(eng, torch, dist, world, dev, barrier, G, 8, steps=2, warm=1)
+    return {"value": done / (ms * 1e-3), "unit": UNIT_MCTS, "trees_per_gpu": T, "network": "SplendorNNetB200 float32 (torch, tf32 off), plain launches", "ms": ms}
+
+
+def bench_config3_arena(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """BASELINE configs[3]: 3-player pit of two random-init networks (seeds 1, 2; seats [A,B,B] / [B,A,A], 1-2-2-1 order), playout-cap
+    randomisation on (prob_fullMCTS 0.25, ratio 5), every game a lane of BatchedArena; games/s and sims/s of whole games"""
+    n, T, sims = 3, 2048, 200
+    nets = [azg.FusedSplendorNNet(n, seed=1, device=local), azg.FusedSplendorNNet(n, seed=2, device=local)]
+    pit = azg.BatchedArena(n, nets, num_sims=sims, device=local, seed=args.seed, game_base=rank * T, prob_full=0.25, ratio_full=5, node_cap=16 * sims, pool_nodes=6 * sims)
+    barrier()
+    t0 = time.perf_counter()
+    one, two, draws, d = pit.play_games(T)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([d["total_sims"], T - d["unfinished"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dt = float(dt.item())
+    return {"games_per_s": int(tot[1]) / dt, "sims_per_s": int(tot[0]) / dt, "games_per_gpu": T, "sims_per_full_move": sims, "seconds": dt,
+            "one_two_draws_rank0": [one, two, draws], "plies": d["plies"], "unfinished_rank0": d["unfinished"],
+            "workload": "configs[3]: 3p Arena pit of two random-init SplendorNNet (fused bf16), playout cap 0.25 / ratio 5, lock-step moves, Philox reveals"}
+
+
+def bench_config2_env4p(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """BASELINE configs[2]: 4 players, 16,384 lanes, Philox reveals keyed (seed 1234, game, ply), canonical rotation after every ply"""
+    import copy
+    a = copy.copy(args)
+    a.players, a.lanes, a.seed, a.no_sweep, a.e2e_lanes, a.env_steps = 4, 16384, 1234, True, 16384, 20
+    out = bench_env(a, torch, dist, azg, world, rank, local, dev, barrier)
+    out["config"]["workload"] = "configs[2]: 4p, 16,384 game lanes per GPU, Philox reveals (seed 1234), canonical rotation every ply, random legal moves"
+    out["note"] = "16,384 lanes are 512 lane tiles = 3.5 per SM: this point is launch- and latency-bound, configs[4] (1 Mi lanes) is the throughput point"
+    return out
 
 
 def bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier):
@@ -580,29 +757,45 @@ def bench_env(args, torch, dist, azg, world, rank, local, dev, barrier):
                      "algorithmic_bytes_per_step": B_STEP[n], "avg_launch_ms": avg_ms},
         "gpu_launches": env.launches - launches0, "games_finished": cnt[0] * world, "clocks": clk.summary(),
     }
-    # e2e through the reference-facing call with HOST buffers
+    # e2e through the reference-facing calls with HOST buffers (pinned): every call uploads the boards (+ actions) and downloads the results
     game = azg.SplendorGame(n, seed=args.seed, device=local)
     Le = args.e2e_lanes
-    eenv = game._env_for(Le)
     src = azg.SplendorEnv(n, Le, device=local, seed=args.seed, game_base=rank * Le)
     src.reset(); src.rollout(20, rotate=True); src.step(None, want_next=True)
-    eenv._h_in.copy_(src.states().cpu()); eenv._h_act.copy_(src.next_actions.cpu())
-    for _ in range(3):
-        game._step_pinned(eenv, 0, False, True)
-    barrier()
-    ke = 5
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        game._step_pinned(eenv, 0, False, True)     # includes H2D of boards+actions and D2H of boards+masks+end vectors
-    barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["e2e"] = {"value": world * Le * ke / float(t.item()), "unit": UNIT_ENV,
-                  "h2d_bytes_per_step": Le * (env.S + 2), "d2h_bytes_per_step": Le * (env.S + 406 + 4 * n),
-                  "call": "SplendorGame.getNextStateBatch (pinned host int8[L,R,7] boards + actions in; next canonical boards, "
-                          "bool[L,406] masks, float32[L,n] end vectors out)", "lanes_per_call": Le}
+    boards0 = src.states().cpu().numpy(); acts0 = src.next_actions.cpu().numpy()
+    pipe = game._pipe_for(Le)
+
+    def timed(fn, ke=5):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            fn()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / ke
+    pipe.h_in.numpy()[...] = boards0.reshape(Le, -1); pipe.h_act.numpy()[...] = acts0
+    dt1 = timed(lambda: pipe.step(0, False, True))                      # getNextStateBatch(..., packed_masks=True) on its pinned buffers
+    Kr = args.plies
+    dtk = timed(lambda: pipe.rollout(Kr))                               # rolloutBatch(boards, plies): one round trip per Kr plies
+    eenv = game._env_for(Le)
+    eenv._h_in.copy_(torch.from_numpy(boards0)); eenv._h_act.copy_(torch.from_numpy(acts0))
+    dt0 = timed(lambda: game._step_pinned(eenv, 0, False, True))        # the one-stream call with bool[L,406] masks
+    h1, d1 = pipe.bytes_per_call(False)
+    hk, dk = pipe.bytes_per_call(True)
+    out["e2e"] = {"value": world * Le * Kr / dtk, "unit": UNIT_ENV, "h2d_bytes_per_step": hk, "d2h_bytes_per_step": dk,
+                  "call": f"SplendorGame.rolloutBatch(host int8[L,R,7] boards, plies={Kr}): the Arena.playGame loop with random players, {Kr} plies per "
+                          f"host round trip (pinned boards up, boards + counters down, {len(pipe.parts)} lane chunks on their own streams)",
+                  "lanes_per_call": Le, "plies_per_call": Kr,
+                  "single_step": {"value": world * Le / dt1, "unit": UNIT_ENV, "h2d_bytes_per_step": h1, "d2h_bytes_per_step": d1,
+                                  "call": "SplendorGame.getNextStateBatch(host boards, actions, packed_masks=True): one ply per round trip; next canonical boards, "
+                                          "52-byte legal masks and end vectors come back; chunked over streams (upload / kernels / download overlap)"},
+                  "single_step_bool_masks": {"value": world * Le / dt0, "unit": UNIT_ENV, "h2d_bytes_per_step": Le * (env.S + 2),
+                                             "d2h_bytes_per_step": Le * (env.S + 406 + 4 * n),
+                                             "call": "SplendorGame.getNextStateBatch(host boards, actions): the reference's bool[L,406] masks, one stream"}}
     del env
     if rank == 0 and not args.no_sweep:
         out["sweep"] = sweep(azg, torch, n, local, args)
@@ -635,6 +828,8 @@ def main():
     args = parse()
     if args.cpu_mcts_worker:
         return cpu_mcts_worker(args.cpu_mcts_worker)
+    if args.cpu_ref_worker:
+        return cpu_ref_worker(args.cpu_ref_worker)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -677,6 +872,10 @@ def main():
         if args.wide_trees > 0:
             line["mcts_wide"] = bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier)
             torch.cuda.empty_cache()
+        if not args.no_extra:
+            for key, fn in (("config2_genbu", bench_config2_genbu), ("fp32_network", bench_fp32_network), ("config3_arena_3p", bench_config3_arena)):
+                line[key] = fn(args, torch, dist, azg, world, rank, local, dev, barrier)
+                torch.cuda.empty_cache()
     if args.workload in ("both", "env"):
         envres = bench_env(args, torch, dist, azg, world, rank, local, dev, barrier)
         if line is None:
@@ -688,15 +887,24 @@ def main():
                     "sweep": envres.get("sweep"), "clocks": envres["clocks"]}
         else:
             line["env_steps"] = envres
+        if not args.no_extra:
+            line["config2_env_4p"] = bench_config2_env4p(args, torch, dist, azg, world, rank, local, dev, barrier)
     if rank == 0:
         if not args.no_cpu:
             if line["metric"] == METRIC_MCTS:
-                sims_cpu = min(args.sims, 400)
+                sims_cpu = args.sims
                 cpu_moves = max(3, int(args.cpu_seconds * 4000 / sims_cpu))     # ~cpu_seconds of work per core at ~4k sims/s
                 rate, cores, tot, secs = cpu_mcts(n, sims_cpu, cpu_moves, args.seed, args.fixed_net)
                 line["cpu_baseline"] = {"value": rate, "unit": UNIT_MCTS, "cores": cores, "kind": "port",
                                         "sample": f"{cores} processes x {cpu_moves} moves x {sims_cpu} sims/move = {tot} simulations in {secs:.1f} s (C port of "
                                                   f"MCTS.py + per-leaf torch-CPU float32 SplendorNNet predict, one thread per core)"}
+                if reference_dir() is not None and not args.no_extra:
+                    ref = cpu_mcts(n, sims_cpu, max(2, cpu_moves // 2), args.seed, args.fixed_net, worker="--cpu-ref-worker")
+                    if ref is not None:
+                        line["cpu_baseline_reference"] = {"value": ref[0], "unit": UNIT_MCTS, "cores": ref[1], "kind": "reference",
+                                                          "sample": f"{ref[1]} processes x {max(2, cpu_moves // 2)} moves x {sims_cpu} sims/move = {ref[2]} simulations in "
+                                                                    f"{ref[3]:.1f} s (the reference's own MCTS.py + Numba Board + NNetWrapper.predict, one thread per core, "
+                                                                    f"JIT and one warm-up move excluded)"}
             if args.workload in ("both", "env"):
                 v, cores, games, plies, dtc = cpu_rollouts(n, args.seed, args.cpu_seconds)
                 cb = {"value": v, "unit": UNIT_ENV, "cores": cores, "kind": "port",
