@@ -330,3 +330,43 @@ def test_no_gpu_fallback_is_loud():
     assert az._native.lib().spl_ctx_create(2, 10, 7, 99, C.byref(h)) < 0      # bad device -> error code, nothing thrown
     assert az._native.lib().spl_ctx_create(5, 10, 7, 0, C.byref(h)) < 0
     assert b"bad" in az._native.lib().spl_last_error()
+
+
+@pytest.mark.parametrize("n,L", [(2, 20000), (3, 1000)])
+def test_packed_pipelined_batch_call_equals_the_plain_call(n, L):
+    """getNextStateBatch(..., packed_masks=True) - lane chunks on their own streams, 52-byte masks - returns what the one-stream call
+    with bool[L,406] masks returns, and what the oracle computes, for a ragged lane count (not a multiple of 32 or of the chunks)"""
+    az = _az()
+    game = az.SplendorGame(n, seed=77)
+    src = az.SplendorEnv(n, L, seed=5)
+    src.reset(); src.rollout(30, rotate=True); src.step(None, want_next=True)
+    boards, acts = src.states().cpu().numpy(), src.next_actions.cpu().numpy()
+    b0, v0, e0 = [x.copy() for x in game.getNextStateBatch(boards, 0, acts, deterministic=True)]
+    b1, m1, e1 = [x.copy() for x in game.getNextStateBatch(boards, 0, acts, deterministic=True, packed_masks=True)]
+    assert m1.dtype == np.uint32 and m1.shape == (L, 13)
+    assert np.array_equal(b0, b1) and np.array_equal(e0, e1) and np.array_equal(v0, game.unpack_masks(m1))
+    for g in range(0, L, max(1, L // 40)):
+        ob = po.Board(n).set_state(boards[g])
+        nxt = ob.make_move(int(acts[g]), 0, -1); ob.swap_players(nxt)
+        assert np.array_equal(ob.state, b1[g]) and np.array_equal(ob.valid_moves(0), v0[g]) and np.array_equal(ob.check_end_game(), e1[g])
+
+
+def test_rollout_batch_round_trip():
+    """rolloutBatch: K plies of random legal play per host round trip; the boards that come back are legal game states `plies`
+    plies further (or restarted), tokens are conserved, the counters add up"""
+    az = _az()
+    n, L, K = 2, 5000, 16
+    game = az.SplendorGame(n, seed=3)
+    src = az.SplendorEnv(n, L, seed=8)
+    src.reset(); src.rollout(10, rotate=True)
+    boards = src.states().cpu().numpy()
+    out, finished, plies = game.rolloutBatch(boards, K)
+    out = out.copy()
+    assert plies == L * K and 0 <= finished < L
+    ply_in, ply_out = boards[:, 0, 6].astype(np.uint8).astype(int), out[:, 0, 6].astype(np.uint8).astype(int)
+    assert ((ply_out == ply_in + K) | (ply_out < ply_in + K)).all() and (ply_out == ply_in + K).mean() > 0.9
+    gems = out[:, 0, :5].astype(int) + out[:, 34, :5] + out[:, 35, :5]
+    assert (gems == 4).all()                                     # 4 gems per colour in a 2-player game, bank + both players
+    for g in range(0, L, 250):
+        ob = po.Board(n).set_state(out[g])
+        assert ob.valid_moves(0).any()
