@@ -11,7 +11,7 @@ from .mcts import MCTS, MCTSArena
 from .nnet import FusedSplendorNNet, SplendorNNetB200
 from .selfplay import SelfPlayEngine
 from .arena import BatchedArena
-from . import examples, nnet, trainbatch
+from . import examples, multigpu, nnet, trainbatch
 from .trainbatch import TrainBatcher
 
-__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "BatchedArena", "TrainBatcher", "nnet", "examples", "trainbatch", "observation_size", "action_size", "rows", "_native"]
+__all__ = ["SplendorEnv", "SplendorGame", "Board", "MCTS", "MCTSArena", "SplendorNNetB200", "FusedSplendorNNet", "SelfPlayEngine", "BatchedArena", "TrainBatcher", "nnet", "examples", "multigpu", "trainbatch", "observation_size", "action_size", "rows", "_native"]

@@ -557,8 +557,15 @@ def check_example_exchange(args, torch, dist, azg, world, rank, local):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     cnt = torch.tensor([local_n], dtype=torch.int64, device=f"cuda:{local}")
     dist.all_reduce(cnt)
+    # the accepted network goes from rank 0 to everybody (Coach.py:156-165); every rank then evaluates the same rows identically
+    sd = azg.multigpu.broadcast_weights(azg.nnet.random_state_dict(n, seed=1000 + rank), src=0, device=f"cuda:{local}")
+    net2 = azg.FusedSplendorNNet(n, state_dict={k: v.cpu() for k, v in sd.items()}, device=local)
+    pi, _ = net2(mine["board"][:64].contiguous(), mine["valids"][:64].contiguous()) if local_n >= 64 else (torch.zeros(1, device=f"cuda:{local}"), None)
+    w = torch.tensor([float(sum(float(v.double().sum()) for v in sd.values()))], dtype=torch.float64, device=f"cuda:{local}")
+    wl, wh = w.clone(), w.clone()
+    dist.all_reduce(wl, op=dist.ReduceOp.MIN); dist.all_reduce(wh, op=dist.ReduceOp.MAX)
     return {"examples_local_rank0": local_n, "examples_gathered": total, "sum_of_local_counts": int(cnt.item()),
-            "identical_on_all_ranks": bool(torch.equal(lo, hi)), "backend": "nccl"}
+            "identical_on_all_ranks": bool(torch.equal(lo, hi)), "weights_broadcast_identical": bool(torch.equal(wl, wh)), "backend": "nccl"}
 
 
 # ----------------------------------------------------------------------------------------------

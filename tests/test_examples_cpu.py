@@ -82,6 +82,34 @@ def test_gather_examples_two_ranks_gloo():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _worker_mg(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from azg_b200 import multigpu as mg, nnet
+    ok = mg.shard(10) == ((0, 5) if rank == 0 else (5, 10)) and mg.shard(7, 1, 3) == (3, 5)
+    sd = nnet.random_state_dict(2, seed=40 + rank)                     # every rank starts from its own weights
+    got = mg.broadcast_weights(sd, src=1)
+    want = nnet.random_state_dict(2, seed=41)
+    ok &= all(torch.equal(got[k], want[k]) and got[k].dtype == want[k].dtype for k in want)
+    ok &= mg.all_reduce_counts([3 + rank, 10 * rank, 1]) == [7, 10, 2]
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_and_count_reduction_two_ranks_gloo():
+    """the accepted network's weights go to every rank, arena tallies are summed"""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_mg, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_game_sharding_is_independent_of_world_size():
     """lane l of rank r is global game r*L + l: the Philox start of a game depends on its id only (CPU check on the rules core)"""
     from tests.hostsim import sim as hs
