@@ -123,9 +123,9 @@ def lib():
         L.spl_symmetries.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
         L.spl_mcts_record_bytes.argtypes = [ci, ci]
         L.spl_mcts_record_bytes.restype = C.c_size_t
-        L.spl_mcts_arena_bytes.argtypes = [ci, ci, ci, C.c_size_t]
+        L.spl_mcts_arena_bytes.argtypes = [ci, ci, ci, C.c_size_t, ci]
         L.spl_mcts_arena_bytes.restype = C.c_size_t
-        L.spl_mcts_create.argtypes = [vp, ci, ci, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]
+        L.spl_mcts_create.argtypes = [vp, ci, ci, C.c_size_t, ci, vp, C.c_size_t, C.POINTER(vp)]
         L.spl_mcts_set_episodes.argtypes = [vp, vp]
         L.spl_mcts_pool_stats.argtypes = [vp, vp, vp]
         L.spl_mcts_destroy.argtypes = [vp]

@@ -69,13 +69,17 @@ __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSe
                        dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, episodes ? episodes[t] : 0u, sc.st, sc.words, sc.dwords);
 }
 
-template <int N>
+template <int N, bool VL>
 __global__ void __launch_bounds__(MW * 32, 7) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int max_levels, int8_t* leaf_states,
                                                                   uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
-    mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+    for (int s = 0; s < (VL ? A.n_slots : 1); s++) {
+        const size_t r = (size_t)mcts_row(A, t, s);
+        mcts_descend_tree<N, VL>(w, A, t, s, P, 1, max_levels, leaf_states + r * MctsLay<N>::S, leaf_valids + r * SPL_ACTIONS);
+        __syncwarp();
+    }
 }
 
 #define RW 2   // warps per CTA of the rules kernel
@@ -96,13 +100,14 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     constexpr int STRIDE = RulesSmem<N>::STRIDE, CH = ML::SP / 16;
     extern __shared__ __align__(16) int8_t tile_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rows = A.n_trees * A.n_slots;            // a row = (tree, in-flight slot)
     const int t0 = (blockIdx.x * RW + warp) * TPW, t = t0 + lane;
     int8_t* wsm = tile_smem + (size_t)warp * TPW * STRIDE;
     bool pending = false;
     uint32_t parent = 0u;
     int action = 0;
-    if (lane < TPW && t < A.n_trees) {
-        const MctsTree* T = A.trees + t;
+    if (lane < TPW && t < n_rows) {
+        const MctsSlot* T = A.trees[t / A.n_slots].slot + t % A.n_slots;
         const int pe = T->pend_edge;
         if (pe >= 0 && T->leaf == 0u) {
             pending = true;
@@ -112,7 +117,8 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     }
     const uint32_t pmask = __ballot_sync(0xffffffffu, pending);
     if (pmask == 0u) return;
-    if (t0 < A.n_trees) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
+    const bool prof_ok = A.n_slots == 1 && t0 < A.n_trees;
+    if (prof_ok) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
 #pragma unroll
     for (int j = 0; j < TPW; j++) {
         const uint32_t par = __shfl_sync(0xffffffffu, parent, j);
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    if (t0 < A.n_trees) PROF_STAMP(A, t0, 8, clock64());
+    if (prof_ok) PROF_STAMP(A, t0, 8, clock64());
     bool ended = false;
     float es[N];
     uint32_t m[SPL_MASK_WORDS];
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
         ended = mcts_rules_core<N>(s, action, rules, es, m);
     }
     __syncwarp();
-    if (t0 < A.n_trees) PROF_STAMP(A, t0, 9, clock64());
+    if (prof_ok) PROF_STAMP(A, t0, 9, clock64());
 #pragma unroll
     for (int j = 0; j < TPW; j++) {
         if ((pmask >> j) & 1u) {
@@ -146,18 +152,18 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     }
     if (pending) {
 #pragma unroll
-        for (int i = 0; i < SPL_MASK_WORDS; i++) A.stage_mask[(size_t)i * A.n_trees + t] = m[i];
+        for (int i = 0; i < SPL_MASK_WORDS; i++) A.stage_mask[(size_t)i * n_rows + t] = m[i];
 #pragma unroll
         for (int i = 0; i < 4; i++) A.stage_es[(size_t)t * 4 + i] = i < N ? es[i] : 0.f;
         A.stage_ended[t] = ended ? 1 : 0;
         A.leaf_src[t] = 1;   // if this child needs the network, its input row is the staging row (spl_mcts_wave_nnet)
     }
-    if (t0 < A.n_trees) { PROF_STAMP(A, t0, 10, clock64()); PROF_STAMP(A, t0, 11, prof_globaltimer()); }
+    if (prof_ok) { PROF_STAMP(A, t0, 10, clock64()); PROF_STAMP(A, t0, 11, prof_globaltimer()); }
 }
 
 template <int N>
 static cudaError_t launch_rules(const MctsArena& A, const SplRules& rules, int tpw, cudaStream_t st) {
-    const int warps = (A.n_trees + tpw - 1) / tpw, grid = (warps + RW - 1) / RW;
+    const int warps = (A.n_trees * A.n_slots + tpw - 1) / tpw, grid = (warps + RW - 1) / RW;
     const int smem = RW * tpw * RulesSmem<N>::STRIDE;
     switch (tpw) {
         case 16: mcts_rules_kernel<N, 16><<<grid, RW * 32, smem, st>>>(A, rules); break;
@@ -168,34 +174,44 @@ static cudaError_t launch_rules(const MctsArena& A, const SplRules& rules, int t
     return cudaGetLastError();
 }
 
-template <int N>
+template <int N, bool VL>
 __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, MctsSearchParams P, int8_t* leaf_states, uint8_t* leaf_valids,
                                                                  uint8_t* leaf_flags, int32_t* counters, bool emit_rows) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
     PROF_STAMP(A, t, 12, prof_globaltimer()); PROF_STAMP(A, t, 13, clock64());
-    const int leaf = mcts_attach_tree<N>(w, A, t, P, A.stage_state + (size_t)t * A.sp, A.stage_ended[t] != 0, A.stage_es + (size_t)t * 4,
-                                         A.stage_mask + t, A.n_trees, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS,
-                                         emit_rows);
+    const int n_rows = A.n_trees * A.n_slots;
+    int leaves = 0;
+    bool waiting = false;
+    for (int s = 0; s < (VL ? A.n_slots : 1); s++) {   // the slots of a tree one after the other: node creation stays deterministic
+        const size_t r = (size_t)mcts_row(A, t, s);
+        const int leaf = mcts_attach_tree<N, VL>(w, A, t, s, P, A.stage_state + r * A.sp, A.stage_ended[r] != 0, A.stage_es + r * 4,
+                                                 A.stage_mask + r, n_rows, leaf_states + r * MctsLay<N>::S, leaf_valids + r * SPL_ACTIONS, emit_rows);
+        __syncwarp();
+        if (w.lane == 0) leaf_flags[r] = (uint8_t)leaf;
+        leaves += leaf;
+        waiting |= A.trees[t].slot[s].pend_edge >= 0 || A.trees[t].slot[s].cur != 0u;
+    }
     PROF_STAMP(A, t, 14, clock64()); PROF_STAMP(A, t, 15, prof_globaltimer());
-    if (w.lane == 0) {
-        leaf_flags[t] = (uint8_t)leaf;
-        if (counters) {   // last round of the wave
-            const MctsTree* T = A.trees + t;
-            if (leaf) atomicAdd(&counters[0], 1);
-            if (T->status == 0u && (leaf || T->pend_edge >= 0 || T->sims_done < T->sims_target)) atomicAdd(&counters[1], 1);
-        }
+    if (w.lane == 0 && counters) {   // last round of the wave
+        const MctsTree* T = A.trees + t;
+        if (leaves) atomicAdd(&counters[0], leaves);
+        if (T->status == 0u && (leaves || waiting || T->sims_done < T->sims_target)) atomicAdd(&counters[1], 1);
     }
 }
 
-template <int N>
+template <int N, bool VL>
 __global__ void __launch_bounds__(MW * 32, 8) mcts_expand_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
-    mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
+    for (int s = 0; s < (VL ? A.n_slots : 1); s++) {
+        const size_t r = (size_t)mcts_row(A, t, s);
+        mcts_expand_tree<N, VL>(w, A, t, s, P, pi + r * SPL_ACTIONS, v + r * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
+        __syncwarp();
+    }
 }
 
 // rotation of a contiguous block of BYTES bytes by `shift` bytes, all lanes of the warp: new[i] = old[(i + shift) mod BYTES]
@@ -223,7 +239,7 @@ __device__ __forceinline__ void coop_roll_rows(int8_t* base, int shift, int lane
 template <int N>
 __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, const SplRules& rules, int8_t* wsm, int lane) {
     constexpr int CH = MctsLay<N>::SP / 16;
-    const MctsTree* T = A.trees + t;
+    const MctsSlot* T = A.trees[t].slot;     // (the rules step inside the descent kernel is a one-leaf-per-tree feature: slot 0)
     const int pe = T->pend_edge;
     if (pe < 0 || T->leaf != 0u) return;
     const int action = (int)mcts_edges(A, T->pend_parent, pe >> 16).ca[pe & 0xFFFF].action;
@@ -288,7 +304,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
 
 // expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree);
 // RULES: followed by the rules step of the tree's pending edge (spl_mcts_wave_nnet; otherwise mcts_rules_kernel does it)
-template <int N, bool RULES>
+template <int N, bool RULES, bool VL>
 __global__ void __launch_bounds__(MW * 32, 7) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
                                                                          int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
@@ -299,12 +315,25 @@ __global__ void __launch_bounds__(MW * 32, 7) mcts_expand_descend_kernel(MctsAre
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // once every block of this grid is running, the next grid may move in behind it
     if (t >= A.n_trees) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
+    if (VL) {   // several simulations per tree and wave: all expansions / backups first, then the descents one after the other
+        for (int s = 0; s < A.n_slots; s++) {
+            const size_t r = (size_t)mcts_row(A, t, s);
+            mcts_expand_tree<N, true>(w, A, t, s, P, pi + r * SPL_ACTIONS, v + r * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
+            __syncwarp();
+        }
+        for (int s = 0; s < A.n_slots; s++) {
+            const size_t r = (size_t)mcts_row(A, t, s);
+            mcts_descend_tree<N, true>(w, A, t, s, P, 1, max_levels, leaf_states + r * MctsLay<N>::S, leaf_valids + r * SPL_ACTIONS);
+            __syncwarp();
+        }
+        return;
+    }
     PROF_STAMP(A, t, 0, prof_globaltimer()); PROF_STAMP(A, t, 1, clock64());
-    mcts_expand_tree<N>(w, A, t, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
+    mcts_expand_tree<N, false>(w, A, t, 0, P, pi + (size_t)t * SPL_ACTIONS, v + (size_t)t * N, dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, sc.dwords);
     w.sync();
     PROF_STAMP(A, t, 2, clock64());
-    const int r = mcts_descend_tree<N>(w, A, t, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
-    PROF_STAMP(A, t, 3, clock64()); PROF_STAMP(A, t, 4, (long long)r * 1000 + A.trees[t].path_len);
+    const int r = mcts_descend_tree<N, false>(w, A, t, 0, P, 1, max_levels, leaf_states + (size_t)t * MctsLay<N>::S, leaf_valids + (size_t)t * SPL_ACTIONS);
+    PROF_STAMP(A, t, 3, clock64()); PROF_STAMP(A, t, 4, (long long)r * 1000 + A.trees[t].slot[0].path_len);
     if (RULES) {
         if (r == 2) rules_for_own_tree<N>(A, t, P.rules, sc.st, w.lane);
         PROF_STAMP(A, t, 9, clock64());
@@ -396,7 +425,7 @@ struct ArenaPlan {
     uint32_t n_pool_pages;
     size_t off_pool, off_fq, off_ctl, off_tpages, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, off_lsrc, total;
 };
-static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes) {
+static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes, int K) {
     ArenaPlan p;
     p.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
     p.hcap = 64;
@@ -418,12 +447,13 @@ static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes) {
     p.off_tpages = o; o = align_up(o + (size_t)T * p.max_pages * 4, 256);
     p.off_htab = o;   o = align_up(o + (size_t)T * p.hcap * 4, 256);
     p.off_trees = o;  o = align_up(o + (size_t)T * sizeof(MctsTree), 256);
-    p.off_path = o;   o = align_up(o + (size_t)T * p.max_depth * 8, 256);
-    p.off_sstate = o; o = align_up(o + (size_t)T * p.sp, 256);
-    p.off_smask = o;  o = align_up(o + (size_t)T * 13 * 4, 256);
-    p.off_ses = o;    o = align_up(o + (size_t)T * 16, 256);
-    p.off_sended = o; o = align_up(o + (size_t)T, 256);
-    p.off_lsrc = o;   o = align_up(o + (size_t)T, 256);
+    const size_t rows = (size_t)T * K;      // (tree, in-flight slot)
+    p.off_path = o;   o = align_up(o + rows * p.max_depth * 8, 256);
+    p.off_sstate = o; o = align_up(o + rows * p.sp, 256);
+    p.off_smask = o;  o = align_up(o + rows * 13 * 4, 256);
+    p.off_ses = o;    o = align_up(o + rows * 16, 256);
+    p.off_sended = o; o = align_up(o + rows, 256);
+    p.off_lsrc = o;   o = align_up(o + rows, 256);
     p.total = o;
     return p;
 }
@@ -442,16 +472,17 @@ size_t spl_mcts_record_bytes(int n_players, int n_edges) {
     return (size_t)(32 + sp + 24 * n_edges + 31) / 32 * 32;
 }
 
-size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes) {
-    if (n_players < 2 || n_players > 4 || n_trees <= 0 || node_limit <= 0) return 0;
-    return plan_arena(n_players, n_trees, node_limit, pool_bytes).total;
+size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes, int leaves_per_tree) {
+    if (n_players < 2 || n_players > 4 || n_trees <= 0 || node_limit <= 0 || leaves_per_tree < 1 || leaves_per_tree > MCTS_KMAX) return 0;
+    return plan_arena(n_players, n_trees, node_limit, pool_bytes, leaves_per_tree).total;
 }
 
-int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, void* arena, size_t arena_bytes, spl_mcts** out) {
+int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, int leaves_per_tree, void* arena, size_t arena_bytes, spl_mcts** out) {
     if (!ctx || !out || !arena || n_trees <= 0 || node_limit < 4) return spl_fail_(SPL_E_ARG, "spl_mcts_create: bad argument");
+    if (leaves_per_tree < 1 || leaves_per_tree > MCTS_KMAX) return spl_fail_(SPL_E_ARG, "spl_mcts_create: leaves_per_tree must be 1..4");
     if (node_limit > (1 << 24)) return spl_fail_(SPL_E_ARG, "spl_mcts_create: node_limit too large");
     if (((uintptr_t)arena & 255u) != 0) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena must be 256-byte aligned");
-    const ArenaPlan p = plan_arena(ctx->n, n_trees, node_limit, pool_bytes);
+    const ArenaPlan p = plan_arena(ctx->n, n_trees, node_limit, pool_bytes, leaves_per_tree);
     if (arena_bytes < p.total) return spl_fail_(SPL_E_ARG, "spl_mcts_create: arena smaller than spl_mcts_arena_bytes");
     if ((size_t)p.n_pool_pages * MCTS_PAGE_UNITS > 0xFFFFFFFFull) return spl_fail_(SPL_E_ARG, "spl_mcts_create: pool larger than 128 GB");
     static_assert(sizeof(MctsNode) == 32 && sizeof(MctsPN) == 8 && sizeof(MctsCA) == 8 && sizeof(MctsTree) == 192, "arena record sizes");
@@ -459,7 +490,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes
     m->ctx = ctx;
     char* base = (char*)arena;
     m->A.n_trees = n_trees; m->A.node_limit = node_limit; m->A.hcap = p.hcap; m->A.sp = p.sp; m->A.max_depth = p.max_depth;
-    m->A.max_pages = p.max_pages; m->A.n_pool_pages = p.n_pool_pages;
+    m->A.max_pages = p.max_pages; m->A.n_pool_pages = p.n_pool_pages; m->A.n_slots = leaves_per_tree;
     m->A.pool = (uint8_t*)(base + p.off_pool);
     m->A.fq_slots = (uint32_t*)(base + p.off_fq);
     m->A.fq_ctl = (int32_t*)(base + p.off_ctl);
@@ -485,8 +516,8 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes
     // rules step inside the descent kernel: one launch boundary less on the critical path of a wave, but the step then runs on one
     // lane per warp - right while every tree's warp is resident at once (latency-bound, measured 102 -> 98 us per wave at 4096
     // trees), wrong in the throughput regime (65,536 trees: 32x the issue slots of mcts_rules_kernel)
-    m->fuse_rules = n_trees <= 6144;
-    if (const char* e = getenv("SPL_MCTS_FUSE_RULES")) m->fuse_rules = atoi(e) != 0;   // tuning hook
+    m->fuse_rules = n_trees <= 6144 && leaves_per_tree == 1;
+    if (const char* e = getenv("SPL_MCTS_FUSE_RULES")) m->fuse_rules = atoi(e) != 0 && leaves_per_tree == 1;   // tuning hook
     m->pdl = 1;
     if (const char* e = getenv("SPL_MCTS_PDL")) m->pdl = atoi(e) != 0;   // tuning hook
     m->side = nullptr; m->ev_fork = nullptr; m->ev_join = nullptr;
@@ -549,12 +580,15 @@ int spl_mcts_select(spl_mcts* m, int8_t* leaf_states, uint8_t* leaf_valids, uint
     ENTER_M(m);
     if (!leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_select: bad argument");
     const SplRules rules = m->ctx->rules;
+    const bool vl = m->A.n_slots > 1;
     DISPATCH_N(m->ctx->n, {
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
-            mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+            if (vl) mcts_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+            else mcts_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
             CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
-            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
+            if (vl) mcts_attach_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
+            else mcts_attach_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
         }
     });
     CU(cudaGetLastError());
@@ -566,13 +600,17 @@ int spl_mcts_expand_select(spl_mcts* m, const float* pi, const float* v, const d
     ENTER_M(m);
     if (!pi || !v || !leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_expand_select: bad argument");
     const SplRules rules = m->ctx->rules;
+    const bool vl = m->A.n_slots > 1;
     DISPATCH_N(m->ctx->n, {
         for (int r = 0; r < m->rounds; r++) {
             int32_t* cnt = r == m->rounds - 1 ? counters : nullptr;
-            if (r == 0) mcts_expand_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
-            else mcts_descend_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+            if (r == 0 && vl) mcts_expand_descend_kernel<N, false, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            else if (r == 0) mcts_expand_descend_kernel<N, false, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            else if (vl) mcts_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+            else mcts_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
             CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
-            mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
+            if (vl) mcts_attach_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
+            else mcts_attach_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, cnt, true);
         }
     });
     CU(cudaGetLastError());
@@ -584,6 +622,8 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
     ENTER_M(m);
     if (!nnet_blob || !pi || !v || !leaf_states || !leaf_valids || !leaf_flags) return spl_fail_(SPL_E_ARG, "spl_mcts_wave_nnet: bad argument");
     const SplRules rules = m->ctx->rules;
+    const bool vl = m->A.n_slots > 1;
+    const int n_rows = m->A.n_trees * m->A.n_slots;
     DISPATCH_N(m->ctx->n, {
         m->P.rules = rules;
         if (m->fuse_rules && m->pdl) {
@@ -596,11 +636,11 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(MW * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&cfg, mcts_expand_descend_kernel<N, true>, m->A, m->P, (const float*)pi, (const float*)v, dir_values, m->max_levels,
+            CU(cudaLaunchKernelEx(&cfg, mcts_expand_descend_kernel<N, true, false>, m->A, m->P, (const float*)pi, (const float*)v, dir_values, m->max_levels,
                                   leaf_states, leaf_valids));
             CU(cudaEventRecord(m->ev_fork, st));
             CU(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-            mcts_attach_kernel<N><<<grid, MW * 32, 0, m->side>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
+            mcts_attach_kernel<N, false><<<grid, MW * 32, 0, m->side>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
             CU(cudaEventRecord(m->ev_join, m->side));
             const int rc = spl_nnet_forward_rows_(m->ctx, nnet_blob, leaf_states, leaf_valids, m->A.leaf_src, m->A.stage_state, m->A.sp, m->A.stage_mask,
                                                   m->A.n_trees, m->A.n_trees, pi, v, st, true);
@@ -610,9 +650,10 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
             return SPL_OK;
         }
         if (m->fuse_rules) {
-            mcts_expand_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            mcts_expand_descend_kernel<N, true, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
         } else {
-            mcts_expand_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            if (vl) mcts_expand_descend_kernel<N, false, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
+            else mcts_expand_descend_kernel<N, false, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
             CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
         }
         // fork: the network reads the rows the descent (leaf rows) or the rules kernel (staging rows) just wrote, while the
@@ -620,10 +661,11 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
         CU(cudaEventRecord(m->ev_fork, st));
         CU(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
         const int rc = spl_nnet_forward_rows_(m->ctx, nnet_blob, leaf_states, leaf_valids, m->A.leaf_src, m->A.stage_state, m->A.sp, m->A.stage_mask,
-                                              m->A.n_trees, m->A.n_trees, pi, v, m->side, false);
+                                              n_rows, n_rows, pi, v, m->side, false);
         if (rc != SPL_OK) return rc;
         CU(cudaEventRecord(m->ev_join, m->side));
-        mcts_attach_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
+        if (vl) mcts_attach_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
+        else mcts_attach_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, counters, false);
         CU(cudaStreamWaitEvent(st, m->ev_join, 0));
     });
     CU(cudaGetLastError());
@@ -633,7 +675,8 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
 int spl_mcts_expand(spl_mcts* m, const float* pi, const float* v, const double* dir_values, void* stream) {
     ENTER_M(m);
     if (!pi || !v) return spl_fail_(SPL_E_ARG, "spl_mcts_expand: bad argument");
-    DISPATCH_N(m->ctx->n, mcts_expand_kernel<N><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values));
+    if (m->A.n_slots > 1) { DISPATCH_N(m->ctx->n, (mcts_expand_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values))); }
+    else { DISPATCH_N(m->ctx->n, (mcts_expand_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values))); }
     CU(cudaGetLastError());
     return SPL_OK;
 }

@@ -148,19 +148,24 @@ struct MctsEdgeV {   // one edge in registers
     uint32_t child;
     uint16_t action, child_ne;
 };
+#define MCTS_KMAX 4   // simulations one tree may have in flight (leaves_per_tree; 1 = the reference's sequential search)
+struct MctsSlot {     // state of one simulation in flight (it survives between the kernels of a wave)
+    uint32_t leaf;         // != 0: this node waits for the network
+    uint32_t cur;          // != 0: continue the descent at this node with path_len edges already recorded; 0: start at the root
+    uint32_t pend_parent;
+    int32_t pend_edge;     // >= 0: the descent stopped at this edge of pend_parent (position | edge count << 16), whose child state is being computed / attached
+    int32_t path_len;
+};
 struct MctsTree {   // 192 B
     int32_t n_nodes, n_edges;          // records / edges this tree holds
-    uint32_t root, leaf;               // record offsets, 0 = none
-    int32_t sims_done, sims_target, path_len;
+    uint32_t root;                     // record offset, 0 = none
+    int32_t sims_done, sims_target;
     uint32_t flags, status;
     int32_t nn_calls, resets, compactions;
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
     int32_t truncated; // searches cut short because the tree hit its node limit or the pool ran dry mid-move
     int32_t depth_sum; // sum of path lengths of the simulations since the last reset (diagnostics)
-    // state of the simulation in flight (it survives between the kernels of a wave):
-    uint32_t cur;         // != 0: continue the descent at this node with path_len edges already recorded; 0: start at the root
-    int32_t pend_edge;    // >= 0: the descent stopped at this edge of pend_parent (position | edge count << 16), whose child state is being computed / attached
-    uint32_t pend_parent;
+    MctsSlot slot[MCTS_KMAX];
     int32_t spec_hits;    // diagnostics: levels of the descents that started from the early-fetched child (see mcts_descend_tree)
     // storage
     int32_t n_pages;      // pages owned: tree_pages[t][0 .. n_pages)
@@ -169,10 +174,11 @@ struct MctsTree {   // 192 B
     uint32_t episode;     // the lane's episode counter at the last begin (Philox key of the on-device Dirichlet sampler)
     uint8_t deck[15];     // the deck bitmasks (rows 26 / 28 / 30, five colours each) every node of a homogeneous tree carries
     uint8_t hetero;       // 1: nodes with different decks may be present (roots that do not follow each other in one game)
-    int32_t pad[17];
+    int32_t pad[2];
 };
 struct MctsArena {
     int n_trees, node_limit, hcap, sp, max_depth, max_pages;
+    int n_slots;            // leaves_per_tree: 1 = parity mode; > 1: virtual-loss leaf batching (rows of the per-tree buffers below: tree * n_slots + slot)
     uint32_t n_pool_pages;
     uint8_t* pool;          // [n_pool_pages][32 KB]   node records of all trees (page 0 is never handed out: offset 0 = none)
     uint32_t* fq_slots;     // [n_pool_pages]          ring of free pages (0 = empty slot)
@@ -180,14 +186,14 @@ struct MctsArena {
     uint32_t* tree_pages;   // [T][max_pages]          pages of every tree; the upper half is room for the copy of a compaction
     uint32_t* htab;         // [T][hcap]               record offsets, linear probing
     MctsTree* trees;        // [T]
-    uint32_t* path;         // [T][max_depth][2]  (record, edge position | edge count << 16) of the current simulation
+    uint32_t* path;         // [T][n_slots][max_depth][2]  (record, edge position | edge count << 16) of the simulations in flight
     // staging between the rules kernel and the attach kernel (the child state of every tree's pending edge)
-    int8_t* stage_state;   // [T][sp]
-    uint32_t* stage_mask;  // [13][T]
-    float* stage_es;       // [T][4]
-    uint8_t* stage_ended;  // [T]
+    int8_t* stage_state;   // [T * n_slots][sp]
+    uint32_t* stage_mask;  // [13][T * n_slots]
+    float* stage_es;       // [T * n_slots][4]
+    uint8_t* stage_ended;  // [T * n_slots]
     long long* prof;       // diagnostics (normally NULL): [T][16] per-tree time stamps of the last wave (spl_mcts_debug_profile)
-    uint8_t* leaf_src;     // [T]  where the network input of the tree's leaf lives: 0 = its leaf row (bytes), 1 = the staging row
+    uint8_t* leaf_src;     // [T * n_slots]  where the network input of the tree's leaf lives: 0 = its leaf row (bytes), 1 = the staging row
                            //      (state bytes + mask words) the rules kernel wrote - lets the network start before the attach
 };
 struct MctsSearchParams {
@@ -215,6 +221,11 @@ struct AosAcc {   // the reference's own array order: cell (row, col) = byte 7*r
 };
 
 // record accessors: [MctsNode 32][state sp][Q double[k]][MctsPN[k]][MctsCA[k]], padded to a multiple of 32 bytes
+SPL_D uint32_t* mcts_path(const MctsArena& A, int t, int s) { return A.path + ((size_t)t * A.n_slots + s) * A.max_depth * 2; }
+SPL_D int mcts_row(const MctsArena& A, int t, int s) { return t * A.n_slots + s; }
+// with several simulations in flight (virtual loss) the top byte of an edge's N counts the simulations currently below it
+#define MCTS_VL_ONE 0x01000000
+#define MCTS_N_MASK 0x00FFFFFF
 SPL_D uint8_t* mcts_ptr(const MctsArena& A, uint32_t rec) { return A.pool + (size_t)rec * MCTS_UNIT; }
 SPL_D MctsNode* mcts_node(const MctsArena& A, uint32_t rec) { return reinterpret_cast<MctsNode*>(mcts_ptr(A, rec)); }
 SPL_D int8_t* mcts_state(const MctsArena& A, uint32_t rec) { return reinterpret_cast<int8_t*>(mcts_ptr(A, rec) + 32); }
@@ -541,9 +552,12 @@ SPL_D void mcts_root_noise(const W& w, MctsPN* ed, int k, const MctsSearchParams
 
 // ------------------------------------------------------------------------------------------
 // pick_highest_UCB :199-219 over the node's edges (already restricted to legal actions, in action order)
-// returns the edge position inside the node
+// returns the edge position inside the node.
+// VL (leaves_per_tree > 1, not the reference's algorithm): the simulations of this tree that are in flight below an edge count
+// as visits that lost - N + vl visits, value (N * Q - vl) / (N + vl) - and the node's visit count includes them, which
+// steers the next simulation of the same wave to another leaf.
 // ------------------------------------------------------------------------------------------
-template <class W>
+template <bool VL, class W>
 SPL_D int mcts_pick(const W& w, const MctsEdges& ed, const MctsEdgeV& first, int k, int Ns, float Qs, const MctsSearchParams& P, bool forced,
                     int n_iter) {   // `first` = edge [lane], fetched by the caller together with the node header
     const double fpu_init = P.fpu > 0.0 ? MC_DADD((double)Qs, -P.fpu) : P.fpu;   // :202
@@ -552,7 +566,14 @@ SPL_D int mcts_pick(const W& w, const MctsEdges& ed, const MctsEdgeV& first, int
     double best_u = 0.0;
     int best_i = -1, forced_i = 0x7fffffff;
     for (int i = w.lane; i < k; i += W::W) {
-        const MctsEdgeV e = i == w.lane ? first : ed.load(i);
+        MctsEdgeV e = i == w.lane ? first : ed.load(i);
+        if (VL) {
+            const int vl = (int)((uint32_t)e.N >> 24), n = e.N & MCTS_N_MASK;
+            if (vl) {
+                e.Q = MC_DDIV(MC_DADD(n ? MC_DMUL((double)n, e.Q) : 0.0, -(double)vl), (double)(n + vl));
+                e.N = n + vl;
+            } else e.N = n;
+        }
         if (forced && forced_i == 0x7fffffff) {   // :207-208 - the first legal action short of its forced visits wins outright
             const long long quota = (long long)MC_DSQRT(MC_DMUL(MC_DMUL(MCTS_KFORCED, (double)e.P), (double)n_iter));
             if ((long long)e.N < quota) forced_i = i;
@@ -584,9 +605,9 @@ SPL_D float mcts_vsel(const float* v, int i) {
     for (int j = 1; j < N; j++) r = i == j ? v[j] : r;
     return r;
 }
-template <int N, class W>
-SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const float* v) {
-    const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+template <int N, bool VL, class W>
+SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int s, int depth, const float* v) {
+    const uint32_t* path = mcts_path(A, t, s);
     for (int d = w.lane; d < depth; d += W::W) {
         const float v0 = mcts_vsel<N>(v, ((d - depth) % N + N) % N);
         const uint32_t rec = path[2 * d], pe = path[2 * d + 1];
@@ -594,10 +615,12 @@ SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const f
         const MctsEdges ed = mcts_edges(A, rec, (int)(pe >> 16));
         const int pos = (int)(pe & 0xFFFFu);
         const MctsPN pn = ed.pn[pos];
-        ed.Q[pos] = MC_DDIV(MC_DADD(MC_DMUL((double)pn.N, ed.Q[pos]), (double)v0), (double)(pn.N + 1));                      // :171
+        const int n = VL ? (pn.N & MCTS_N_MASK) : pn.N;
+        ed.Q[pos] = MC_DDIV(MC_DADD(MC_DMUL((double)n, ed.Q[pos]), (double)v0), (double)(n + 1));                            // :171
         nd->u.x.Qs = MC_FDIV(MC_FADD(MC_FMUL((float)(nd->u.x.Ns + 1), nd->u.x.Qs), v0), (float)(nd->u.x.Ns + 2));          // :172
-        ed.pn[pos].N = pn.N + 1;
+        ed.pn[pos].N = VL ? pn.N - MCTS_VL_ONE + 1 : pn.N + 1;      // (VL: the simulation is no longer in flight below this edge)
         nd->u.x.Ns += 1;
+        if (VL) nd->u.x.pad -= 1u;
     }
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
@@ -607,9 +630,27 @@ SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int depth, const f
     }
 }
 
+// VL: a simulation that cannot go on this wave (another simulation of the tree already waits at the same node or edge) is
+// given up: its virtual visits are taken back along the recorded path, nothing else was changed
+template <class W>
+SPL_D void mcts_abandon(const W& w, const MctsArena& A, int t, int s, int depth) {
+    const uint32_t* path = mcts_path(A, t, s);
+    for (int d = w.lane; d < depth; d += W::W) {
+        const uint32_t rec = path[2 * d], pe = path[2 * d + 1];
+        const MctsEdges ed = mcts_edges(A, rec, (int)(pe >> 16));
+        ed.pn[pe & 0xFFFFu].N -= MCTS_VL_ONE;
+        mcts_node(A, rec)->u.x.pad -= 1u;
+    }
+    if (w.lane == 0) {
+        MctsSlot* S = A.trees[t].slot + s;
+        S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->path_len = 0;
+    }
+    w.sync();
+}
+
 // hands a node that waits for the network to the leaf row of its tree (:136-138)
 template <int N, class W>
-SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
+SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int s, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
                           bool rows = true) {   // rows = false: the staging row of the rules kernel already holds this very state and mask
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
@@ -622,14 +663,18 @@ SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, uint32_t node, 
         const int k = (int)nd->n_edges;
         const MctsEdges ed = mcts_edges(A, node, k);
         for (int i = w.lane; i < k; i += W::W) leaf_valid[ed.ca[i].action] = 1;
-        if (w.lane == 0) A.leaf_src[t] = 0;
+        if (w.lane == 0) A.leaf_src[mcts_row(A, t, s)] = 0;
     }
-    if (w.lane == 0) { T->leaf = node; T->path_len = depth; T->sims_done = sims_done; T->cur = 0u; T->pend_edge = -1; }
+    if (w.lane == 0) {
+        MctsSlot* S = T->slot + s;
+        S->leaf = node; S->path_len = depth; S->cur = 0u; S->pend_edge = -1;
+        if (sims_done >= 0) T->sims_done = sims_done;
+    }
     w.sync();
 }
 
 // ------------------------------------------------------------------------------------------
-// descent (light: no rules code): runs simulations of tree t until one
+// descent (light: no rules code): runs simulations of tree t (in-flight slot s) until one
 //   * reaches a node that waits for the network  -> leaf row written, returns 1
 //   * reaches an edge that was never taken       -> records it as pending (the rules kernel computes the child state,
 //                                                    mcts_attach_tree links it), returns 2
@@ -637,23 +682,32 @@ SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, uint32_t node, 
 // Simulations that end in a terminal node are backed up on the spot, at most `max_terminal` of them per call (then 3 is
 // returned and the next call carries on): near the end of a game almost every simulation is such a one, and a single
 // tree working through its whole budget would hold up the wave. For the same reason a call walks at most `max_levels`
-// edges before it yields (3). Trees with a leaf or a pending edge are skipped.
+// edges before it yields (3). Slots with a leaf or a pending edge are skipped.
+// VL (leaves_per_tree > 1): the edges walked carry a virtual visit until the simulation is backed up; a simulation that runs
+// into a node or an edge another slot of the tree already waits at is given up for this wave (returns 0).
 // ------------------------------------------------------------------------------------------
-template <int N, class W>
-SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int max_terminal, int max_levels,
+template <int N, bool VL, class W>
+SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, int max_terminal, int max_levels,
                             int8_t* leaf_state, uint8_t* leaf_valid) {
     MctsTree* T = A.trees + t;
-    if (T->leaf != 0u) return 1;
-    if (T->pend_edge >= 0) return 2;
+    MctsSlot* S = T->slot + s;
+    if (S->leaf != 0u) return 1;
+    if (S->pend_edge >= 0) return 2;
     if (T->status != 0u) return 0;
     const uint32_t root = T->root;
     int sims_done = T->sims_done;
-    const int target = T->sims_target;
-    if (root == 0u || sims_done >= target) return 0;
-    uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+    int target = T->sims_target;
+    uint32_t cur = S->cur;
+    if (VL && cur == 0u) {   // a new simulation only if the budget is not already covered by the ones in flight
+        int in_flight = 0;
+        for (int j = 0; j < A.n_slots; j++)
+            in_flight += (j != s && (T->slot[j].leaf != 0u || T->slot[j].pend_edge >= 0 || T->slot[j].cur != 0u)) ? 1 : 0;
+        target -= in_flight;
+    }
+    if (root == 0u || (cur == 0u && sims_done >= target)) return 0;
+    uint32_t* path = mcts_path(A, t, s);
     const uint32_t flags = T->flags;
-    uint32_t cur = T->cur;
-    int depth = cur != 0u ? T->path_len : 0;
+    int depth = cur != 0u ? S->path_len : 0;
     if (cur == 0u) cur = root;
     // the edge count of `cur`: known from the parent's edge, or from the node header at the start of a walk
     int ne = mcts_node(A, cur)->kind == MCTS_NODE_TERMINAL ? 0 : (int)mcts_node(A, cur)->n_edges;
@@ -663,7 +717,7 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
     bool have_spec = false;
     MctsEdgeV spec_first = mcts_edge_none();
     MctsNode spec_nd;
-    while (sims_done < target) {
+    for (;;) {
         for (;;) {
             const MctsEdges ed = mcts_edges(A, cur, ne);
             MctsEdgeV first;                                  // header and first 32 edges: one round trip
@@ -678,14 +732,19 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             have_spec = false;
             const int kind = nd.kind;
             if (kind == MCTS_NODE_NEEDS_NN) {
-                mcts_emit_leaf<N>(w, A, t, cur, depth, sims_done, leaf_state, leaf_valid);
+                if (VL) {
+                    bool taken = false;
+                    for (int j = 0; j < A.n_slots; j++) taken |= j != s && T->slot[j].leaf == cur;
+                    if (taken) { mcts_abandon(w, A, t, s, depth); return 0; }
+                }
+                mcts_emit_leaf<N>(w, A, t, s, cur, depth, VL ? -1 : sims_done, leaf_state, leaf_valid);
                 return 1;
             }
             if (kind == MCTS_NODE_TERMINAL) break;   // :130-132
             int hp = -1;
             const int hint = (int)nd.u.x.hint - 1;
 #ifdef __CUDACC__
-            if (hint >= 0 && hint < 32 && hint < (int)nd.n_edges) {
+            if (!VL && hint >= 0 && hint < 32 && hint < (int)nd.n_edges) {
                 const uint32_t hchild = __shfl_sync(0xffffffffu, first.child, hint);
                 const int hne = __shfl_sync(0xffffffffu, (int)first.child_ne, hint);
                 if (hchild != 0u) {
@@ -698,15 +757,11 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             long long prof_t0 = 0;
             if (A.prof) prof_t0 = clock64();
 #endif
-            const int ei = mcts_pick(w, ed, first, (int)nd.n_edges, nd.u.x.Ns, nd.u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
+            const int ns_eff = VL ? nd.u.x.Ns + (int)nd.u.x.pad : nd.u.x.Ns;
+            const int ei = mcts_pick<VL>(w, ed, first, (int)nd.n_edges, ns_eff, nd.u.x.Qs, P, depth == 0 && (flags & MCTS_F_FORCED), sims_done);
 #ifdef __CUDACC__
             if (A.prof && w.lane == 0) { A.prof[(size_t)t * 16 + 6] += clock64() - prof_t0; A.prof[(size_t)t * 16 + 7] += 1; }   // diagnostics: cycles inside the pick, levels
 #endif
-            if (w.lane == 0) {
-                path[2 * depth] = cur; path[2 * depth + 1] = (uint32_t)ei | ((uint32_t)nd.n_edges << 16);
-                if (ei != hint) mcts_node(A, cur)->u.x.hint = (uint32_t)ei + 1u;
-            }
-            depth++;
             uint32_t child;
             int child_ne;
 #ifdef __CUDACC__
@@ -719,15 +774,28 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
                 const MctsCA sel = ed.ca[ei];
                 child = sel.child; child_ne = (int)sel.child_ne;
             }
+            if (VL && child == 0u) {   // an edge another simulation of this wave is already opening
+                bool taken = false;
+                for (int j = 0; j < A.n_slots; j++)
+                    taken |= j != s && T->slot[j].pend_edge >= 0 && T->slot[j].pend_parent == cur && (T->slot[j].pend_edge & 0xFFFF) == ei;
+                if (taken) { mcts_abandon(w, A, t, s, depth); return 0; }
+            }
+            if (w.lane == 0) {
+                path[2 * depth] = cur; path[2 * depth + 1] = (uint32_t)ei | ((uint32_t)nd.n_edges << 16);
+                if (ei != hint) mcts_node(A, cur)->u.x.hint = (uint32_t)ei + 1u;
+                if (VL) { ed.pn[ei].N += MCTS_VL_ONE; mcts_node(A, cur)->u.x.pad += 1u; }
+            }
+            depth++;
             if (child != 0u && --max_levels <= 0) {   // yield: a very deep path finishes in the next call instead of holding up the wave
-                if (w.lane == 0) { T->cur = child; T->path_len = depth; T->sims_done = sims_done; }
+                if (w.lane == 0) { S->cur = child; S->path_len = depth; if (!VL) T->sims_done = sims_done; }
                 w.sync();
                 return 3;
             }
             if (child == 0u) {   // first traversal of this edge
                 if (w.lane == 0) {
-                    T->pend_edge = (int32_t)((uint32_t)ei | ((uint32_t)nd.n_edges << 16)); T->pend_parent = cur;
-                    T->path_len = depth; T->sims_done = sims_done; T->cur = 0u;
+                    S->pend_edge = (int32_t)((uint32_t)ei | ((uint32_t)nd.n_edges << 16)); S->pend_parent = cur;
+                    S->path_len = depth; S->cur = 0u;
+                    if (!VL) T->sims_done = sims_done;
                 }
                 w.sync();
                 return 2;
@@ -743,19 +811,26 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
             float v[N];
 #pragma unroll
             for (int i = 0; i < N; i++) v[i] = mcts_node(A, cur)->u.es[i];
-            mcts_backup<N>(w, A, t, depth, v);
+            w.sync();
+            mcts_backup<N, VL>(w, A, t, s, depth, v);
         }
         w.sync();
-        sims_done++;
+        sims_done = VL ? T->sims_done + 1 : sims_done + 1;
+        if (VL) {
+            if (w.lane == 0) { T->sims_done = sims_done; S->cur = 0u; S->path_len = 0; }
+            w.sync();
+            return 3;   // one simulation per slot and call
+        }
         cur = root; depth = 0;
         ne = mcts_node(A, root)->kind == MCTS_NODE_TERMINAL ? 0 : (int)mcts_node(A, root)->n_edges;
-        if (--max_terminal <= 0 && sims_done < target) {
-            if (w.lane == 0) { T->sims_done = sims_done; T->cur = 0u; T->path_len = 0; }
+        if (sims_done >= target) break;
+        if (--max_terminal <= 0) {
+            if (w.lane == 0) { T->sims_done = sims_done; S->cur = 0u; S->path_len = 0; }
             w.sync();
             return 3;
         }
     }
-    if (w.lane == 0) { T->sims_done = sims_done; T->cur = 0u; T->path_len = 0; }
+    if (w.lane == 0) { T->sims_done = sims_done; S->cur = 0u; S->path_len = 0; }
     w.sync();
     return 0;
 }
@@ -763,66 +838,74 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, const MctsSea
 // attaches the child state computed for the pending edge: st = its bytes (sp, zero padded, 16-aligned), ended / es /
 // mask from mcts_rules_core. The dictionary may already hold the state (transposition, :120): then the descent goes on
 // from that node in the next mcts_descend_tree call. Returns 1 if a leaf row was written, 0 otherwise.
-template <int N, class W>
-SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* st, bool ended, const float* es,
+template <int N, bool VL, class W>
+SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, const int8_t* st, bool ended, const float* es,
                            const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid, bool emit_rows = true) {
     MctsTree* T = A.trees + t;
-    const int pe = T->pend_edge;
-    if (pe < 0) return T->leaf != 0u ? 1 : 0;
+    MctsSlot* S = T->slot + s;
+    const int pe = S->pend_edge;
+    if (pe < 0) return S->leaf != 0u ? 1 : 0;
     const uint64_t h = mcts_hash(w, st, A.sp);
     uint32_t rec = mcts_lookup(w, A, t, st, h);
     if (rec == 0u) rec = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
     if (rec == 0u) {   // no room: the search of this tree stops here (status bit set)
-        if (w.lane == 0) { T->pend_edge = -1; T->cur = 0u; T->path_len = 0; }
+        if (VL) mcts_abandon(w, A, t, s, S->path_len);
+        if (w.lane == 0) { S->pend_edge = -1; S->cur = 0u; S->path_len = 0; }
         w.sync();
         return 0;
     }
     const MctsNode* cn = mcts_node(A, rec);
     const int kind = cn->kind;
     if (w.lane == 0) {
-        MctsCA* e = mcts_edges(A, T->pend_parent, pe >> 16).ca + (pe & 0xFFFF);
+        MctsCA* e = mcts_edges(A, S->pend_parent, pe >> 16).ca + (pe & 0xFFFF);
         e->child = rec;
         e->child_ne = kind == MCTS_NODE_TERMINAL ? (uint16_t)0 : cn->n_edges;
     }
     w.sync();
-    const int depth = T->path_len, sims_done = T->sims_done;
+    const int depth = S->path_len, sims_done = T->sims_done;
     if (kind == MCTS_NODE_NEEDS_NN) {
-        mcts_emit_leaf<N>(w, A, t, rec, depth, sims_done, leaf_state, leaf_valid, emit_rows);
+        if (VL) {   // a transposition into a node another simulation of this wave already waits at
+            bool taken = false;
+            for (int j = 0; j < A.n_slots; j++) taken |= j != s && T->slot[j].leaf == rec;
+            if (taken) { mcts_abandon(w, A, t, s, depth); return 0; }
+        }
+        mcts_emit_leaf<N>(w, A, t, s, rec, depth, VL ? -1 : sims_done, leaf_state, leaf_valid, emit_rows);
         return 1;
     }
     if (kind == MCTS_NODE_TERMINAL) {
         float v[N];
 #pragma unroll
         for (int i = 0; i < N; i++) v[i] = cn->u.es[i];
-        mcts_backup<N>(w, A, t, depth, v);
-        if (w.lane == 0) { T->sims_done = sims_done + 1; T->pend_edge = -1; T->cur = 0u; T->path_len = 0; }
+        mcts_backup<N, VL>(w, A, t, s, depth, v);
+        if (w.lane == 0) { T->sims_done = sims_done + 1; S->pend_edge = -1; S->cur = 0u; S->path_len = 0; }
     } else {   // an expanded node reached through a new edge: keep descending from it
-        if (w.lane == 0) { T->pend_edge = -1; T->cur = rec; }
+        if (w.lane == 0) { S->pend_edge = -1; S->cur = rec; }
     }
     w.sync();
     return 0;
 }
 
 // expansion + backup: pi = the network's probability row for the leaf (float32[406], masked softmax), v = float32[N]
-template <int N, class W>
-SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const float* pi, const float* vin,
+template <int N, bool VL, class W>
+SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, const float* pi, const float* vin,
                             const double* dir, double* dscratch) {
     MctsTree* T = A.trees + t;
-    const uint32_t leaf = T->leaf;
+    MctsSlot* S = T->slot + s;
+    const uint32_t leaf = S->leaf;
     if (leaf == 0u) return;
     MctsNode* nd = mcts_node(A, leaf);
 #ifdef __CUDACC__
-    {
+    if (!VL) {
         // The common case in three rounds of loads instead of seven dependent ones: (1) the leaf's header, the value vector and
         // the recorded path, (2) the leaf's edge actions and the statistics of the path's nodes and edges, (3) the network's
         // probabilities; the float32 normalisation sums in action order through shuffles (same additions as `normalise :239`),
         // the backup (:168-177) uses the statistics fetched in round 2. Same arithmetic as the general path below.
-        const int depth = T->path_len;
+        const int depth = S->path_len;
         const bool noise = leaf == T->root && T->sims_done == 0 && (T->flags & MCTS_F_NOISE);
         const MctsNode hdr = *nd;
         const int k = hdr.n_edges;
         if (!noise && k <= 32 && depth <= 32) {
-            const uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
+            const uint32_t* path = mcts_path(A, t, s);
             float v[N];
 #pragma unroll
             for (int i = 0; i < N; i++) v[i] = vin[i];
@@ -839,9 +922,9 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
             const int ppos = (int)(pe & 0xFFFFu);
             if (w.lane < depth) { eN = ped.pn[ppos].N; eQ = ped.Q[ppos]; nNs = pnode->u.x.Ns; nQs = pnode->u.x.Qs; }
             float p = w.lane < k ? pi[act] : 0.f;
-            float s = 0.f;
-            for (int i = 0; i < k; i++) s = MC_FADD(s, __shfl_sync(0xffffffffu, p, i));
-            if (w.lane < k) ed.pn[w.lane].P = MC_FDIV(p, s);
+            float sm = 0.f;
+            for (int i = 0; i < k; i++) sm = MC_FADD(sm, __shfl_sync(0xffffffffu, p, i));
+            if (w.lane < k) ed.pn[w.lane].P = MC_FDIV(p, sm);
             if (w.lane == 0) {
                 nd->u.x.Ns = 0;
                 nd->u.x.Qs = v[0];   // :147
@@ -859,7 +942,7 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
                 for (int i = 0; i < 4; i++) T->last_v[i] = i < N ? mcts_vsel<N>(v, ((i - depth) % N + N) % N) : 0.f;
                 T->depth_sum += depth;
                 T->sims_done += 1;
-                T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->path_len = 0;
+                S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->path_len = 0;
                 T->nn_calls += 1;
             }
             w.sync();
@@ -875,13 +958,13 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
         mcts_root_noise(w, ed.pn, k, P, dir, P.game_base + (uint32_t)t, T->episode, (uint32_t)nd->ply, dscratch);
     } else {                                                                      // normalise :144
         if (w.lane == 0) {
-            float s = 0.f;
-            for (int i = 0; i < k; i++) s = MC_FADD(s, ed.pn[i].P);
-            reinterpret_cast<float*>(dscratch)[0] = s;
+            float sm = 0.f;
+            for (int i = 0; i < k; i++) sm = MC_FADD(sm, ed.pn[i].P);
+            reinterpret_cast<float*>(dscratch)[0] = sm;
         }
         w.sync();
-        const float s = reinterpret_cast<float*>(dscratch)[0];
-        for (int i = w.lane; i < k; i += W::W) ed.pn[i].P = MC_FDIV(ed.pn[i].P, s);
+        const float sm = reinterpret_cast<float*>(dscratch)[0];
+        for (int i = w.lane; i < k; i += W::W) ed.pn[i].P = MC_FDIV(ed.pn[i].P, sm);
         w.sync();
     }
     float v[N];
@@ -893,11 +976,11 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, const MctsSea
         nd->kind = MCTS_NODE_EXPANDED;
     }
     w.sync();
-    mcts_backup<N>(w, A, t, T->path_len, v);
+    mcts_backup<N, VL>(w, A, t, s, S->path_len, v);
     w.sync();
     if (w.lane == 0) {
         T->sims_done += 1;
-        T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->path_len = 0;
+        S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->path_len = 0;
         T->nn_calls += 1;
     }
     w.sync();
@@ -945,8 +1028,9 @@ SPL_D void mcts_clear_tree(const W& w, const MctsArena& A, int t) {   // reset_a
     mcts_release_storage(w, A, t);
     if (w.lane == 0) {
         MctsTree* T = A.trees + t;
-        T->root = 0u; T->leaf = 0u; T->sims_done = 0; T->sims_target = 0; T->path_len = 0;
-        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->spec_hits = 0; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u;
+        T->root = 0u; T->sims_done = 0; T->sims_target = 0;
+        T->flags = 0u; T->status = 0u; T->depth_sum = 0; T->spec_hits = 0;
+        for (int j = 0; j < MCTS_KMAX; j++) { MctsSlot* S = T->slot + j; S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->pend_parent = 0u; S->path_len = 0; }
         T->n_dropped = 0; T->hetero = 0;
     }
     w.sync();
@@ -960,7 +1044,8 @@ SPL_D void mcts_retire_all(const W& w, const MctsArena& A, int t) {
     mcts_release_storage(w, A, t);
     if (w.lane == 0) {
         T->n_dropped += n; T->compactions += 1;
-        T->root = 0u; T->leaf = 0u; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u; T->path_len = 0; T->hetero = 0;
+        T->root = 0u; T->hetero = 0;
+        for (int j = 0; j < MCTS_KMAX; j++) { MctsSlot* S = T->slot + j; S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->pend_parent = 0u; S->path_len = 0; }
     }
     w.sync();
 }
@@ -1088,20 +1173,23 @@ SPL_D bool mcts_compact(const W& w, const MctsArena& A, int t, bool use_marks, i
         return false;
     }
     w.sync();
-    // the simulation in flight follows its nodes (a dropped node has fwd == 0)
-    {
-        uint32_t* path = A.path + (size_t)t * A.max_depth * 2;
-        const bool in_flight = T->leaf != 0u || T->cur != 0u || T->pend_edge >= 0;
-        const int plen = in_flight ? T->path_len : 0;
+    // the simulations in flight follow their nodes (a dropped node has fwd == 0)
+    for (int j = 0; j < A.n_slots; j++) {
+        MctsSlot* S = T->slot + j;
+        uint32_t* path = mcts_path(A, t, j);
+        const bool in_flight = S->leaf != 0u || S->cur != 0u || S->pend_edge >= 0;
+        const int plen = in_flight ? S->path_len : 0;
         for (int d = w.lane; d < plen; d += W::W) path[2 * d] = mcts_node(A, path[2 * d])->fwd;
+        w.sync();
         if (w.lane == 0) {
-            if (T->root) T->root = mcts_node(A, T->root)->fwd;     // (0 if the root itself was dropped: begin re-creates it)
-            if (T->leaf) T->leaf = mcts_node(A, T->leaf)->fwd;
-            if (T->cur) T->cur = mcts_node(A, T->cur)->fwd;
-            if (T->pend_edge >= 0) T->pend_parent = mcts_node(A, T->pend_parent)->fwd;
+            if (S->leaf) S->leaf = mcts_node(A, S->leaf)->fwd;
+            if (S->cur) S->cur = mcts_node(A, S->cur)->fwd;
+            if (S->pend_edge >= 0) S->pend_parent = mcts_node(A, S->pend_parent)->fwd;
         }
         w.sync();
     }
+    if (w.lane == 0 && T->root) T->root = mcts_node(A, T->root)->fwd;     // (0 if the root itself was dropped: begin re-creates it)
+    w.sync();
     // new table; every lane walks the records it copied: children follow the forwarding pointers of the old copies
     {
         uint4* t4 = reinterpret_cast<uint4*>(tab);
@@ -1180,6 +1268,11 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     MctsTree* T = A.trees + t;
     for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
     w.sync();
+    if (A.n_slots > 1)      // simulations a truncated search left in flight give their virtual visits back
+        for (int j = 0; j < A.n_slots; j++) {
+            const MctsSlot* S = T->slot + j;
+            if (S->leaf != 0u || S->cur != 0u || S->pend_edge >= 0) mcts_abandon(w, A, t, j, S->path_len);
+        }
     const int root_ply = (int)(uint8_t)st[6];
     const uint64_t h = mcts_hash(w, st, A.sp);
     uint8_t deck[15];
@@ -1239,8 +1332,9 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     uint32_t rec = mcts_lookup(w, A, t, st, h);
     if (rec == 0u) rec = mcts_create_node<N>(w, A, t, P, st, h, scratch);
     if (w.lane == 0) {
-        T->root = rec; T->leaf = 0u; T->sims_done = 0; T->sims_target = rec == 0u ? 0 : sims_target; T->path_len = 0;
-        T->flags = flags; T->cur = 0u; T->pend_edge = -1; T->pend_parent = 0u; T->episode = episode;
+        T->root = rec; T->sims_done = 0; T->sims_target = rec == 0u ? 0 : sims_target;
+        T->flags = flags; T->episode = episode;
+        for (int j = 0; j < MCTS_KMAX; j++) { MctsSlot* S = T->slot + j; S->leaf = 0u; S->cur = 0u; S->pend_edge = -1; S->pend_parent = 0u; S->path_len = 0; }
     }
     w.sync();
     // a root the tree already expanded gets the noise on its stored Ps before the first simulation picks (:150-154);

@@ -30,14 +30,20 @@ def _ptr(t):
 class MCTSArena:
     def __init__(self, n_players, n_trees, node_cap, edge_cap=None, device=0, cpuct=1.0, fpu=0.0, temperature0=1.0,
                  dirichlet_alpha=0.3, seed=0, game_base=0, edge_reserve=32, gc_reachable=False, rounds=1, max_levels=0, token_limit=10,
-                 rule_flags=nat.RULES_DEFAULT, pool_nodes=None, pool_bytes=None):
+                 rule_flags=nat.RULES_DEFAULT, pool_nodes=None, pool_bytes=None, leaves_per_tree=1):
         """node_cap: the most nodes ONE tree may hold (its hash table is sized for it). The node records themselves come from a
         page pool all trees share: `pool_nodes` records per tree on average (default node_cap, i.e. every tree can reach its
         limit at once; production sizes it for the average tree - a tree is retired whenever a real move reveals a card) with
-        `edge_cap` edges per tree on average (default 24 per pooled node); or give `pool_bytes` directly."""
+        `edge_cap` edges per tree on average (default 24 per pooled node); or give `pool_bytes` directly.
+        leaves_per_tree (1..4): simulations one tree may have in flight per wave. 1 = the reference's sequential search (the parity
+        mode). More = virtual-loss leaf batching - NOT the reference's algorithm: a simulation in flight counts as a lost visit on
+        the edges it walked, so one wave evaluates several different leaves of a tree; the leaf buffers then hold
+        n_trees * leaves_per_tree rows (row = tree * leaves_per_tree + slot)."""
         if not torch.cuda.is_available():
             raise RuntimeError("MCTSArena needs a CUDA device (sm_100a); there is no CPU fallback")
         self.n, self.T = int(n_players), int(n_trees)
+        self.K = int(leaves_per_tree)
+        self.rows = self.T * self.K
         self.R, self.S = rows(self.n), 7 * rows(self.n)
         self.device = torch.device("cuda", device)
         self.node_cap = int(node_cap)
@@ -50,24 +56,26 @@ class MCTSArena:
         if pool_bytes is None:
             pool_bytes = self.T * (self.pool_nodes * self._lib.spl_mcts_record_bytes(self.n, 0) + self.edge_cap * 24) + (2 * self.T + 64) * 32768
         self.pool_bytes = int(pool_bytes)
-        nbytes = self._lib.spl_mcts_arena_bytes(self.n, self.T, self.node_cap, self.pool_bytes)
+        nbytes = self._lib.spl_mcts_arena_bytes(self.n, self.T, self.node_cap, self.pool_bytes, self.K)
+        if nbytes == 0:
+            raise ValueError("MCTSArena: bad sizes (leaves_per_tree must be 1..4)")
         with torch.cuda.device(self.device):
             self.arena = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)      # spl_mcts_reset initialises what needs it
             off = (-self.arena.data_ptr()) % 256
             self._arena_ptr = self.arena.data_ptr() + off
-            self.leaf_states = torch.zeros((self.T, self.R, 7), dtype=torch.int8, device=self.device)
-            self.leaf_valids = torch.zeros((self.T, nat.NUM_ACTIONS), dtype=torch.uint8, device=self.device)
-            self.leaf_flags = torch.zeros(self.T, dtype=torch.uint8, device=self.device)
+            self.leaf_states = torch.zeros((self.rows, self.R, 7), dtype=torch.int8, device=self.device)
+            self.leaf_valids = torch.zeros((self.rows, nat.NUM_ACTIONS), dtype=torch.uint8, device=self.device)
+            self.leaf_flags = torch.zeros(self.rows, dtype=torch.uint8, device=self.device)
             self.counters = torch.zeros(2, dtype=torch.int32, device=self.device)
         m = C.c_void_p()
-        nat.check(self._lib.spl_mcts_create(self._ctx, self.T, self.node_cap, self.pool_bytes, C.c_void_p(self._arena_ptr), nbytes, C.byref(m)))
+        nat.check(self._lib.spl_mcts_create(self._ctx, self.T, self.node_cap, self.pool_bytes, self.K, C.c_void_p(self._arena_ptr), nbytes, C.byref(m)))
         self._m = m
         self.arena_bytes = nbytes
         self.params = dict(cpuct=cpuct, fpu=fpu, temperature0=temperature0, dirichlet_alpha=dirichlet_alpha, seed=seed,
                            game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds), max_levels=int(max_levels))
         self.set_params()
         self.launches = 0
-        self.wave_nnet_launches = 3 if self.T <= 6144 else 4      # descent (+ rules step inside it up to 6144 trees), attach, network
+        self.wave_nnet_launches = 3 if (self.T <= 6144 and self.K == 1) else 4      # descent (+ rules step inside it up to 6144 trees), attach, network
         self._nn_pending, self._nn_dir = None, None
         self.reset()
 
@@ -133,8 +141,8 @@ class MCTSArena:
         self.launches += 3 * self.params["rounds"]
 
     def expand(self, pi, v, dir_values=None):
-        assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.numel() == self.T * nat.NUM_ACTIONS
-        assert v.dtype == torch.float32 and v.is_contiguous() and v.numel() == self.T * self.n
+        assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.numel() == self.rows * nat.NUM_ACTIONS
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.numel() == self.rows * self.n
         nat.check(self._lib.spl_mcts_expand(self._m, _ptr(pi), _ptr(v), _ptr(dir_values), self._stream()))
         self.launches += 1
 
@@ -153,7 +161,7 @@ class MCTSArena:
         """steady-state wave with the fused evaluator inside (spl_mcts_wave_nnet): expansion of the previous leaves + next
         descent -> rules -> {attach || network}. `net` = FusedSplendorNNet; its static output rows carry the network results
         from one wave to the next. Same results as `wave_steady`."""
-        pi, v = net.out_buffers(self.T)
+        pi, v = net.out_buffers(self.rows)
         if self._nn_pending is not net:      # leaves were selected the classic way: their rows need the network first
             net(self.leaf_states, self.leaf_valids)
             self._nn_pending = net
@@ -165,7 +173,7 @@ class MCTSArena:
     def drain_nnet(self, dir_values=None):
         """after `wave_nnet`: back the pending network results up, so that the classic calls (select / expand / finish) can follow"""
         if self._nn_pending is not None:
-            pi, v = self._nn_pending.out_buffers(self.T)
+            pi, v = self._nn_pending.out_buffers(self.rows)
             self._nn_pending = None
             self.expand(pi, v, dir_values if dir_values is not None else self._nn_dir)
 
@@ -196,6 +204,7 @@ class MCTSArena:
         self.begin(roots, sims, move_flags, tree_select, dir_values)
         if waves is None:
             waves = int(sims.max().item())
+        waves = -(-waves // self.K)        # a wave finishes up to leaves_per_tree simulations of a tree
         if self._is_fused(evaluator):      # network inside the wave, next to the attach kernel (same results)
             self.select()
             for _ in range(waves):

@@ -25,7 +25,7 @@ class SelfPlayEngine:
                  prob_full=1.0, ratio_full=5, forced_playouts=False, dirichlet_noise=False, dirichlet_alpha=0.3,
                  temperature0=1.0, node_cap=None, edge_cap=None, gc_reachable=False, edge_reserve=24, graph_waves=0, rounds=1,
                  max_levels=0, record_examples=False, clean_every=0, clean_percent=50, overlap_nnet=None, tick_graph=None, pool_nodes=None,
-                 absolute=None):
+                 absolute=None, leaves_per_tree=1):
         self.n, self.T, self.num_sims = n_players, n_games, int(num_sims)
         self.prob_full, self.ratio_full = float(prob_full), int(ratio_full)
         self.forced, self.noise = bool(forced_playouts), bool(dirichlet_noise)
@@ -44,7 +44,7 @@ class SelfPlayEngine:
         node_cap = node_cap or (3 if gc_reachable else 8) * self.num_sims
         self.arena = MCTSArena(n_players, n_games, node_cap, edge_cap, device=device, cpuct=cpuct, fpu=fpu, temperature0=temperature0,
                                dirichlet_alpha=dirichlet_alpha, seed=seed, game_base=game_base, edge_reserve=edge_reserve,
-                               gc_reachable=gc_reachable, rounds=rounds, max_levels=max_levels, pool_nodes=pool_nodes)
+                               gc_reachable=gc_reachable, rounds=rounds, max_levels=max_levels, pool_nodes=pool_nodes, leaves_per_tree=leaves_per_tree)
         self.arena.set_episodes(self.env.episodes)      # the on-device Dirichlet sampler is keyed (seed, game, episode, ply)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed) * 1000003 + int(game_base))
@@ -182,7 +182,7 @@ class SelfPlayEngine:
             self._run_waves(0)
             self.arena.reset()
         self.arena.begin(self.roots, self.sims, self.flags, None, dir_values)
-        self._run_waves(max_sims)
+        self._run_waves(-(-max_sims // self.arena.K))
         chunk = None
         if self.graph_waves > 0:
             def chunk():

@@ -616,6 +616,24 @@ def bench_config2_genbu(args, torch, dist, azg, world, rank, local, dev, barrier
             "truncated_searches": int(st["truncated"].sum()), "lossy_resets": int(st["resets"].sum())}
 
 
+def bench_virtual_loss(args, torch, dist, azg, world, rank, local, dev, barrier):
+    """north star (3), an explicit NON-parity option: leaves_per_tree = 4 simulations of a tree in flight per wave (virtual-loss
+    leaf batching) - the batch of the evaluator comes from 4096 trees x 4 leaves instead of 16,384 trees, at a quarter of the memory"""
+    n, T, sims, K = args.players, 4096, args.sims, 4
+    G = args.graph_waves or 16
+    net = azg.FusedSplendorNNet(n, seed=args.seed, device=local)
+    eng = azg.SelfPlayEngine(n, T, net, sims, device=local, seed=args.seed, game_base=rank * T, node_cap=20 * sims, pool_nodes=int(5.5 * sims),
+                             graph_waves=args.graph_waves, max_levels=args.max_levels, tick_graph=True, leaves_per_tree=K)
+    eng.env.rollout(args.opening_plies, rotate=True)
+    eng.start_async()
+    done, ms = _timed_async(eng, torch, dist, world, dev, barrier, G, max(1, sims // (2 * G)), steps=4)
+    st = eng.arena.root_stats(want_arrays=False)
+    return {"value": done / (ms * 1e-3), "unit": UNIT_MCTS, "trees_per_gpu": T, "leaves_per_tree": K, "sims_per_move": sims, "ms": ms,
+            "arena_gb_per_gpu": eng.arena.arena_bytes / 1e9, "truncated_searches": int(st["truncated"].sum()), "lossy_resets": int(st["resets"].sum()),
+            "note": "not the reference's sequential search: visit counts differ from MCTS.py (tests/test_gpu_mcts.py::test_virtual_loss_leaf_batching "
+                    "measures how far); the headline value is the parity mode, one leaf per tree"}
+
+
 def bench_fp32_network(args, torch, dist, azg, world, rank, local, dev, barrier):
     """the same search with the float32 evaluator (torch kernels, tf32 off): what the bf16 tensor-core kernel buys"""
     n, T, sims, G = args.players, 4096, args.sims, 16
@@ -880,7 +898,8 @@ def main():
             line["mcts_wide"] = bench_mcts_wide(args, torch, dist, azg, world, rank, local, dev, barrier)
             torch.cuda.empty_cache()
         if not args.no_extra:
-            for key, fn in (("config2_genbu", bench_config2_genbu), ("fp32_network", bench_fp32_network), ("config3_arena_3p", bench_config3_arena)):
+            for key, fn in (("config2_genbu", bench_config2_genbu), ("virtual_loss_4_leaves", bench_virtual_loss), ("fp32_network", bench_fp32_network),
+                            ("config3_arena_3p", bench_config3_arena)):
                 line[key] = fn(args, torch, dist, azg, world, rank, local, dev, barrier)
                 torch.cuda.empty_cache()
     if args.workload in ("both", "env"):

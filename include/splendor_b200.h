@@ -196,10 +196,15 @@ typedef struct {
 size_t spl_mcts_record_bytes(int n_players, int n_edges);
 /* bytes of device memory an arena needs. node_limit: most nodes ONE tree may hold (sizes its hash table); pool_bytes: the page
  * pool all trees share - size it for the AVERAGE tree (a tree is retired whenever a real move reveals a card) */
-size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes);
+size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes, int leaves_per_tree);
 /* MCTS.__init__ (:21-43): `arena` is caller-owned device memory of at least spl_mcts_arena_bytes, 256-byte aligned.
  * Call spl_mcts_reset(m, NULL, stream) once before the first spl_mcts_begin (it fills the ring of free pages). */
-int  spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, void* arena, size_t arena_bytes, spl_mcts** out);
+int  spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes, int leaves_per_tree, void* arena, size_t arena_bytes, spl_mcts** out);
+/* leaves_per_tree (1..4): simulations one tree may have in flight per wave. 1 = the reference's sequential search (parity mode: visit
+ * counts identical to MCTS.py). > 1 = virtual-loss leaf batching, NOT the reference's algorithm: every simulation in flight counts as
+ * a lost visit (value -1) on the edges it walked until its value is backed up, so the simulations of one wave spread over different
+ * leaves; the per-tree row buffers (leaf_states, leaf_valids, leaf_flags, pi, v) then hold n_trees * leaves_per_tree rows, row =
+ * tree * leaves_per_tree + slot. One warp owns a tree, so the updates of Ns / Nsa / Qsa need no atomics. */
 /* the lanes' episode counters (device uint32[T], read by spl_mcts_begin; may be NULL = 0): part of the key of the on-device
  * Dirichlet sampler, so that every episode of a lane draws its own root noise */
 int  spl_mcts_set_episodes(spl_mcts* m, const uint32_t* episodes);

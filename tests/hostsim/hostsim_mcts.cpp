@@ -22,7 +22,7 @@ struct HsMcts {
 
 template <int N>
 static void hm_step_rules(HsMcts* m, int8_t* st, bool* ended, float* es, uint32_t* mask) {
-    const MctsTree& T = m->A.trees[0];
+    const MctsSlot& T = m->A.trees[0].slot[0];
     memcpy(st, mcts_state(m->A, T.pend_parent), m->A.sp);
     AosAcc s{st};
     const int action = (int)mcts_edges(m->A, T.pend_parent, T.pend_edge >> 16).ca[T.pend_edge & 0xFFFF].action;
@@ -35,7 +35,7 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     HsMcts* m = (HsMcts*)calloc(1, sizeof *m);
     m->n = n;
     MctsArena& A = m->A;
-    A.n_trees = 1; A.node_limit = cap;
+    A.n_trees = 1; A.node_limit = cap; A.n_slots = 1;
     A.hcap = 64; while (A.hcap < 2 * cap) A.hcap *= 2;
     A.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
     A.max_depth = 62 * n + 8;
@@ -53,7 +53,7 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     A.trees = (MctsTree*)calloc(1, sizeof(MctsTree));
     A.path = (uint32_t*)calloc((size_t)A.max_depth * 2, 4);
     A.leaf_src = (uint8_t*)calloc(1, 1);
-    A.trees[0].pend_edge = -1;
+    for (int j = 0; j < MCTS_KMAX; j++) A.trees[0].slot[j].pend_edge = -1;
     m->P.cpuct = cpuct; m->P.fpu = fpu; m->P.temperature0 = temperature0; m->P.dirichlet_alpha = 0.3; m->P.seed = 0; m->P.game_base = 0;
     m->P.rules.limit = limit; m->P.rules.flags = rule_flags;
     m->edge_reserve = edge_reserve; m->gc_reachable = gc_reachable;
@@ -92,7 +92,7 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
     DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->gc_reachable, dir, m->episode, st, scratch, dscratch));
     for (;;) {
         int r = 0;
-        DISPATCH(m->n, r = mcts_descend_tree<N>(w, m->A, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid));
+        DISPATCH(m->n, (r = mcts_descend_tree<N, false>(w, m->A, 0, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid)));
         hm_maybe_clean(m);
         if (r == 0) break;
         if (r == 3) continue;
@@ -100,12 +100,12 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
             bool ended = false; float es[4] = {0, 0, 0, 0}; uint32_t mask[13];
             memset(st, 0, sizeof st);
             DISPATCH(m->n, hm_step_rules<N>(m, st, &ended, es, mask));
-            DISPATCH(m->n, r = mcts_attach_tree<N>(w, m->A, 0, m->P, st, ended, es, mask, 1, m->leaf_state, m->leaf_valid));
+            DISPATCH(m->n, (r = mcts_attach_tree<N, false>(w, m->A, 0, 0, m->P, st, ended, es, mask, 1, m->leaf_state, m->leaf_valid)));
             hm_maybe_clean(m);
             if (r == 0) continue;
         }
         DISPATCH(m->n, mcts_fixed_net_row<N>(w, m->leaf_state, m->leaf_valid, m->pi, m->v, scratch));
-        DISPATCH(m->n, mcts_expand_tree<N>(w, m->A, 0, m->P, m->pi, m->v, dir, dscratch));
+        DISPATCH(m->n, (mcts_expand_tree<N, false>(w, m->A, 0, 0, m->P, m->pi, m->v, dir, dscratch)));
     }
     return (int)m->A.trees[0].status;
 }

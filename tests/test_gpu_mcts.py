@@ -511,3 +511,77 @@ def test_sample_moves_follows_the_policy():
         nsa = _np(ar.root_stats()["nsa"][0])
         if not forced:
             assert (_np(a0).astype(np.int64)[: T // 2] == int(nsa.argmax())).all()
+
+
+@pytest.mark.parametrize("K", [2, 4])
+def test_virtual_loss_leaf_batching(K):
+    """leaves_per_tree > 1 (north star: virtual-loss leaf batching) - an explicit NON-parity option: several simulations of a tree
+    per wave, each in flight as a lost visit on the edges it walked. Checked here: every search spends exactly its budget, visit
+    counts add up, no virtual visit is left behind, a search needs about 1/K of the waves - and it still finds what the sequential
+    search finds (same most visited move in most trees, visit distributions close)."""
+    az = _azg()
+    n, T, sims = 2, 256, 200
+    env = az.SplendorEnv(n, T, seed=17)
+    env.reset(); env.rollout(24, rotate=True)
+    roots = env.states()
+    simt = torch.full((T,), sims, dtype=torch.int32, device=roots.device)
+    simt[::5] = 37                                                     # ragged budgets, not multiples of K
+    def run(ar):
+        ar.begin(roots, simt)
+        waves, early = 0, 0
+        while True:
+            ar.counters.zero_()
+            ar.select(count=True)
+            leaves, left = [int(x) for x in ar.counters.cpu()]
+            if left == 0:
+                return waves, early
+            if 4 <= waves < 30:
+                early += leaves                                        # rows handed to the network per wave while every tree is still searching
+            pi, v = ar.fixed_net()
+            ar.expand(pi, v)
+            waves += 1
+    ref = az.MCTSArena(n, T, node_cap=1024, cpuct=1.5, fpu=0.2)
+    waves1, early1 = run(ref)                                          # the sequential search, driven the same way
+    ar = az.MCTSArena(n, T, node_cap=1024, cpuct=1.5, fpu=0.2, leaves_per_tree=K)
+    assert ar.leaf_states.shape[0] == T * K
+    waves, early = run(ar)
+    ar.check_status()
+    a, b = ref.root_stats(), ar.root_stats()
+    assert torch.equal(b["sims_done"], simt)
+    nsa = b["nsa"]
+    assert int(nsa.max()) < (1 << 24) and torch.equal(nsa.sum(1), b["ns"])          # no virtual visit left in any counter
+    assert torch.equal(b["ns"], a["ns"])                                            # the same number of real visits as the sequential search
+    probs, _ = ar.policy(1.0)
+    assert np.allclose(_np(probs).sum(1), 1.0, atol=1e-9)
+    assert waves < waves1 and waves >= sims // K and early > (1.5 if K == 2 else 2.2) * early1, (waves, waves1, early, early1)
+    pa, pb = _np(a["nsa"]).astype(np.float64), _np(nsa).astype(np.float64)
+    pa, pb = pa / pa.sum(1, keepdims=True), pb / pb.sum(1, keepdims=True)
+    tv = 0.5 * np.abs(pa - pb).sum(1)
+    agree = (pa.argmax(1) == pb.argmax(1)).mean()
+    print(f"leaves_per_tree {K}: {waves} waves for {sims} simulations ({waves1} with one leaf per tree; network rows per wave x{early / early1:.2f}), top move agrees in {agree:.2%} of the trees, mean TV distance {tv.mean():.3f}")
+    assert agree > 0.6 and tv.mean() < 0.3
+    # a second move on the same trees (reuse), then the whole thing once more through the fused network and the one-call wave
+    env.step(probs.argmax(1).to(torch.int16), player=0, chance="philox", rotate=True)
+    ar.search(env.states(), simt, lambda s, v: ar.fixed_net(s, v))
+    ar.check_status()
+    assert torch.equal(ar.root_stats()["sims_done"], simt)
+    net = az.FusedSplendorNNet(n, seed=4)
+    ar.search(env.states(), simt, net)
+    ar.check_status()
+    st = ar.root_stats()
+    assert torch.equal(st["sims_done"], simt) and int(st["nsa"].max()) < (1 << 24)
+
+
+def test_selfplay_async_with_virtual_loss():
+    az = _azg()
+    n, T, sims = 2, 256, 64
+    net = az.FusedSplendorNNet(n, seed=2)
+    eng = az.SelfPlayEngine(n, T, net, sims, seed=13, node_cap=16 * sims, graph_waves=8, max_levels=16, tick_graph=True, leaves_per_tree=2)
+    eng.env.rollout(40, rotate=True)
+    eng.start_async()
+    for _ in range(60):
+        eng.tick(8)
+    moves, done_sims = int(eng.moves_completed.item()), int(eng.sims_completed.item())
+    assert moves > 6 * T and done_sims == moves * sims
+    st = eng.arena.root_stats(want_arrays=False)
+    assert int(st["status"].max()) == 0 and int(st["truncated"].sum()) == 0
