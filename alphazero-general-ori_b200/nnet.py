@@ -216,7 +216,7 @@ def load_checkpoint_file(path, allow_pickle=False):
 
 
 def state_dict_from_npz(path):
-    """the weights frozen by oracle/refgen/gen_genbu_golden.py (keys 'sd/<name>') -> dict of tensors"""
+    """weights stored as an .npz with keys 'sd/<name>' plus the list 'sd_keys' (how tests/golden keeps a checkpoint) -> dict of tensors"""
     z = np.load(path)
     return {str(k): torch.from_numpy(z["sd/" + str(k)]) for k in z["sd_keys"]}
 
