@@ -45,14 +45,16 @@ struct WarpScratch {
     int8_t* st;
     uint32_t* words;
     double* dwords;
+    uint8_t* cs;     // 128 bytes: a compact node state
 };
 
 __device__ __forceinline__ WarpScratch warp_scratch(int warp) {
     __shared__ __align__(16) int8_t s_state[MW][MSP];
     __shared__ uint32_t s_words[MW][24];
     __shared__ double s_dwords[MW][4];
+    __shared__ __align__(16) uint8_t s_cs[MW][128];
     WarpScratch s;
-    s.st = s_state[warp]; s.words = s_words[warp]; s.dwords = s_dwords[warp];
+    s.st = s_state[warp]; s.words = s_words[warp]; s.dwords = s_dwords[warp]; s.cs = s_cs[warp];
     return s;
 }
 
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSe
     if (tree_select && !tree_select[t]) return;
     MctsWarp w{(int)(threadIdx.x & 31)};
     mcts_begin_tree<N>(w, A, t, P, roots + (size_t)t * MctsLay<N>::S, sims[t], move_flags ? (uint32_t)move_flags[t] : 0u, gc_reachable,
-                       dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, episodes ? episodes[t] : 0u, sc.st, sc.words, sc.dwords);
+                       dir ? dir + (size_t)t * SPL_ACTIONS : nullptr, episodes ? episodes[t] : 0u, sc.st, sc.cs, sc.words, sc.dwords);
 }
 
 template <int N, bool VL>
@@ -119,19 +121,19 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     if (pmask == 0u) return;
     const bool prof_ok = A.n_slots == 1 && t0 < A.n_trees;
     if (prof_ok) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
+    {   // the parents' states: records hold the compact form, the rules code reads the reference's layout (the whole warp decodes each)
+        const MctsWarp w{lane};
 #pragma unroll
-    for (int j = 0; j < TPW; j++) {
-        const uint32_t par = __shfl_sync(0xffffffffu, parent, j);
-        if ((pmask >> j) & 1u) {
-            const int8_t* src = mcts_state(A, par);
-            for (int i = lane; i < CH; i += 32) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + j * STRIDE + 16 * i);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
+        for (int j = 0; j < TPW; j++) {
+            const uint32_t par = __shfl_sync(0xffffffffu, parent, j);
+            if ((pmask >> j) & 1u) {
+                int8_t* dst = wsm + j * STRIDE;
+                mcts_decode<N>(w, mcts_cstate(A, par), dst);
+                for (int i = ML::S + lane; i < ML::SP; i += 32) dst[i] = 0;
             }
         }
+        __syncwarp();
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
     if (prof_ok) PROF_STAMP(A, t0, 8, clock64());
     bool ended = false;
     float es[N];
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, Mc
                                                                  uint8_t* leaf_flags, int32_t* counters, bool emit_rows) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
+    __shared__ __align__(16) uint8_t s_cs[MW][128];
     MctsWarp w{(int)(threadIdx.x & 31)};
     PROF_STAMP(A, t, 12, prof_globaltimer()); PROF_STAMP(A, t, 13, clock64());
     const int n_rows = A.n_trees * A.n_slots;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, Mc
     bool waiting = false;
     for (int s = 0; s < (VL ? A.n_slots : 1); s++) {   // the slots of a tree one after the other: node creation stays deterministic
         const size_t r = (size_t)mcts_row(A, t, s);
-        const int leaf = mcts_attach_tree<N, VL>(w, A, t, s, P, A.stage_state + r * A.sp, A.stage_ended[r] != 0, A.stage_es + r * 4,
+        const int leaf = mcts_attach_tree<N, VL>(w, A, t, s, P, A.stage_state + r * A.sp, s_cs[warp], A.stage_ended[r] != 0, A.stage_es + r * 4,
                                                  A.stage_mask + r, n_rows, leaf_states + r * MctsLay<N>::S, leaf_valids + r * SPL_ACTIONS, emit_rows);
         __syncwarp();
         if (w.lane == 0) leaf_flags[r] = (uint8_t)leaf;
@@ -243,13 +246,12 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     const int pe = T->pend_edge;
     if (pe < 0 || T->leaf != 0u) return;
     const int action = (int)mcts_edges(A, T->pend_parent, pe >> 16).ca[pe & 0xFFFF].action;
-    const int8_t* src = mcts_state(A, T->pend_parent);
-    for (int i = lane; i < CH; i += 32) {
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm + 16 * i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * i) : "memory");
+    {
+        const MctsWarp w{lane};
+        mcts_decode<N>(w, mcts_cstate(A, T->pend_parent), wsm);
+        for (int i = MctsLay<N>::S + lane; i < MctsLay<N>::SP; i += 32) wsm[i] = 0;
+        __syncwarp();
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
     PROF_STAMP(A, t, 8, clock64());
     // make_move on lane 0; swap_players (a byte rotation of the four per-player blocks) and the 15 candidate cards of valid_moves
     // spread over the lanes; the rest of valid_moves and getGameEnded on lane 0 again - the same arithmetic as mcts_rules_core
@@ -421,13 +423,14 @@ __global__ void __launch_bounds__(MW * 32) mcts_fixed_net_kernel(const int8_t* s
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ArenaPlan {
-    int sp, hcap, max_depth, max_pages;
+    int sp, cp, hcap, max_depth, max_pages;
     uint32_t n_pool_pages;
     size_t off_pool, off_fq, off_ctl, off_tpages, off_htab, off_trees, off_path, off_sstate, off_smask, off_ses, off_sended, off_lsrc, total;
 };
 static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes, int K) {
     ArenaPlan p;
     p.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
+    p.cp = n == 2 ? MctsCLay<2>::CP : n == 3 ? MctsCLay<3>::CP : MctsCLay<4>::CP;
     p.hcap = 64;
     while (p.hcap < 2 * node_limit) p.hcap *= 2;
     p.max_depth = 62 * n + 8;
@@ -437,7 +440,7 @@ static ArenaPlan plan_arena(int n, int T, int node_limit, size_t pool_bytes, int
     if (pages < (size_t)T + 8) pages = (size_t)T + 8;
     p.n_pool_pages = (uint32_t)pages;
     // per-tree page list: room for node_limit records of 40 edges, twice (the copy of a compaction)
-    size_t half = ((size_t)node_limit * (size_t)(32 + p.sp + 24 * 40) + page_bytes - 1) / page_bytes + 2;
+    size_t half = ((size_t)node_limit * (size_t)(32 + p.cp + 24 * 40) + page_bytes - 1) / page_bytes + 2;
     if (half > pages) half = pages;
     p.max_pages = (int)(2 * half);
     size_t o = 0;
@@ -468,8 +471,8 @@ extern "C" {
 
 size_t spl_mcts_record_bytes(int n_players, int n_edges) {
     if (n_players < 2 || n_players > 4 || n_edges < 0) return 0;
-    const int sp = (7 * (32 + 10 * n_players + n_players * n_players) + 15) / 16 * 16;
-    return (size_t)(32 + sp + 24 * n_edges + 31) / 32 * 32;
+    const int cp = n_players == 2 ? MctsCLay<2>::CP : n_players == 3 ? MctsCLay<3>::CP : MctsCLay<4>::CP;
+    return (size_t)(32 + cp + 24 * n_edges + 31) / 32 * 32;
 }
 
 size_t spl_mcts_arena_bytes(int n_players, int n_trees, int node_limit, size_t pool_bytes, int leaves_per_tree) {
@@ -489,7 +492,7 @@ int spl_mcts_create(spl_ctx* ctx, int n_trees, int node_limit, size_t pool_bytes
     spl_mcts* m = new spl_mcts;
     m->ctx = ctx;
     char* base = (char*)arena;
-    m->A.n_trees = n_trees; m->A.node_limit = node_limit; m->A.hcap = p.hcap; m->A.sp = p.sp; m->A.max_depth = p.max_depth;
+    m->A.n_trees = n_trees; m->A.node_limit = node_limit; m->A.hcap = p.hcap; m->A.sp = p.sp; m->A.cp = p.cp; m->A.max_depth = p.max_depth;
     m->A.max_pages = p.max_pages; m->A.n_pool_pages = p.n_pool_pages; m->A.n_slots = leaves_per_tree;
     m->A.pool = (uint8_t*)(base + p.off_pool);
     m->A.fq_slots = (uint32_t*)(base + p.off_fq);

@@ -124,7 +124,7 @@ struct MctsWarp {
 // ------------------------------------------------------------------------------------------
 enum { MCTS_NODE_TERMINAL = 1, MCTS_NODE_NEEDS_NN = 2, MCTS_NODE_EXPANDED = 3 };
 enum { MCTS_F_FORCED = 1u, MCTS_F_NOISE = 2u };                       // per-move flags (getActionProb :54-58)
-enum { MCTS_S_OVERFLOW_NODES = 1u, MCTS_S_OVERFLOW_POOL = 2u, MCTS_S_PROTOCOL = 4u };   // sticky status bits
+enum { MCTS_S_OVERFLOW_NODES = 1u, MCTS_S_OVERFLOW_POOL = 2u, MCTS_S_PROTOCOL = 4u, MCTS_S_BAD_STATE = 8u };   // sticky status bits
 
 #define MCTS_UNIT 32u            // the pool is addressed in 32-byte units: a 32-bit record offset spans 128 GB
 #define MCTS_PAGE_UNITS 1024u    // 32 KB pages; the largest record (4 players, 406 edges: 10.4 KB) fits
@@ -177,7 +177,7 @@ struct MctsTree {   // 192 B
     int32_t pad[2];
 };
 struct MctsArena {
-    int n_trees, node_limit, hcap, sp, max_depth, max_pages;
+    int n_trees, node_limit, hcap, sp, cp, max_depth, max_pages;   // sp: padded bytes of the reference's state (staging rows); cp: of its compact form (records)
     int n_slots;            // leaves_per_tree: 1 = parity mode; > 1: virtual-loss leaf batching (rows of the per-tree buffers below: tree * n_slots + slot)
     uint32_t n_pool_pages;
     uint8_t* pool;          // [n_pool_pages][32 KB]   node records of all trees (page 0 is never handed out: offset 0 = none)
@@ -220,7 +220,7 @@ struct AosAcc {   // the reference's own array order: cell (row, col) = byte 7*r
     SPL_M void set(int row, int col, int v) { p[7 * row + col] = (int8_t)v; }
 };
 
-// record accessors: [MctsNode 32][state sp][Q double[k]][MctsPN[k]][MctsCA[k]], padded to a multiple of 32 bytes
+// record accessors: [MctsNode 32][compact state cp][Q double[k]][MctsPN[k]][MctsCA[k]], padded to a multiple of 32 bytes
 SPL_D uint32_t* mcts_path(const MctsArena& A, int t, int s) { return A.path + ((size_t)t * A.n_slots + s) * A.max_depth * 2; }
 SPL_D int mcts_row(const MctsArena& A, int t, int s) { return t * A.n_slots + s; }
 // with several simulations in flight (virtual loss) the top byte of an edge's N counts the simulations currently below it
@@ -228,8 +228,8 @@ SPL_D int mcts_row(const MctsArena& A, int t, int s) { return t * A.n_slots + s;
 #define MCTS_N_MASK 0x00FFFFFF
 SPL_D uint8_t* mcts_ptr(const MctsArena& A, uint32_t rec) { return A.pool + (size_t)rec * MCTS_UNIT; }
 SPL_D MctsNode* mcts_node(const MctsArena& A, uint32_t rec) { return reinterpret_cast<MctsNode*>(mcts_ptr(A, rec)); }
-SPL_D int8_t* mcts_state(const MctsArena& A, uint32_t rec) { return reinterpret_cast<int8_t*>(mcts_ptr(A, rec) + 32); }
-SPL_D uint32_t mcts_rec_units(const MctsArena& A, int k) { return (uint32_t)(32 + A.sp + 24 * k + 31) / MCTS_UNIT; }
+SPL_D uint8_t* mcts_cstate(const MctsArena& A, uint32_t rec) { return mcts_ptr(A, rec) + 32; }
+SPL_D uint32_t mcts_rec_units(const MctsArena& A, int k) { return (uint32_t)(32 + A.cp + 24 * k + 31) / MCTS_UNIT; }
 struct MctsEdges {   // the three edge arrays of one record
     double* Q;
     MctsPN* pn;
@@ -243,7 +243,7 @@ struct MctsEdges {   // the three edge arrays of one record
     }
 };
 SPL_D MctsEdges mcts_edges(const MctsArena& A, uint32_t rec, int k) {
-    uint8_t* b = mcts_ptr(A, rec) + 32 + A.sp;
+    uint8_t* b = mcts_ptr(A, rec) + 32 + A.cp;
     MctsEdges e;
     e.Q = reinterpret_cast<double*>(b);
     e.pn = reinterpret_cast<MctsPN*>(b + 8 * (size_t)k);
@@ -264,7 +264,7 @@ SPL_D uint64_t mcts_mix64(uint64_t x) {
 // 64-bit hash of a padded state (sp bytes, 8-byte aligned): a sum of position-salted word mixes, so that any
 // partition of the words over lanes gives the same value
 template <class W>
-SPL_D uint64_t mcts_hash(const W& w, const int8_t* st, int sp) {
+SPL_D uint64_t mcts_hash(const W& w, const uint8_t* st, int sp) {
     const uint64_t* q = reinterpret_cast<const uint64_t*>(st);
     uint64_t h = 0;
     for (int i = w.lane; i < sp / 8; i += W::W) h += mcts_mix64(q[i] + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull);
@@ -288,6 +288,157 @@ SPL_D bool mcts_equal16(const W& w, const void* a, const void* b, int bytes) {
         diff |= (p.x != q.x) | (p.y != q.y) | (p.z != q.z) | (p.w != q.w);
     }
     return w.ballot(diff) == 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// compact node states. A record does not hold the reference's int8[R,7] array (392 / 497 / 616 bytes) but a lossless
+// 80 / 96 / 128-byte form of it: the cells that carry information verbatim (bank + ply counter, the 15 deck bitmasks, the
+// players' gems and card bonuses) and one byte per card / noble row pair (its index in the reference's tables,
+// SplendorLogic.py:320-473) - SURVEY App. A. The transposition key is the compact form: two states are equal iff their compact
+// forms are, because the encoder refuses (returns false) anything it could not give back byte for byte - a row that is no
+// card of the tables, a deck count that is not the popcount of its mask, a cell the rules never write. The rules step and the
+// network read the reference's layout again (mcts_decode).
+// ------------------------------------------------------------------------------------------
+template <int N> struct MctsCLay {
+    static constexpr int BANK = 0, VIS = 7, DECK = 19, NOB = 34, PGEMS = NOB + N + 1, PNOB = PGEMS + 6 * N, PCARDS = PNOB + N * (N + 1),
+                         RES = PCARDS + 6 * N, BYTES = RES + 3 * N;
+    static constexpr int CP = (BYTES + 15) / 16 * 16;                       // 80 / 96 / 128
+    static constexpr int ITEMS = 12 + 3 * N + (N + 1) + N * (N + 1);        // card / noble row groups: one byte each
+};
+#define MCTS_C_DECK 19   // offset of the 15 deck bitmasks (the same for every player count)
+
+SPL_D uint32_t mcts_pack_card(const int8_t* cost, const int8_t* gain, bool* ok) {   // -> the packed form of spl_tables.cuh, 0 = empty slot
+    uint32_t pk = 0u;
+    int ones = 0, col = 0, sum = 0;
+    bool good = cost[5] == 0 && cost[6] == 0 && gain[5] == 0;
+    for (int c = 0; c < 5; c++) {
+        good &= cost[c] >= 0 && cost[c] <= 15 && (gain[c] == 0 || gain[c] == 1);
+        pk |= (uint32_t)(cost[c] & 15) << (4 * c);
+        if (gain[c] == 1) { ones++; col = c; }
+        sum += cost[c];
+    }
+    if (sum == 0 && ones == 0 && gain[6] == 0) { *ok = good; return 0u; }
+    good &= ones == 1 && gain[6] >= 0 && gain[6] <= 15;
+    *ok = good;
+    return pk | ((uint32_t)col << 20) | ((uint32_t)(gain[6] & 15) << 24);
+}
+SPL_D int mcts_find_card(uint32_t pk, int tier_lo, int tier_hi) {   // index tier * 40 + colour * 8 + idx of the first table entry equal to pk, or -1
+    const uint32_t* tab = &SPL_CARDS[0][0][0];
+    for (int i = 40 * tier_lo; i < 40 * tier_hi; i++)
+        if (tab[i] == pk) return i;
+    return -1;
+}
+
+// aos: the reference's int8[R,7] bytes (any memory); cst: CP bytes (zero padded). Every lane of the group takes part; the return value
+// (the same in every lane) says whether the state is one the compact form can give back exactly.
+template <int N, class W>
+SPL_D bool mcts_encode(const W& w, const int8_t* aos, uint8_t* cst) {
+    typedef SplLay<N> L;
+    typedef MctsCLay<N> C;
+    bool ok = true;
+    for (int i = w.lane; i < C::CP; i += W::W) {   // the cells kept verbatim, padding zero
+        int v = 0;
+        if (i < 7) v = aos[i];                                                                        // bank, gold, ply counter
+        else if (i >= C::DECK && i < C::DECK + 15) {
+            const int tier = (i - C::DECK) / 5, c = (i - C::DECK) % 5;
+            v = aos[7 * (L::DECK + 2 * tier + 1) + c];
+            ok &= (int)aos[7 * (L::DECK + 2 * tier) + c] == SPL_POPC((uint32_t)(uint8_t)v);             // count row = cards left in the mask
+            if (c == 0) ok &= aos[7 * (L::DECK + 2 * tier) + 5] == 0 && aos[7 * (L::DECK + 2 * tier) + 6] == 0 &&
+                              aos[7 * (L::DECK + 2 * tier + 1) + 5] == 0 && aos[7 * (L::DECK + 2 * tier + 1) + 6] == 0;
+        } else if (i >= C::PGEMS && i < C::PGEMS + 6 * N) {
+            const int p = (i - C::PGEMS) / 6, c = (i - C::PGEMS) % 6;
+            v = aos[7 * (L::PGEMS + p) + c];
+            if (c == 0) ok &= aos[7 * (L::PGEMS + p) + 6] == 0;
+        } else if (i >= C::PCARDS && i < C::PCARDS + 6 * N) {
+            const int p = (i - C::PCARDS) / 6, c = (i - C::PCARDS) % 6;
+            v = aos[7 * (L::PCARDS + p) + (c < 5 ? c : 6)];                                            // five bonuses + points
+            if (c == 0) ok &= aos[7 * (L::PCARDS + p) + 5] == 0;
+        } else if ((i >= 7 && i < C::DECK) || (i >= C::NOB && i < C::PGEMS) || (i >= C::PNOB && i < C::PCARDS) || (i >= C::RES && i < C::BYTES)) {
+            continue;                                                                                 // card / noble bytes: below
+        }
+        cst[i] = (uint8_t)v;
+    }
+    for (int it = w.lane; it < C::ITEMS; it += W::W) {
+        int at, id = 0xFF;
+        bool good = true;
+        if (it < 12 + 3 * N) {   // a card: two rows (cost, gain)
+            const bool vis = it < 12;
+            const int row = vis ? L::CARDS + 2 * it : L::PRES + 2 * (it - 12);
+            at = vis ? C::VIS + it : C::RES + (it - 12);
+            const uint32_t pk = mcts_pack_card(aos + 7 * row, aos + 7 * (row + 1), &good);
+            if (pk) {
+                const int f = vis ? mcts_find_card(pk, it / 4, it / 4 + 1) : mcts_find_card(pk, 0, 3);
+                good &= f >= 0;
+                id = vis ? f - 40 * (it / 4) : f;
+            }
+        } else {                 // a noble row: on the table or in a player's block
+            const bool tab = it < 12 + 3 * N + N + 1;
+            const int j = it - (12 + 3 * N) - (tab ? 0 : N + 1);
+            const int8_t* r = aos + 7 * ((tab ? L::NOBLES : L::PNOBLES) + j);
+            at = (tab ? C::NOB : C::PNOB) + j;
+            uint32_t pk = 0u;
+            int sum = 0;
+            good = r[5] == 0;
+            for (int c = 0; c < 5; c++) { good &= r[c] >= 0 && r[c] <= 15; pk |= (uint32_t)(r[c] & 15) << (4 * c); sum += r[c]; }
+            if (sum == 0) good &= r[6] == 0;
+            else {
+                good &= r[6] == 3;
+                int f = -1;
+                for (int q = 0; q < 10; q++)
+                    if (SPL_NOBLES[q] == pk && f < 0) f = q;
+                good &= f >= 0;
+                id = f;
+            }
+        }
+        ok &= good;
+        cst[at] = (uint8_t)id;
+    }
+    w.sync();
+    return w.ballot(!ok) == 0u;
+}
+
+// cst -> the reference's int8[R,7] bytes (S of them; any memory)
+template <int N, class W>
+SPL_D void mcts_decode(const W& w, const uint8_t* cst, int8_t* aos) {
+    typedef SplLay<N> L;
+    typedef MctsCLay<N> C;
+    for (int i = w.lane; i < L::CELLS; i += W::W) {   // the verbatim cells, zero elsewhere (card / noble rows are written below)
+        const int row = i / 7, col = i % 7;
+        int v = 0;
+        if (row == 0) v = (int8_t)cst[col];
+        else if (row >= L::DECK && row < L::DECK + 6 && col < 5) {
+            const int m = cst[C::DECK + 5 * ((row - L::DECK) >> 1) + col];
+            v = ((row - L::DECK) & 1) ? (int)(int8_t)m : SPL_POPC((uint32_t)m);
+        } else if (row >= L::PGEMS && row < L::PGEMS + N && col < 6) v = (int8_t)cst[C::PGEMS + 6 * (row - L::PGEMS) + col];
+        else if (row >= L::PCARDS && row < L::PCARDS + N && col != 5) v = (int8_t)cst[C::PCARDS + 6 * (row - L::PCARDS) + (col < 5 ? col : 5)];
+        else if ((row >= L::CARDS && row < L::DECK) || (row >= L::NOBLES && row < L::PGEMS) || (row >= L::PNOBLES && row < L::PCARDS) || row >= L::PRES)
+            continue;
+        aos[i] = (int8_t)v;
+    }
+    for (int it = w.lane; it < C::ITEMS; it += W::W) {
+        if (it < 12 + 3 * N) {
+            const bool vis = it < 12;
+            const int row = vis ? L::CARDS + 2 * it : L::PRES + 2 * (it - 12);
+            const int id = cst[vis ? C::VIS + it : C::RES + (it - 12)];
+            const uint32_t pk = id == 0xFF ? 0u : (&SPL_CARDS[0][0][0])[vis ? 40 * (it / 4) + id : id];
+            const int col = (int)((pk >> 20) & 7u), pts = (int)((pk >> 24) & 15u);
+            int8_t* r = aos + 7 * row;
+            for (int c = 0; c < 5; c++) {
+                r[c] = (int8_t)((pk >> (4 * c)) & 15u);
+                r[7 + c] = (int8_t)((pk && col == c) ? 1 : 0);
+            }
+            r[5] = 0; r[6] = 0; r[12] = 0; r[13] = (int8_t)(pk ? pts : 0);
+        } else {
+            const bool tab = it < 12 + 3 * N + N + 1;
+            const int j = it - (12 + 3 * N) - (tab ? 0 : N + 1);
+            const int id = cst[(tab ? C::NOB : C::PNOB) + j];
+            const uint32_t pk = id == 0xFF ? 0u : SPL_NOBLES[id];
+            int8_t* r = aos + 7 * ((tab ? L::NOBLES : L::PNOBLES) + j);
+            for (int c = 0; c < 5; c++) r[c] = (int8_t)((pk >> (4 * c)) & 15u);
+            r[5] = 0; r[6] = (int8_t)(pk ? 3 : 0);
+        }
+    }
+    w.sync();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -364,13 +515,13 @@ SPL_D uint32_t mcts_alloc(const W& w, const MctsArena& A, int t, uint32_t units,
 
 // nodes_data.get(s) :120 -> record offset or 0
 template <class W>
-SPL_D uint32_t mcts_lookup(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h) {
+SPL_D uint32_t mcts_lookup(const W& w, const MctsArena& A, int t, const uint8_t* st, uint64_t h) {
     const uint32_t* tab = A.htab + (size_t)t * A.hcap;
     uint32_t slot = (uint32_t)h & (uint32_t)(A.hcap - 1);
     for (;;) {
         const uint32_t e = tab[slot];
         if (e == 0u) return 0u;
-        if (mcts_node(A, e)->hash == h && mcts_equal16(w, mcts_state(A, e), st, A.sp)) return e;
+        if (mcts_node(A, e)->hash == h && mcts_equal16(w, mcts_cstate(A, e), st, A.cp)) return e;
         slot = (slot + 1u) & (uint32_t)(A.hcap - 1);
     }
 }
@@ -386,11 +537,11 @@ SPL_D void mcts_table_insert(const W& w, const MctsArena& A, int t, uint32_t rec
     w.sync();
 }
 
-// New node for the state `st` (sp bytes, zero padded) whose end-of-game vector / legal mask are already known:
+// New node for the state with compact form `st` (cp bytes, zero padded) whose end-of-game vector / legal mask are already known:
 // stores the bytes, allocates one edge per legal action (in action order), links it into the hash table.
 // m: the 13 mask words at m[i * mstride]; es: N floats (used when ended). Returns the record or 0 (no room: status bit set).
 template <int N, class W>
-SPL_D uint32_t mcts_store_node(const W& w, const MctsArena& A, int t, const int8_t* st, uint64_t h, bool ended, const float* es,
+SPL_D uint32_t mcts_store_node(const W& w, const MctsArena& A, int t, const uint8_t* st, uint64_t h, bool ended, const float* es,
                                const uint32_t* m, int mstride) {
     MctsTree* T = A.trees + t;
     if (T->n_nodes >= A.node_limit) {
@@ -417,7 +568,7 @@ SPL_D uint32_t mcts_store_node(const W& w, const MctsArena& A, int t, const int8
             nd->u.x.Ns = 0; nd->u.x.Qs = 0.f; nd->u.x.hint = 0u; nd->u.x.pad = 0u;
         }
     }
-    mcts_copy16(w, mcts_state(A, rec), st, A.sp);
+    mcts_copy16(w, mcts_cstate(A, rec), st, A.cp);
     if (!ended) {   // edges in action order: word i of the mask owns a contiguous run
         const MctsEdges ed = mcts_edges(A, rec, k);
         for (int i = w.lane; i < SPL_MASK_WORDS; i += W::W) {
@@ -467,7 +618,7 @@ SPL_D bool mcts_rules_core(S& s, int action, SplRules rules, float* es, uint32_t
 // root creation at the start of a move (one per move per tree: lane 0 evaluates the state, the warp stores it)
 // `scratch` = 24 uint32 of per-warp scratch.
 template <int N, class W>
-SPL_D uint32_t mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, uint64_t h, uint32_t* scratch) {
+SPL_D uint32_t mcts_create_node(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, int8_t* st, const uint8_t* cst, uint64_t h, uint32_t* scratch) {
     if (w.lane == 0) {
         AosAcc s{st};
         float es[N];
@@ -478,7 +629,7 @@ SPL_D uint32_t mcts_create_node(const W& w, const MctsArena& A, int t, const Mct
     w.sync();
     float es[N];
     for (int i = 0; i < N; i++) memcpy(&es[i], &scratch[16 + i], 4);
-    const uint32_t rec = mcts_store_node<N>(w, A, t, st, h, scratch[13] != 0u, es, scratch, 1);
+    const uint32_t rec = mcts_store_node<N>(w, A, t, cst, h, scratch[13] != 0u, es, scratch, 1);
     w.sync();
     return rec;
 }
@@ -652,12 +803,10 @@ SPL_D void mcts_abandon(const W& w, const MctsArena& A, int t, int s, int depth)
 template <int N, class W>
 SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int s, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
                           bool rows = true) {   // rows = false: the staging row of the rules kernel already holds this very state and mask
-    typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
     if (rows) {
         const MctsNode* nd = mcts_node(A, node);
-        const int8_t* src = mcts_state(A, node);
-        for (int i = w.lane; i < ML::S; i += W::W) leaf_state[i] = src[i];
+        mcts_decode<N>(w, mcts_cstate(A, node), leaf_state);
         for (int i = w.lane; i < SPL_ACTIONS; i += W::W) leaf_valid[i] = 0;
         w.sync();
         const int k = (int)nd->n_edges;
@@ -839,15 +988,19 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, int s, const 
 // mask from mcts_rules_core. The dictionary may already hold the state (transposition, :120): then the descent goes on
 // from that node in the next mcts_descend_tree call. Returns 1 if a leaf row was written, 0 otherwise.
 template <int N, bool VL, class W>
-SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, const int8_t* st, bool ended, const float* es,
-                           const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid, bool emit_rows = true) {
+SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, const int8_t* st_aos, uint8_t* st /* cp bytes of scratch */,
+                           bool ended, const float* es, const uint32_t* m, int mstride, int8_t* leaf_state, uint8_t* leaf_valid, bool emit_rows = true) {
     MctsTree* T = A.trees + t;
     MctsSlot* S = T->slot + s;
     const int pe = S->pend_edge;
     if (pe < 0) return S->leaf != 0u ? 1 : 0;
-    const uint64_t h = mcts_hash(w, st, A.sp);
-    uint32_t rec = mcts_lookup(w, A, t, st, h);
-    if (rec == 0u) rec = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
+    uint32_t rec = 0u;
+    if (mcts_encode<N>(w, st_aos, st)) {
+        const uint64_t h = mcts_hash(w, st, A.cp);
+        rec = mcts_lookup(w, A, t, st, h);
+        if (rec == 0u) rec = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
+    } else if (w.lane == 0) T->status |= MCTS_S_BAD_STATE;   // cannot happen for states the rules produced from a representable root
+    w.sync();
     if (rec == 0u) {   // no room: the search of this tree stops here (status bit set)
         if (VL) mcts_abandon(w, A, t, s, S->path_len);
         if (w.lane == 0) { S->pend_edge = -1; S->cur = 0u; S->path_len = 0; }
@@ -998,14 +1151,12 @@ SPL_D void mcts_expand_tree(const W& w, const MctsArena& A, int t, int s, const 
 // When a tree reaches its node limit the survivors are COPIED into fresh pages (every copy independent: lane per record,
 // forwarding pointers in the old headers), the hash table is rebuilt and the old pages go back to the pool.
 // ------------------------------------------------------------------------------------------
-SPL_D void mcts_deck_of(const int8_t* st, uint8_t* deck15) {
-    for (int tier = 0; tier < 3; tier++)
-        for (int c = 0; c < 5; c++) deck15[5 * tier + c] = (uint8_t)st[7 * (26 + 2 * tier) + c];
+SPL_D void mcts_deck_of(const uint8_t* cst, uint8_t* deck15) {   // of a compact state
+    for (int i = 0; i < 15; i++) deck15[i] = cst[MCTS_C_DECK + i];
 }
-SPL_D bool mcts_deck_subset(const int8_t* st, const uint8_t* deck15) {   // every card still in the deck of `st` is still in deck15
+SPL_D bool mcts_deck_subset(const uint8_t* cst, const uint8_t* deck15) {   // every card still in the deck of `cst` is still in deck15
     bool ok = true;
-    for (int tier = 0; tier < 3; tier++)
-        for (int c = 0; c < 5; c++) ok &= ((uint8_t)st[7 * (26 + 2 * tier) + c] & ~deck15[5 * tier + c]) == 0;
+    for (int i = 0; i < 15; i++) ok &= (cst[MCTS_C_DECK + i] & ~deck15[i]) == 0;
     return ok;
 }
 
@@ -1119,7 +1270,7 @@ SPL_D bool mcts_compact(const W& w, const MctsArena& A, int t, bool use_marks, i
             const MctsNode* nd = mcts_node(A, rec);
             k = nd->kind == MCTS_NODE_TERMINAL ? 0 : (int)nd->n_edges;
             if (use_marks) live = nd->fwd != 0u;
-            else live = (int)nd->ply >= min_ply && (!check_deck || mcts_deck_subset(mcts_state(A, rec), deck15));
+            else live = (int)nd->ply >= min_ply && (!check_deck || mcts_deck_subset(mcts_cstate(A, rec), deck15));
         }
         const uint32_t lb = w.ballot(live);
         if (lb == 0u) continue;
@@ -1252,7 +1403,7 @@ SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes,
         mcts_compact(w, A, t, true, 0, nullptr, false);
     } else {
         uint8_t deck[15];
-        mcts_deck_of(mcts_state(A, T->root), deck);
+        mcts_deck_of(mcts_cstate(A, T->root), deck);
         mcts_compact(w, A, t, false, (int)mcts_node(A, T->root)->ply, deck, T->hetero != 0);
     }
 }
@@ -1263,20 +1414,26 @@ SPL_D void mcts_clean_tree(const W& w, const MctsArena& A, int t, int max_nodes,
 // dictionary would not do).
 template <int N, class W>
 SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSearchParams& P, const int8_t* root_state, int sims_target,
-                           uint32_t flags, int gc_reachable, const double* dir, uint32_t episode, int8_t* st, uint32_t* scratch, double* dscratch) {
+                           uint32_t flags, int gc_reachable, const double* dir, uint32_t episode, int8_t* st, uint8_t* cst /* cp bytes */, uint32_t* scratch,
+                           double* dscratch) {
     typedef MctsLay<N> ML;
     MctsTree* T = A.trees + t;
     for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
     w.sync();
+    if (!mcts_encode<N>(w, st, cst)) {   // a board the reference's rules cannot have produced (a row that is no card, a count that is not its mask's)
+        if (w.lane == 0) { T->status |= MCTS_S_BAD_STATE; T->root = 0u; T->sims_done = 0; T->sims_target = 0; }
+        w.sync();
+        return;
+    }
     if (A.n_slots > 1)      // simulations a truncated search left in flight give their virtual visits back
         for (int j = 0; j < A.n_slots; j++) {
             const MctsSlot* S = T->slot + j;
             if (S->leaf != 0u || S->cur != 0u || S->pend_edge >= 0) mcts_abandon(w, A, t, j, S->path_len);
         }
     const int root_ply = (int)(uint8_t)st[6];
-    const uint64_t h = mcts_hash(w, st, A.sp);
+    const uint64_t h = mcts_hash(w, cst, A.cp);
     uint8_t deck[15];
-    mcts_deck_of(st, deck);
+    mcts_deck_of(cst, deck);
     if (T->n_nodes > 0 && !T->hetero) {
         bool same = true, subset = true;
         for (int i = 0; i < 15; i++) { same &= deck[i] == T->deck[i]; subset &= (deck[i] & ~T->deck[i]) == 0; }
@@ -1289,7 +1446,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     const uint32_t overflowed = T->status & (MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_POOL);
     if (overflowed || T->n_nodes + need_nodes > A.node_limit) {
         if (gc_reachable) {
-            const uint32_t old_root = mcts_lookup(w, A, t, st, h);
+            const uint32_t old_root = mcts_lookup(w, A, t, cst, h);
             if (old_root) {
                 mcts_mark_reachable(w, A, old_root);
                 mcts_compact(w, A, t, true, 0, nullptr, false);
@@ -1304,7 +1461,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
             if (T->n_nodes + need_nodes > A.node_limit) {
                 // the exact cleaning did not free enough: fall back to the reachable set of the new root (counted as lossy:
                 // nodes that only a not-yet-linked edge could transpose into are dropped)
-                const uint32_t old_root = mcts_lookup(w, A, t, st, h);
+                const uint32_t old_root = mcts_lookup(w, A, t, cst, h);
                 if (old_root) {
                     mcts_mark_reachable(w, A, old_root);
                     mcts_compact(w, A, t, true, 0, nullptr, false);
@@ -1321,7 +1478,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
         }
         if (w.lane == 0) {
             if (overflowed) T->truncated += 1;
-            T->status &= ~(uint32_t)(MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_POOL);
+            T->status &= ~(uint32_t)(MCTS_S_OVERFLOW_NODES | MCTS_S_OVERFLOW_POOL | MCTS_S_BAD_STATE);
         }
         w.sync();
     }
@@ -1329,8 +1486,8 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
         if (w.lane == 0) { for (int i = 0; i < 15; i++) T->deck[i] = deck[i]; T->hetero = 0; }
         w.sync();
     }
-    uint32_t rec = mcts_lookup(w, A, t, st, h);
-    if (rec == 0u) rec = mcts_create_node<N>(w, A, t, P, st, h, scratch);
+    uint32_t rec = mcts_lookup(w, A, t, cst, h);
+    if (rec == 0u) rec = mcts_create_node<N>(w, A, t, P, st, cst, h, scratch);
     if (w.lane == 0) {
         T->root = rec; T->sims_done = 0; T->sims_target = rec == 0u ? 0 : sims_target;
         T->flags = flags; T->episode = episode;

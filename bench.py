@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--gc", default="exact", choices=["exact", "reachable"],
                     help="tree cleaning: exact = drops only nodes no later search can look up again (ply + deck rule; the parity-tested mode), "
                          "reachable = a tree at its node limit keeps only what the root reaches")
-    ap.add_argument("--pool-nodes", type=float, default=0, help="node records per tree the shared page pool is sized for (0: 5.5 x sims; measured mean 4.6 x sims)")
+    ap.add_argument("--pool-nodes", type=float, default=0, help="node records per tree the shared page pool is sized for (0: 4.8 x sims; measured mean 4.6 x sims at the sampling points)")
     ap.add_argument("--clean-moves", type=float, default=4.0, help="asynchronous mode: clean over-full trees every this many moves' worth of waves")
     ap.add_argument("--rounds", type=int, default=1, help="(descend, rules, attach) passes per selection wave")
     ap.add_argument("--async-moves", type=int, default=1, help="1: every lane moves on as soon as its own search is complete (no lock-step per move)")
@@ -358,7 +358,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
         net = azg.SplendorNNetB200(n, seed=args.seed, device=local, dtype=torch.float32 if args.nn_dtype == "fp32" else torch.bfloat16)
     reach = args.gc == "reachable"
     cap = args.node_cap or 20 * sims          # node limit of ONE tree: a line of ~20 moves without a revealed card
-    pool_nodes = int(args.pool_nodes or 5.5 * sims)  # the shared page pool holds this many records per tree on average
+    pool_nodes = int(args.pool_nodes or 4.8 * sims)  # the shared page pool holds this many records per tree on average (32-bit offsets x 32 B: <= 128 GB)
     G0 = args.tick_waves or (args.graph_waves if args.graph_waves > 0 else 16)
     # exact mode: begin retires / cleans a tree when it has to; reachable mode: periodic cleaning of the over-full trees between waves
     clean_every = max(1, int(args.clean_moves * sims / G0)) if (args.async_moves and reach) else 0

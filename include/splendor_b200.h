@@ -174,6 +174,8 @@ typedef struct spl_mcts spl_mcts;
 #define SPL_MCTS_ST_OVERFLOW_NODES 1  /* the tree holds node_limit nodes */
 #define SPL_MCTS_ST_OVERFLOW_POOL 2   /* no free page left in the shared pool */
 #define SPL_MCTS_ST_PROTOCOL 4        /* select called while a leaf was still waiting for spl_mcts_expand */
+#define SPL_MCTS_ST_BAD_STATE 8       /* a board the rules cannot have produced (a row that is no card of the tables, a deck count that is not
+                                         its mask's popcount): node records hold a compact form that cannot represent it */
 
 typedef struct {
     double   cpuct, fpu;        /* args.cpuct, args.fpu (pick_highest_UCB :199-213) */
@@ -192,7 +194,8 @@ typedef struct {
                                    wave's latency by the typical, not the deepest, path; result-neutral */
 } spl_mcts_params;
 
-/* bytes of one node record with n_edges legal actions (header + state + 24 bytes per edge, rounded to 32): for sizing the pool */
+/* bytes of one node record with n_edges legal actions (32-byte header + compact state of 80 / 96 / 128 bytes + 24 bytes per edge,
+ * rounded to 32): for sizing the pool */
 size_t spl_mcts_record_bytes(int n_players, int n_edges);
 /* bytes of device memory an arena needs. node_limit: most nodes ONE tree may hold (sizes its hash table); pool_bytes: the page
  * pool all trees share - size it for the AVERAGE tree (a tree is retired whenever a real move reveals a card) */

@@ -23,7 +23,8 @@ struct HsMcts {
 template <int N>
 static void hm_step_rules(HsMcts* m, int8_t* st, bool* ended, float* es, uint32_t* mask) {
     const MctsSlot& T = m->A.trees[0].slot[0];
-    memcpy(st, mcts_state(m->A, T.pend_parent), m->A.sp);
+    MctsWarp w{0};
+    mcts_decode<N>(w, mcts_cstate(m->A, T.pend_parent), st);
     AosAcc s{st};
     const int action = (int)mcts_edges(m->A, T.pend_parent, T.pend_edge >> 16).ca[T.pend_edge & 0xFFFF].action;
     *ended = mcts_rules_core<N>(s, action, m->P.rules, es, mask);
@@ -38,8 +39,9 @@ HsMcts* hm_create(int n, int cap, int ecap, int limit, uint32_t rule_flags, doub
     A.n_trees = 1; A.node_limit = cap; A.n_slots = 1;
     A.hcap = 64; while (A.hcap < 2 * cap) A.hcap *= 2;
     A.sp = (7 * (32 + 10 * n + n * n) + 15) / 16 * 16;
+    A.cp = n == 2 ? MctsCLay<2>::CP : n == 3 ? MctsCLay<3>::CP : MctsCLay<4>::CP;
     A.max_depth = 62 * n + 8;
-    const size_t pool_bytes = (size_t)cap * (32 + A.sp) + (size_t)ecap * 24;
+    const size_t pool_bytes = (size_t)cap * (32 + A.cp) + (size_t)ecap * 24;
     A.n_pool_pages = (uint32_t)(pool_bytes / (MCTS_PAGE_UNITS * MCTS_UNIT)) + 4;
     A.max_pages = 2 * (int)A.n_pool_pages;
     A.pool = (uint8_t*)aligned_alloc(256, (size_t)A.n_pool_pages * MCTS_PAGE_UNITS * MCTS_UNIT);
@@ -89,7 +91,8 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
     alignas(16) int8_t st[640];
     uint32_t scratch[24];
     double dscratch[4];
-    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->gc_reachable, dir, m->episode, st, scratch, dscratch));
+    alignas(16) uint8_t cst[128];
+    DISPATCH(m->n, mcts_begin_tree<N>(w, m->A, 0, m->P, root, sims, flags, m->gc_reachable, dir, m->episode, st, cst, scratch, dscratch));
     for (;;) {
         int r = 0;
         DISPATCH(m->n, (r = mcts_descend_tree<N, false>(w, m->A, 0, 0, m->P, 2, 3, m->leaf_state, m->leaf_valid)));
@@ -100,7 +103,7 @@ int hm_search(HsMcts* m, const int8_t* root, int sims, uint32_t flags, const dou
             bool ended = false; float es[4] = {0, 0, 0, 0}; uint32_t mask[13];
             memset(st, 0, sizeof st);
             DISPATCH(m->n, hm_step_rules<N>(m, st, &ended, es, mask));
-            DISPATCH(m->n, (r = mcts_attach_tree<N, false>(w, m->A, 0, 0, m->P, st, ended, es, mask, 1, m->leaf_state, m->leaf_valid)));
+            DISPATCH(m->n, (r = mcts_attach_tree<N, false>(w, m->A, 0, 0, m->P, st, cst, ended, es, mask, 1, m->leaf_state, m->leaf_valid)));
             hm_maybe_clean(m);
             if (r == 0) continue;
         }
@@ -117,6 +120,16 @@ void hm_policy(HsMcts* m, double temp, double* probs, double* q) {
 void hm_root_stats(HsMcts* m, int32_t* nsa, double* qsa, float* ps, int32_t* info8) {
     MctsWarp w{0};
     mcts_root_stats_tree(w, m->A, 0, nsa, qsa, ps, info8);
+}
+int hm_codec_roundtrip(int n, const int8_t* aos, int8_t* back, uint8_t* cst_out) {   // encode -> decode; returns 1 if the encoder accepted the state
+    MctsWarp w{0};
+    alignas(16) uint8_t cst[128];
+    memset(cst, 0, sizeof cst);
+    bool ok = false;
+    DISPATCH(n, ok = mcts_encode<N>(w, aos, cst));
+    if (ok) { DISPATCH(n, mcts_decode<N>(w, cst, back)); }
+    memcpy(cst_out, cst, 128);
+    return ok ? 1 : 0;
 }
 void hm_fixed_net(int n, const int8_t* state, const uint8_t* valid, float* pi, float* v) {
     MctsWarp w{0};

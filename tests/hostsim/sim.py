@@ -110,6 +110,7 @@ def lib_mcts():
         L.hm_root_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.hm_set_clean.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hm_set_episode.argtypes = [C.c_void_p, C.c_uint32]
+        L.hm_codec_roundtrip.argtypes = [C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_int8), C.POINTER(C.c_uint8)]
         L.hm_free_pages.argtypes = [C.c_void_p]
         L.hm_total_pages.argtypes = [C.c_void_p]
         L.hm_fixed_net.argtypes = [C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -158,6 +159,14 @@ class TreeSim:
         return dict(probs=probs, q=q, nsa=nsa.astype(np.int64), qsa=qsa, ps=ps, ns=int(info[2]), qs=info[7:8].view(np.float32)[0],
                     nodes=int(info[0]), edges=int(info[1]), dropped=int(info[14]), pages=int(info[15]), nn_calls=int(info[4]), status=status, truncated=int(info[5]) >> 8, resets=int(info[6]) >> 16,
                     compactions=int(info[6]) & 0xFFFF)
+
+
+def codec_roundtrip(state, n):
+    """compact node-state codec of the tree arena: -> (accepted, decoded state, compact bytes)"""
+    st = np.ascontiguousarray(state, dtype=np.int8)
+    back = np.zeros_like(st); cst = np.zeros(128, dtype=np.uint8)
+    ok = lib_mcts().hm_codec_roundtrip(n, _p(st, C.c_int8), _p(back, C.c_int8), _p(cst, C.c_uint8))
+    return bool(ok), back, cst
 
 
 def fixed_net(state, valids, n):
