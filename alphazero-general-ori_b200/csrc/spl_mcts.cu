@@ -18,6 +18,9 @@
 #include "spl_mcts.cuh"
 
 #define MW 4                 // warps (trees) per CTA
+#ifndef DESC_MINB
+#define DESC_MINB 8          // resident CTAs per SM the descent kernel is compiled for (64 registers)
+#endif
 #define MSP 640              // per-warp state scratch (>= MctsLay<4>::SP = 624)
 
 struct spl_mcts {
@@ -104,7 +107,9 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_rows = A.n_trees * A.n_slots;            // a row = (tree, in-flight slot)
     const int t0 = (blockIdx.x * RW + warp) * TPW, t = t0 + lane;
-    int8_t* wsm = tile_smem + (size_t)warp * TPW * STRIDE;
+    int8_t* wsm = tile_smem + (size_t)warp * (TPW * (STRIDE + 128) + 64);
+    uint8_t* csm = reinterpret_cast<uint8_t*>(wsm + TPW * STRIDE);      // the parents' compact states, 128 bytes each
+    uint32_t* psm = reinterpret_cast<uint32_t*>(csm + TPW * 128);       // their record offsets
     bool pending = false;
     uint32_t parent = 0u;
     int action = 0;
@@ -121,17 +126,25 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
     if (pmask == 0u) return;
     const bool prof_ok = A.n_slots == 1 && t0 < A.n_trees;
     if (prof_ok) { PROF_STAMP(A, t0, 6, prof_globaltimer()); PROF_STAMP(A, t0, 7, clock64()); }
-    {   // the parents' states: records hold the compact form, the rules code reads the reference's layout (the whole warp decodes each)
+    {   // the parents' states: records hold the compact form, the rules code reads the reference's layout. All compact states of the
+        // warp's trees come in with ONE batch of 16-byte loads (one memory round trip), then the whole warp decodes tree after tree.
         const MctsWarp w{lane};
-#pragma unroll
-        for (int j = 0; j < TPW; j++) {
-            const uint32_t par = __shfl_sync(0xffffffffu, parent, j);
-            if ((pmask >> j) & 1u) {
-                int8_t* dst = wsm + j * STRIDE;
-                mcts_decode<N>(w, mcts_cstate(A, par), dst);
-                for (int i = ML::S + lane; i < ML::SP; i += 32) dst[i] = 0;
-            }
+        constexpr int C16 = MctsCLay<N>::CP / 16;
+        if (lane < TPW) psm[lane] = parent;
+        __syncwarp();
+        for (int i = lane; i < TPW * C16; i += 32) {
+            const int j = i / C16, c = i - j * C16;
+            if ((pmask >> j) & 1u) reinterpret_cast<uint4*>(csm + 128 * j)[c] = reinterpret_cast<const uint4*>(mcts_cstate(A, psm[j]))[c];
         }
+        uint4 z; z.x = z.y = z.z = z.w = 0u;
+        for (int i = lane; i < TPW * CH; i += 32) {
+            const int j = i / CH, c = i - j * CH;
+            reinterpret_cast<uint4*>(wsm + j * STRIDE)[c] = z;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TPW; j++)
+            if ((pmask >> j) & 1u) mcts_decode<N>(w, csm + 128 * j, wsm + j * STRIDE, true);
         __syncwarp();
     }
     if (prof_ok) PROF_STAMP(A, t0, 8, clock64());
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(RW * 32) mcts_rules_kernel(MctsArena A, SplRul
 template <int N>
 static cudaError_t launch_rules(const MctsArena& A, const SplRules& rules, int tpw, cudaStream_t st) {
     const int warps = (A.n_trees * A.n_slots + tpw - 1) / tpw, grid = (warps + RW - 1) / RW;
-    const int smem = RW * tpw * RulesSmem<N>::STRIDE;
+    const int smem = RW * (tpw * (RulesSmem<N>::STRIDE + 128) + 64);
     switch (tpw) {
         case 16: mcts_rules_kernel<N, 16><<<grid, RW * 32, smem, st>>>(A, rules); break;
         case 8: mcts_rules_kernel<N, 8><<<grid, RW * 32, smem, st>>>(A, rules); break;
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, Mc
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
     __shared__ __align__(16) uint8_t s_cs[MW][128];
+    __shared__ __align__(16) int8_t s_aos[MW][MSP];
     MctsWarp w{(int)(threadIdx.x & 31)};
     PROF_STAMP(A, t, 12, prof_globaltimer()); PROF_STAMP(A, t, 13, clock64());
     const int n_rows = A.n_trees * A.n_slots;
@@ -189,7 +203,12 @@ __global__ void __launch_bounds__(MW * 32, 8) mcts_attach_kernel(MctsArena A, Mc
     bool waiting = false;
     for (int s = 0; s < (VL ? A.n_slots : 1); s++) {   // the slots of a tree one after the other: node creation stays deterministic
         const size_t r = (size_t)mcts_row(A, t, s);
-        const int leaf = mcts_attach_tree<N, VL>(w, A, t, s, P, A.stage_state + r * A.sp, s_cs[warp], A.stage_ended[r] != 0, A.stage_es + r * 4,
+        if (A.trees[t].slot[s].pend_edge >= 0) {   // the child's bytes: staging row -> shared memory (the encoder reads them cell by cell)
+            const uint4* src = reinterpret_cast<const uint4*>(A.stage_state + r * A.sp);
+            for (int i = w.lane; i < A.sp / 16; i += 32) reinterpret_cast<uint4*>(s_aos[warp])[i] = src[i];
+        }
+        __syncwarp();
+        const int leaf = mcts_attach_tree<N, VL>(w, A, t, s, P, s_aos[warp], s_cs[warp], A.stage_ended[r] != 0, A.stage_es + r * 4,
                                                  A.stage_mask + r, n_rows, leaf_states + r * MctsLay<N>::S, leaf_valids + r * SPL_ACTIONS, emit_rows);
         __syncwarp();
         if (w.lane == 0) leaf_flags[r] = (uint8_t)leaf;
@@ -248,8 +267,11 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
     const int action = (int)mcts_edges(A, T->pend_parent, pe >> 16).ca[pe & 0xFFFF].action;
     {
         const MctsWarp w{lane};
-        mcts_decode<N>(w, mcts_cstate(A, T->pend_parent), wsm);
-        for (int i = MctsLay<N>::S + lane; i < MctsLay<N>::SP; i += 32) wsm[i] = 0;
+        uint4 z; z.x = z.y = z.z = z.w = 0u;
+        if (lane < CH) reinterpret_cast<uint4*>(wsm)[lane] = z;
+        if (lane + 32 < CH) reinterpret_cast<uint4*>(wsm)[lane + 32] = z;
+        __syncwarp();
+        mcts_decode<N>(w, mcts_cstate(A, T->pend_parent), wsm, true);
         __syncwarp();
     }
     PROF_STAMP(A, t, 8, clock64());
@@ -307,7 +329,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
 // expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree);
 // RULES: followed by the rules step of the tree's pending edge (spl_mcts_wave_nnet; otherwise mcts_rules_kernel does it)
 template <int N, bool RULES, bool VL>
-__global__ void __launch_bounds__(MW * 32, 7) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
+__global__ void __launch_bounds__(MW * 32, DESC_MINB) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
                                                                          int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);

@@ -165,8 +165,8 @@ struct MctsTree {   // 192 B
     float last_v[4];   // value vector the last finished simulation returned at the root (what MCTS.search returns)
     int32_t truncated; // searches cut short because the tree hit its node limit or the pool ran dry mid-move
     int32_t depth_sum; // sum of path lengths of the simulations since the last reset (diagnostics)
-    MctsSlot slot[MCTS_KMAX];
     int32_t spec_hits;    // diagnostics: levels of the descents that started from the early-fetched child (see mcts_descend_tree)
+    MctsSlot slot[MCTS_KMAX];
     // storage
     int32_t n_pages;      // pages owned: tree_pages[t][0 .. n_pages)
     uint32_t bump, page_end;   // next free unit / end of the page being filled
@@ -322,41 +322,65 @@ SPL_D uint32_t mcts_pack_card(const int8_t* cost, const int8_t* gain, bool* ok) 
     *ok = good;
     return pk | ((uint32_t)col << 20) | ((uint32_t)(gain[6] & 15) << 24);
 }
-SPL_D int mcts_find_card(uint32_t pk, int tier_lo, int tier_hi) {   // index tier * 40 + colour * 8 + idx of the first table entry equal to pk, or -1
+// index tier * 40 + deck colour * 8 + idx of the table entry equal to pk, or -1. The tables are grouped by the DECK colour of
+// SplendorLogic.py (np_all_cards_*), which is a fixed permutation of the card's gain colour: only that group of 8 is searched.
+SPL_D int mcts_find_card(uint32_t pk, int tier_lo, int tier_hi) {
     const uint32_t* tab = &SPL_CARDS[0][0][0];
-    for (int i = 40 * tier_lo; i < 40 * tier_hi; i++)
-        if (tab[i] == pk) return i;
-    return -1;
+    const int g = (int)((pk >> 20) & 7u);
+    const int dc = g == 0 ? 3 : g == 1 ? 0 : g == 2 ? 4 : g == 3 ? 1 : 2;
+    int f = -1;
+    for (int t = tier_hi - 1; t >= tier_lo; t--) {   // branch-free: the 8 loads of a group are independent (one round trip)
+        const uint32_t* grp = tab + 40 * t + 8 * dc;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) f = grp[i] == pk ? 40 * t + 8 * dc + i : f;
+    }
+    return f;
+}
+
+// compact byte i (one of the verbatim ones) <-> cell of the reference's layout; returns false for the card / noble bytes and the padding
+template <int N>
+SPL_D bool mcts_cmap(int i, int* cell, int* count_cell) {
+    typedef SplLay<N> L;
+    typedef MctsCLay<N> C;
+    *count_cell = -1;
+    if (i < 7) { *cell = i; return true; }                                                              // bank, gold, ply counter
+    if (i >= C::DECK && i < C::DECK + 15) {
+        const int j = i - C::DECK, tier = j / 5, c = j - 5 * tier;
+        *cell = 7 * (L::DECK + 2 * tier + 1) + c; *count_cell = 7 * (L::DECK + 2 * tier) + c;             // mask byte; its count = popcount
+        return true;
+    }
+    if (i >= C::PGEMS && i < C::PGEMS + 6 * N) { const int j = i - C::PGEMS, p = j / 6; *cell = 7 * (L::PGEMS + p) + (j - 6 * p); return true; }
+    if (i >= C::PCARDS && i < C::PCARDS + 6 * N) {
+        const int j = i - C::PCARDS, p = j / 6, c = j - 6 * p;
+        *cell = 7 * (L::PCARDS + p) + (c < 5 ? c : 6);                                                  // five bonuses + points
+        return true;
+    }
+    return false;
 }
 
 // aos: the reference's int8[R,7] bytes (any memory); cst: CP bytes (zero padded). Every lane of the group takes part; the return value
-// (the same in every lane) says whether the state is one the compact form can give back exactly.
-template <int N, class W>
+// (the same in every lane) says whether the state is one the compact form can give back exactly. VALIDATE = false: for states the
+// rules code itself produced from an accepted state (children inside the tree): only the table look-ups, no checks.
+template <int N, bool VALIDATE, class W>
 SPL_D bool mcts_encode(const W& w, const int8_t* aos, uint8_t* cst) {
     typedef SplLay<N> L;
     typedef MctsCLay<N> C;
     bool ok = true;
-    for (int i = w.lane; i < C::CP; i += W::W) {   // the cells kept verbatim, padding zero
-        int v = 0;
-        if (i < 7) v = aos[i];                                                                        // bank, gold, ply counter
-        else if (i >= C::DECK && i < C::DECK + 15) {
-            const int tier = (i - C::DECK) / 5, c = (i - C::DECK) % 5;
-            v = aos[7 * (L::DECK + 2 * tier + 1) + c];
-            ok &= (int)aos[7 * (L::DECK + 2 * tier) + c] == SPL_POPC((uint32_t)(uint8_t)v);             // count row = cards left in the mask
-            if (c == 0) ok &= aos[7 * (L::DECK + 2 * tier) + 5] == 0 && aos[7 * (L::DECK + 2 * tier) + 6] == 0 &&
-                              aos[7 * (L::DECK + 2 * tier + 1) + 5] == 0 && aos[7 * (L::DECK + 2 * tier + 1) + 6] == 0;
-        } else if (i >= C::PGEMS && i < C::PGEMS + 6 * N) {
-            const int p = (i - C::PGEMS) / 6, c = (i - C::PGEMS) % 6;
-            v = aos[7 * (L::PGEMS + p) + c];
-            if (c == 0) ok &= aos[7 * (L::PGEMS + p) + 6] == 0;
-        } else if (i >= C::PCARDS && i < C::PCARDS + 6 * N) {
-            const int p = (i - C::PCARDS) / 6, c = (i - C::PCARDS) % 6;
-            v = aos[7 * (L::PCARDS + p) + (c < 5 ? c : 6)];                                            // five bonuses + points
-            if (c == 0) ok &= aos[7 * (L::PCARDS + p) + 5] == 0;
-        } else if ((i >= 7 && i < C::DECK) || (i >= C::NOB && i < C::PGEMS) || (i >= C::PNOB && i < C::PCARDS) || (i >= C::RES && i < C::BYTES)) {
-            continue;                                                                                 // card / noble bytes: below
+    for (int i = w.lane; i < C::CP; i += W::W) {
+        int cell, cnt;
+        if (mcts_cmap<N>(i, &cell, &cnt)) {
+            const int v = aos[cell];
+            cst[i] = (uint8_t)v;
+            if (VALIDATE && cnt >= 0) ok &= (int)aos[cnt] == SPL_POPC((uint32_t)(uint8_t)v);
+        } else if (i >= C::BYTES) cst[i] = 0;
+    }
+    if (VALIDATE) {   // cells the rules never write must be zero (the decoder writes zeros there)
+        for (int i = w.lane; i < 6 + 2 * N; i += W::W) {
+            const int row = i < 6 ? L::DECK + i : (i < 6 + N ? L::PGEMS + (i - 6) : L::PCARDS + (i - 6 - N));
+            if (i < 6) ok &= aos[7 * row + 5] == 0 && aos[7 * row + 6] == 0;
+            else if (i < 6 + N) ok &= aos[7 * row + 6] == 0;
+            else ok &= aos[7 * row + 5] == 0;
         }
-        cst[i] = (uint8_t)v;
     }
     for (int it = w.lane; it < C::ITEMS; it += W::W) {
         int at, id = 0xFF;
@@ -384,8 +408,8 @@ SPL_D bool mcts_encode(const W& w, const int8_t* aos, uint8_t* cst) {
             else {
                 good &= r[6] == 3;
                 int f = -1;
-                for (int q = 0; q < 10; q++)
-                    if (SPL_NOBLES[q] == pk && f < 0) f = q;
+#pragma unroll
+                for (int q = 9; q >= 0; q--) f = SPL_NOBLES[q] == pk ? q : f;
                 good &= f >= 0;
                 id = f;
             }
@@ -394,48 +418,46 @@ SPL_D bool mcts_encode(const W& w, const int8_t* aos, uint8_t* cst) {
         cst[at] = (uint8_t)id;
     }
     w.sync();
-    return w.ballot(!ok) == 0u;
+    return VALIDATE ? w.ballot(!ok) == 0u : true;
 }
 
-// cst -> the reference's int8[R,7] bytes (S of them; any memory)
+// cst -> the reference's int8[R,7] bytes (S of them; any memory). ZEROED: the destination is already all zero.
 template <int N, class W>
-SPL_D void mcts_decode(const W& w, const uint8_t* cst, int8_t* aos) {
+SPL_D void mcts_decode(const W& w, const uint8_t* cst, int8_t* aos, bool zeroed = false) {
     typedef SplLay<N> L;
     typedef MctsCLay<N> C;
-    for (int i = w.lane; i < L::CELLS; i += W::W) {   // the verbatim cells, zero elsewhere (card / noble rows are written below)
-        const int row = i / 7, col = i % 7;
-        int v = 0;
-        if (row == 0) v = (int8_t)cst[col];
-        else if (row >= L::DECK && row < L::DECK + 6 && col < 5) {
-            const int m = cst[C::DECK + 5 * ((row - L::DECK) >> 1) + col];
-            v = ((row - L::DECK) & 1) ? (int)(int8_t)m : SPL_POPC((uint32_t)m);
-        } else if (row >= L::PGEMS && row < L::PGEMS + N && col < 6) v = (int8_t)cst[C::PGEMS + 6 * (row - L::PGEMS) + col];
-        else if (row >= L::PCARDS && row < L::PCARDS + N && col != 5) v = (int8_t)cst[C::PCARDS + 6 * (row - L::PCARDS) + (col < 5 ? col : 5)];
-        else if ((row >= L::CARDS && row < L::DECK) || (row >= L::NOBLES && row < L::PGEMS) || (row >= L::PNOBLES && row < L::PCARDS) || row >= L::PRES)
-            continue;
-        aos[i] = (int8_t)v;
+    if (!zeroed) {
+        for (int i = w.lane; i < L::CELLS; i += W::W) aos[i] = 0;
+        w.sync();
+    }
+    for (int i = w.lane; i < C::BYTES; i += W::W) {   // the verbatim cells
+        int cell, cnt;
+        if (mcts_cmap<N>(i, &cell, &cnt)) {
+            const int v = cst[i];
+            aos[cell] = (int8_t)v;
+            if (cnt >= 0) aos[cnt] = (int8_t)SPL_POPC((uint32_t)v);
+        }
     }
     for (int it = w.lane; it < C::ITEMS; it += W::W) {
         if (it < 12 + 3 * N) {
             const bool vis = it < 12;
-            const int row = vis ? L::CARDS + 2 * it : L::PRES + 2 * (it - 12);
             const int id = cst[vis ? C::VIS + it : C::RES + (it - 12)];
-            const uint32_t pk = id == 0xFF ? 0u : (&SPL_CARDS[0][0][0])[vis ? 40 * (it / 4) + id : id];
-            const int col = (int)((pk >> 20) & 7u), pts = (int)((pk >> 24) & 15u);
+            if (id == 0xFF) continue;
+            const int row = vis ? L::CARDS + 2 * it : L::PRES + 2 * (it - 12);
+            const uint32_t pk = (&SPL_CARDS[0][0][0])[vis ? 40 * (it / 4) + id : id];
             int8_t* r = aos + 7 * row;
-            for (int c = 0; c < 5; c++) {
-                r[c] = (int8_t)((pk >> (4 * c)) & 15u);
-                r[7 + c] = (int8_t)((pk && col == c) ? 1 : 0);
-            }
-            r[5] = 0; r[6] = 0; r[12] = 0; r[13] = (int8_t)(pk ? pts : 0);
+            for (int c = 0; c < 5; c++) r[c] = (int8_t)((pk >> (4 * c)) & 15u);
+            r[7 + (int)((pk >> 20) & 7u)] = 1;
+            r[13] = (int8_t)((pk >> 24) & 15u);
         } else {
             const bool tab = it < 12 + 3 * N + N + 1;
             const int j = it - (12 + 3 * N) - (tab ? 0 : N + 1);
             const int id = cst[(tab ? C::NOB : C::PNOB) + j];
-            const uint32_t pk = id == 0xFF ? 0u : SPL_NOBLES[id];
+            if (id == 0xFF) continue;
+            const uint32_t pk = SPL_NOBLES[id];
             int8_t* r = aos + 7 * ((tab ? L::NOBLES : L::PNOBLES) + j);
             for (int c = 0; c < 5; c++) r[c] = (int8_t)((pk >> (4 * c)) & 15u);
-            r[5] = 0; r[6] = (int8_t)(pk ? 3 : 0);
+            r[6] = 3;
         }
     }
     w.sync();
@@ -783,8 +805,13 @@ SPL_D void mcts_backup(const W& w, const MctsArena& A, int t, int s, int depth, 
 
 // VL: a simulation that cannot go on this wave (another simulation of the tree already waits at the same node or edge) is
 // given up: its virtual visits are taken back along the recorded path, nothing else was changed
+#ifdef __CUDACC__
+template <class W>
+static __device__ __noinline__ void mcts_abandon(const W& w, const MctsArena& A, int t, int s, int depth) {
+#else
 template <class W>
 SPL_D void mcts_abandon(const W& w, const MctsArena& A, int t, int s, int depth) {
+#endif
     const uint32_t* path = mcts_path(A, t, s);
     for (int d = w.lane; d < depth; d += W::W) {
         const uint32_t rec = path[2 * d], pe = path[2 * d + 1];
@@ -800,8 +827,14 @@ SPL_D void mcts_abandon(const W& w, const MctsArena& A, int t, int s, int depth)
 }
 
 // hands a node that waits for the network to the leaf row of its tree (:136-138)
+#ifdef __CUDACC__
 template <int N, class W>
-SPL_D void mcts_emit_leaf(const W& w, const MctsArena& A, int t, int s, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
+static __device__ __noinline__ void mcts_emit_leaf(
+#else
+template <int N, class W>
+SPL_D void mcts_emit_leaf(
+#endif
+const W& w, const MctsArena& A, int t, int s, uint32_t node, int depth, int sims_done, int8_t* leaf_state, uint8_t* leaf_valid,
                           bool rows = true) {   // rows = false: the staging row of the rules kernel already holds this very state and mask
     MctsTree* T = A.trees + t;
     if (rows) {
@@ -995,7 +1028,7 @@ SPL_D int mcts_attach_tree(const W& w, const MctsArena& A, int t, int s, const M
     const int pe = S->pend_edge;
     if (pe < 0) return S->leaf != 0u ? 1 : 0;
     uint32_t rec = 0u;
-    if (mcts_encode<N>(w, st_aos, st)) {
+    if (mcts_encode<N, false>(w, st_aos, st)) {   // (the child of a node of this tree: made by the rules code from an accepted state)
         const uint64_t h = mcts_hash(w, st, A.cp);
         rec = mcts_lookup(w, A, t, st, h);
         if (rec == 0u) rec = mcts_store_node<N>(w, A, t, st, h, ended, es, m, mstride);
@@ -1420,7 +1453,7 @@ SPL_D void mcts_begin_tree(const W& w, const MctsArena& A, int t, const MctsSear
     MctsTree* T = A.trees + t;
     for (int i = w.lane; i < ML::SP; i += W::W) st[i] = i < ML::S ? root_state[i] : (int8_t)0;
     w.sync();
-    if (!mcts_encode<N>(w, st, cst)) {   // a board the reference's rules cannot have produced (a row that is no card, a count that is not its mask's)
+    if (!mcts_encode<N, true>(w, st, cst)) {   // a board the reference's rules cannot have produced (a row that is no card, a count that is not its mask's)
         if (w.lane == 0) { T->status |= MCTS_S_BAD_STATE; T->root = 0u; T->sims_done = 0; T->sims_target = 0; }
         w.sync();
         return;

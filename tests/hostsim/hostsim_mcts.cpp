@@ -126,7 +126,7 @@ int hm_codec_roundtrip(int n, const int8_t* aos, int8_t* back, uint8_t* cst_out)
     alignas(16) uint8_t cst[128];
     memset(cst, 0, sizeof cst);
     bool ok = false;
-    DISPATCH(n, ok = mcts_encode<N>(w, aos, cst));
+    DISPATCH(n, (ok = mcts_encode<N, true>(w, aos, cst)));
     if (ok) { DISPATCH(n, mcts_decode<N>(w, cst, back)); }
     memcpy(cst_out, cst, 128);
     return ok ? 1 : 0;
