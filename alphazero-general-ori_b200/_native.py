@@ -29,7 +29,7 @@ EXPORTS = [
     "spl_scores", "spl_symmetries",
     "spl_mcts_record_bytes", "spl_mcts_arena_bytes", "spl_mcts_create", "spl_mcts_set_episodes", "spl_mcts_pool_stats", "spl_mcts_destroy", "spl_mcts_set_params", "spl_mcts_reset", "spl_mcts_clean", "spl_mcts_begin",
     "spl_mcts_select", "spl_mcts_expand", "spl_mcts_expand_select", "spl_mcts_wave_nnet", "spl_mcts_debug_profile", "spl_mcts_policy", "spl_mcts_sample_moves", "spl_mcts_root_stats", "spl_mcts_fixed_net",
-    "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_nnet_debug_cta_times", "spl_umma_selftest",
+    "spl_nnet_blob_bytes", "spl_nnet_pack", "spl_nnet_forward", "spl_nnet_debug_stamps", "spl_nnet_debug_tile_stamps", "spl_nnet_debug_cta_times", "spl_umma_selftest", "spl_umma_selftest_mn", "spl_umma_mma_cycles", "spl_umma_stream_cycles",
 ]
 MCTS_MOVE_FORCED, MCTS_MOVE_NOISE = 1, 2
 MCTS_INFO_WORDS = 16
@@ -147,6 +147,9 @@ def lib():
         L.spl_nnet_blob_bytes.restype = C.c_size_t
         L.spl_nnet_pack.argtypes = [ci, C.POINTER(C.POINTER(C.c_float)), vp, C.c_size_t]
         L.spl_umma_selftest.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp]
+        L.spl_umma_selftest_mn.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
+        L.spl_umma_stream_cycles.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
+        L.spl_umma_mma_cycles.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
         L.spl_nnet_forward.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp]
         _lib = L
     return _lib

@@ -22,6 +22,18 @@ int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, c
                            const int8_t* alt_states, int alt_stride, const uint32_t* alt_mask, int alt_mask_stride, int n_rows, float* pi,
                            float* v, cudaStream_t st, bool programmatic_dependent = false);
 
+// spl_nnet2.cu: the transposed evaluator (default); spl_nnet.cu keeps the first version behind SPL_NNET_IMPL=1 for comparison
+namespace nn2 {
+size_t blob_bytes(int n);
+int pack(int n, const float* const* T, void* blob, size_t blob_bytes_);
+int forward_rows(spl_ctx* c, const void* blob, const int8_t* states, const uint8_t* valids, const uint8_t* row_src, const int8_t* alt_states,
+                 int alt_stride, const uint32_t* alt_mask, int alt_mask_stride, int n_rows, float* pi, float* v, cudaStream_t st,
+                 bool programmatic_dependent);
+int debug_stamps(long long* out32);
+int debug_tile_stamps(long long* out);
+}
+int spl_nnet_impl_();   // 1 or 2 (environment variable SPL_NNET_IMPL, read once)
+
 #define DISPATCH_N(n, ...)                                   \
     switch (n) {                                             \
         case 2: { constexpr int N = 2; __VA_ARGS__; } break; \

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "spl_internal.h"
@@ -698,15 +699,26 @@ void pack_canonical(unsigned char* dst, const float* W, int N, int K, int n0, in
 
 }   // namespace
 
+int spl_nnet_impl_() {
+    static const int impl = [] { const char* e = getenv("SPL_NNET_IMPL"); return (e && e[0] == '1') ? 1 : 2; }();
+    return impl;
+}
+
 extern "C" {
 
 size_t spl_nnet_blob_bytes(int n_players) {
     if (n_players < 2 || n_players > 4) return 0;
+    if (spl_nnet_impl_() == 2) return nn2::blob_bytes(n_players);
     return (size_t)make_plan(n_players).total_bytes;
 }
 
 int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_bytes) {
     if (n_players < 2 || n_players > 4 || !T || !blob) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: bad argument");
+    if (spl_nnet_impl_() == 2) {
+        for (int i = 0; i < 46; i++)
+            if (!T[i]) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: null tensor");
+        return nn2::pack(n_players, T, blob, blob_bytes);
+    }
     const NnPlan p = make_plan(n_players);
     if (blob_bytes < (size_t)p.total_bytes) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: blob smaller than spl_nnet_blob_bytes");
     for (int i = 0; i < 46; i++)
@@ -756,9 +768,15 @@ int spl_nnet_pack(int n_players, const float* const* T, void* blob, size_t blob_
 }
 
 int spl_nnet_debug_stamps(long long* out32) {   /* diagnostics only: SM-clock stamps of the last launch's CTA 0 */
+    if (spl_nnet_impl_() == 2) return nn2::debug_stamps(out32);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpyFromSymbol(out32, g_nn_stamps, sizeof(long long) * 32));
     return SPL_OK;
+}
+
+int spl_nnet_debug_tile_stamps(long long* out144) {   /* diagnostics only: per weight tile of CTA 0: requested / landed / MMAs issued (SM clock) */
+    if (spl_nnet_impl_() != 2) return spl_fail_(SPL_E_ARG, "spl_nnet_debug_tile_stamps: transposed evaluator only");
+    return nn2::debug_tile_stamps(out144);
 }
 
 int spl_nnet_debug_cta_times(long long* out320) {   /* diagnostics only: globaltimer (ns) at the start / end of the first 160 CTAs */
@@ -781,6 +799,8 @@ int spl_nnet_forward_rows_(spl_ctx* c, const void* blob, const int8_t* states, c
     if (!blob || !states || !valids || !pi || !v || n_rows <= 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: bad argument");
     if (row_src && (!alt_states || !alt_mask)) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: row_src without staging rows");
     if (((uintptr_t)blob & 15u) != 0) return spl_fail_(SPL_E_ARG, "spl_nnet_forward: blob must be 16-byte aligned");
+    if (spl_nnet_impl_() == 2)
+        return nn2::forward_rows(c, blob, states, valids, row_src, alt_states, alt_stride, alt_mask, alt_mask_stride, n_rows, pi, v, st, programmatic_dependent);
     const NnPlan p = make_plan(c->n);
     const int grid = (n_rows + NN_SB * NN_GROUPS - 1) / (NN_SB * NN_GROUPS);
     const int smem = (int)sizeof(NnSmem);

@@ -27,6 +27,12 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// the same with the B operand MN-major (bit 16): B is stored [K][N] with N contiguous - core matrices of 8 k-rows x 16 bytes (8
+// consecutive n), element (n, k) at (n / 8) * SBO + (k / 8) * LBO + (k % 8) * 16 + (n % 8) * 2 (cute: ((1,n),(8,k)):((X,SBO),(1,LBO)) in
+// 16-byte units). This is the layout an epilogue thread that owns ONE accumulator row (= one k of the next product) writes with plain
+// 16-byte stores: 8 consecutive columns per store, the 32 lanes of a warp 512 contiguous bytes.
+__host__ __device__ constexpr uint32_t instr_desc_bf16_bmn(int m, int n) { return instr_desc_bf16(m, n) | (1u << 16); }
+
 // byte offset of element (r, k) inside an operand tile (see above); k8 = k / 8 (the 16-byte chunk), kc = chunks per row
 __device__ __forceinline__ uint32_t chunk_off(int r, int k8, int kc) { return (uint32_t)((r >> 3) * kc * 128 + k8 * 128 + (r & 7) * 16); }
 

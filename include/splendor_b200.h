@@ -295,8 +295,21 @@ int spl_nnet_forward(spl_ctx* ctx, const void* blob, const int8_t* states, const
 /* self-test of the tcgen05 / TMEM building blocks the evaluator is made of: out float[128][n] = A bf16[128][k] . B bf16[n][k]^T on
  * one CTA (n a multiple of 32, k a multiple of 16, both <= 256; device pointers). *err_flag (device int) becomes 1 if the completion barrier timed out. */
 int spl_umma_selftest(spl_ctx* ctx, const void* a_bf16, const void* b_bf16, float* out, int n, int k, int* err_flag, void* stream);
+/* the same product with B staged MN-major in shared memory (element (n, k) at (n/8) stride_n8 + (k/8) stride_k8 + (k%8) 16 + (n%8) 2 bytes;
+   lbo / sbo = the two byte offsets of the shared-memory descriptor): the operand layout of the transposed evaluator (spl_nnet.cu) */
+int spl_umma_selftest_mn(spl_ctx* ctx, const void* a_bf16, const void* b_bf16, float* out, int n, int k, int stride_k8, int stride_n8, int lbo,
+                         int sbo, int* err_flag, void* stream);
+/* diagnostics: SM cycles per CTA to stream `tiles` tiles of tile_bytes from an L2-resident buffer of src_tiles tiles into a ring of `depth`
+   shared-memory slots, all `grid` CTAs at once (mode 0: cp.async.bulk by one thread, 1: 16-byte cp.async by one warp); out[grid] on the device */
+int spl_umma_stream_cycles(spl_ctx* ctx, const void* src, int src_tiles, int tile_bytes, int depth, int tiles, int mode, int grid, long long* out,
+                           void* stream);
+/* diagnostics: SM cycles of reps x ksteps tcgen05.mma (M 128, N n, K 16) on zero operands: out2[0] issue, out2[1] until the commit arrives
+   (device memory); b_mn = 1: B operand MN-major with the given SBO */
+int spl_umma_mma_cycles(spl_ctx* ctx, int n, int ksteps, int b_mn, int sbo, int reps, long long* out2, void* stream);
 /* diagnostics: SM-clock time stamps of the phases of CTA 0 in the last spl_nnet_forward launch (long long[32]) */
 int spl_nnet_debug_stamps(long long* out32);
+/* diagnostics: per weight tile of CTA 0 in the last launch: SM clock when it was requested, when it had landed, when its MMAs were issued (long long[3][48]) */
+int spl_nnet_debug_tile_stamps(long long* out144);
 /* diagnostics: globaltimer (ns) at the start and the end of the first 160 CTAs of the last spl_nnet_forward launch (long long[320]) */
 int spl_nnet_debug_cta_times(long long* out320);
 
