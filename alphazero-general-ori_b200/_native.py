@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.realpath(os.path.join(HERE, "..", "include"))
-LIB = os.path.join(HERE, "libsplendor_b200.so")
+LIB = os.environ.get("SPL_B200_LIB") or os.path.join(HERE, "libsplendor_b200.so")   # SPL_B200_LIB: a variant build (experiments)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -109,22 +109,59 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_mn_kernel(const __nv_bfl
     if (warp == 0) umma::tmem_dealloc(tbase, 256);
 }
 
+__device__ long long g_sink;
 // diagnostics: SM cycles of `reps` x `ksteps` MMAs (M = 128, N = n, K = 16 each) on zero operands, from the first issue to the arrival
 // of the commit; b_mn: B operand MN-major (LBO 128, SBO = sbo bytes) instead of K-major (LBO 128, SBO = ksteps * 256)
-__global__ void __launch_bounds__(128, 1) umma_cycles_kernel(int n, int ksteps, int b_mn, int sbo, int reps, long long* __restrict__ out) {
+__global__ void __launch_bounds__(128, 1) umma_cycles_kernel(int n, int ksteps, int b_mn_in, int sbo, int reps, long long* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2, bar3;
+    const int b_mn = b_mn_in & 1;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     umma::fence_smem_to_async();
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
-    if (tid == 0) umma::mbar_init(&bar, 1);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1); umma::mbar_init(&bar2, 1); umma::mbar_init(&bar3, 1);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar3)) : "memory");   // phase 0 of bar3 is complete
+    }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tbase = tmem_slot;
-    if (tid == 0) {
+    if ((b_mn_in & 12) && warp == 0) {
+        // lean issue: descriptors built once, groups of 4 k-steps unrolled with immediate offsets; bit 2: one thread, bit 3: the whole
+        // warp runs the loop and an elected lane issues (uniform registers); bit 1: a commit after every group
+        const uint32_t idesc = b_mn ? umma::instr_desc_bf16_bmn(128, n) : umma::instr_desc_bf16(128, n);
+        const uint32_t sA = umma::smem_u32(smem), sB = sA + 32 * 1024;
+        const uint64_t ad0 = umma::smem_desc(sA, 128, 4 * 256), bd0 = umma::smem_desc(sB, 128, b_mn ? sbo : 4 * 256);
+        const bool one = (b_mn_in & 4) != 0, com = (b_mn_in & 2) != 0;
+        uint32_t el = 0;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
+        const bool me = one ? tid == 0 : el != 0u;
+        const int groups = reps * ksteps / 4;
+        const long long t0 = clock64();
+        if (!one || tid == 0) {
+            for (int g = 0; g < groups; g++) {
+                if (me) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) umma::mma_bf16_ss(tbase, ad0 + (uint64_t)(16 * k), bd0 + (uint64_t)(16 * k), idesc, k > 0 || g > 0);
+                    if (com) umma::commit(&bar2);
+                    if (b_mn_in & 16) umma::mbar_wait(&bar3, 0u, 1u << 20);      // a wait on a phase that completed long ago
+                    if (b_mn_in & 32) umma::fence_after_sync();
+                    if (b_mn_in & 64) g_sink = clock64();
+                }
+                if (!one) __syncwarp();
+            }
+        }
+        const long long t1 = clock64();
+        if (me) {
+            umma::commit(&bar);
+            umma::mbar_wait(&bar, 0, 1u << 24);
+            const long long t2 = clock64();
+            out[0] = t1 - t0; out[1] = t2 - t0;
+        }
+    } else if (tid == 0) {
         const uint32_t idesc = b_mn ? umma::instr_desc_bf16_bmn(128, n) : umma::instr_desc_bf16(128, n);
         const uint32_t sA = umma::smem_u32(smem), sB = sA + 32 * 1024;
         const long long t0 = clock64();
@@ -133,6 +170,7 @@ __global__ void __launch_bounds__(128, 1) umma_cycles_kernel(int n, int ksteps, 
                 const uint64_t ad = umma::smem_desc(sA + k * 256, 128, ksteps * 256);
                 const uint64_t bd = umma::smem_desc(sB + k * 256, 128, b_mn ? sbo : ksteps * 256);
                 umma::mma_bf16_ss(tbase, ad, bd, idesc, k > 0 || r > 0);
+                if ((b_mn_in & 2) && k == ksteps - 1) umma::commit(&bar2);     // a commit after every group of `ksteps` MMAs (nobody waits for it)
             }
         const long long t1 = clock64();
         umma::commit(&bar);
@@ -174,6 +212,18 @@ __global__ void __launch_bounds__(256, 1) stream_cycles_kernel(const unsigned ch
                         for (int p = 0; p < pieces; p++)
                             umma::bulk_load(smem + (size_t)sl * tile_bytes + p * pb, src + (size_t)(t % src_tiles) * tile_bytes + p * pb, (uint32_t)pb, &full[sl]);
                     }
+                }
+            }
+        } else if (kind == 2) {
+            // every lane < my_depth of the warp owns ONE slot and streams tiles through it on its own (is the ~840-cycle service time of a
+            // bulk copy a per-thread or a per-warp property?)
+            if (lane < my_depth) {
+                const int sl = warp + nw * lane;
+                int n_done = 0;
+                for (int t = warp + nw * lane; t < tiles; t += nw * my_depth, n_done++) {
+                    umma::mbar_expect(&full[sl], (uint32_t)tile_bytes);
+                    umma::bulk_load(smem + (size_t)sl * tile_bytes, src + (size_t)(t % src_tiles) * tile_bytes, (uint32_t)tile_bytes, &full[sl]);
+                    umma::mbar_wait(&full[sl], (uint32_t)(n_done & 1));
                 }
             }
         } else {
@@ -228,7 +278,7 @@ extern "C" int spl_umma_stream_cycles(spl_ctx* c, const void* src, int src_tiles
 extern "C" int spl_umma_mma_cycles(spl_ctx* c, int n, int ksteps, int b_mn, int sbo, int reps, long long* out2, void* stream) {
     if (!c) return spl_fail_(SPL_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
-    if (!out2 || n < 16 || n > 256 || n % 16 || ksteps < 1 || ksteps > 8 || reps < 1 || sbo < 0 || (sbo & 15) || (size_t)(n / 8) * (b_mn ? sbo : ksteps * 256) > 128 * 1024)
+    if (!out2 || n < 16 || n > 256 || n % 16 || ksteps < 1 || ksteps > 8 || reps < 1 || sbo < 0 || (sbo & 15) || (size_t)(n / 8) * ((b_mn & 1) ? sbo : ksteps * 256) > 128 * 1024)
         return spl_fail_(SPL_E_ARG, "spl_umma_mma_cycles: bad argument");
     CU(cudaFuncSetAttribute(umma_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     umma_cycles_kernel<<<1, 128, 160 * 1024, (cudaStream_t)stream>>>(n, ksteps, b_mn, sbo, reps, out2);

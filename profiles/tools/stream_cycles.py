@@ -18,9 +18,14 @@ def run(grid, kind, nw, pieces, tile_bytes, depth):
         nat.check(lib.spl_umma_stream_cycles(h, C.c_void_p(src.data_ptr()), src_tiles, tile_bytes, depth, tiles, mode, grid, C.c_void_p(out.data_ptr()), st))
         torch.cuda.synchronize()
     cyc = float(out.max().item())
-    print(f"grid {grid:3d} {'bulk' if kind == 0 else 'cp.async16'} warps {nw} pieces {pieces} tile {tile_bytes:5d} B depth {depth}: {cyc / tiles:8.1f} cycles per tile = "
+    print(f"grid {grid:3d} {('bulk', 'cp.async16', 'bulk, a lane per slot')[kind]} warps {nw} pieces {pieces} tile {tile_bytes:5d} B depth {depth}: {cyc / tiles:8.1f} cycles per tile = "
           f"{tile_bytes * tiles / cyc:6.1f} B/clk per SM, {grid * tile_bytes * tiles / cyc * 1.965:8.0f} GB/s chip", flush=True)
 for grid in (1, 148):
+    run(grid, 2, 1, 1, 16384, 6)
+    run(grid, 2, 1, 1, 16384, 12)
+    run(grid, 2, 1, 1, 8192, 12)
+    run(grid, 2, 2, 1, 16384, 12)
+    run(grid, 2, 1, 1, 65536, 2)
     run(grid, 0, 1, 1, 16384, 6)
     run(grid, 0, 1, 1, 65536, 2)
     run(grid, 0, 1, 1, 32768, 4)
