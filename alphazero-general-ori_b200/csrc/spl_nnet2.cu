@@ -16,7 +16,7 @@
 //     in the next layer's B operand (the 32 lanes of a warp write 512 contiguous bytes: no bank conflicts, no transposition).
 // A CTA carries 64 leaves: in the 2d layers as two halves of 32 whose MMAs and epilogues alternate (the tensor pipe works on one
 // half while all 16 epilogue warps work on the other), in the 1d layers as one N = 64 chain. Roles: warps 0..15 epilogues,
-// warp 16 weight producer, warp 17 MMA issuer (one thread each); they meet only on mbarriers.
+// warps 16, 17 weight producers, warps 18 / 19 MMA issuers (A: the 2d layers; A and B share the 1d layers); they meet only on mbarriers.
 //
 // The pooled halves of DenseAndPartialGPool (SplendorNNet.py:6-29; max / mean over groups of OUTPUT FEATURES, i.e. across TMEM
 // lanes) are computed from the shared-memory operand by a few threads into a 16-row side operand and enter the next layer as
@@ -52,10 +52,14 @@ constexpr int POOL_BYTES = 2 * (HC / 8) * 256;    // side operand [16 k][448 col
 constexpr int LSTR = 416;              // fp32 logits row stride (aliases the operand region once the head's MMAs are done)
 constexpr int NN_ACTIONS = 406;
 constexpr int EPI_THREADS = 512;       // warps 0..15: epilogues
-constexpr int PRODUCERS = 3;           // warps 16..18: weight producers (bulk copies of ONE warp complete one after the other, ~840 cycles
-                                       // each whatever their size - profiles/tools/stream_cycles.py - so tile t is requested by warp 16 + t % 3)
-constexpr int MMA_WARP = 16 + PRODUCERS;
-constexpr int THREADS = 32 * (MMA_WARP + 1);
+constexpr int PRODUCERS = 2;           // warps 16, 17: weight producers (bulk copies of ONE thread complete one after the other, ~840 cycles
+                                       // each whatever their size - profiles/tools/stream_cycles.py - so tile t is requested by warp 16 + t % 2;
+                                       // 20 warps in all: a 21st would cut the register budget from 96 to 80 per thread - five warps per
+                                       // sub-partition instead of six)
+constexpr int MMA_WARP = 16 + PRODUCERS;   // issuer A: the 2d layers and its share of the 1d layers
+constexpr int MMA_WARP_B = MMA_WARP + 1;   // issuer B: the other share of the 1d layers (the cost of a weight tile is the issuing thread's
+                                           // time - wait ~180 cycles, descriptors, 4 x 86 cycles of issue - not the tensor pipe's)
+constexpr int THREADS = 32 * (MMA_WARP_B + 1);
 constexpr int MAX_TILES = 48;
 static_assert(VEC_OFF + 8 * 2048 <= OPER_BYTES, "1d operand inside the region");
 static_assert(NL * LSTR * 4 <= OPER_BYTES, "logits inside the region");
@@ -100,7 +104,8 @@ struct Smem {
     __align__(128) unsigned char pool[POOL_BYTES];
     __align__(128) unsigned char ring[RING][TILE];
     uint64_t full[RING], empty[RING];   // weight tiles: producer -> MMA issuer -> slot free
-    uint64_t acc[2];                    // tcgen05.commit: the accumulator of half h (1d layers: acc[0]) is complete
+    uint64_t acc[2];                    // tcgen05.commit: the accumulator of half h of a 2d layer is complete
+    uint64_t acc1d;                     // two arrivals (tcgen05.commit of both issuers): the accumulators of a 1d layer are complete
     uint64_t epi[2];                    // 16 arrivals (one per epilogue warp): the B operand of half h (1d layers: epi[0]) is written
     uint32_t tmem_base;
     uint64_t inbar;                     // the staged input rows have landed
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
     if (warp == MMA_WARP) umma::tmem_alloc(&sm.tmem_base, 512);
     if (tid == EPI_THREADS) {
         for (int i = 0; i < RING; i++) { umma::mbar_init(&sm.full[i], 1); umma::mbar_init(&sm.empty[i], 1); }
-        umma::mbar_init(&sm.acc[0], 1); umma::mbar_init(&sm.acc[1], 1); umma::mbar_init(&sm.inbar, 1);
+        umma::mbar_init(&sm.acc[0], 1); umma::mbar_init(&sm.acc[1], 1); umma::mbar_init(&sm.inbar, 1); umma::mbar_init(&sm.acc1d, 2);
         umma::mbar_init(&sm.epi[0], EPI_THREADS / 32); umma::mbar_init(&sm.epi[1], EPI_THREADS / 32);
     }
     if (tid < EPI_THREADS) {
@@ -208,20 +213,24 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
             }
             __syncwarp();
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == MMA_WARP || warp == MMA_WARP_B) {
         // ---------------------------------------------------------------- MMA issuer: the whole warp runs the (uniform) control flow, the
         // tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane (operands stay in uniform registers; a
         // single divergent lane made every MMA a ~25-instruction loop that could not keep up next to four busy epilogue warps)
         const uint32_t oper = umma::smem_u32(sm.oper), pool = umma::smem_u32(sm.pool);
         const uint32_t id224 = umma::instr_desc_bf16_bmn(128, HC), id64 = umma::instr_desc_bf16_bmn(128, NL);
+        const int who = warp - MMA_WARP;           // issuer A (0) or B (1)
         uint32_t epi_n[2] = {0u, 0u};
         auto commit1 = [&](uint64_t* bar) { if (elect_one()) umma::commit(bar); __syncwarp(); };
         // the MMAs of one product: tiles [t0, t0 + nd) against the operand at b_addr (consecutive k), then (pooled) one K = 16 step
         // against the side operand. wait_full: first use of these tiles; free: give each slot back as soon as its MMAs are done
+        // split: the tiles of the product alternate between the two issuers (tile j belongs to issuer j & 1; each issuer accumulates into
+        // its own columns `dcol` and the epilogue adds the two accumulators)
         auto product = [&](int t0, int nd, bool pooled, uint32_t b_addr, uint32_t b_sbo, uint32_t p_addr, uint32_t idesc, uint32_t dcol,
-                           bool wait_full, bool free_slots) {
+                           bool wait_full, bool free_slots, bool split = false) {
             bool accum = false;
             for (int j = 0; j < nd + (pooled ? 1 : 0); j++) {
+                if (split && (j & 1) != who) { if (j < nd) b_addr += (uint32_t)(plan.bytes[t0 + j] / KSTEP_BYTES) * 256; continue; }
                 const int t = t0 + j, sl = t % RING;
                 if (wait_full) { if (elect_one()) wait(&sm.full[sl], (uint32_t)((t / RING) & 1)); __syncwarp(); umma::fence_after_sync(); if (blockIdx.x == 0 && lane == 0) g_tile_stamps[1][t] = clock64(); }
                 const int ks = plan.bytes[t] / KSTEP_BYTES;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
         };
         auto wait_epi = [&](int h) { if (elect_one()) wait(&sm.epi[h], epi_n[h] & 1u); __syncwarp(); epi_n[h]++; umma::fence_after_sync(); };
         int t0 = 0;
-        // 2d layers: L1, L2, G1, L3; the two halves share every tile
+        // 2d layers: L1, L2, G1, L3; the two halves share every tile. Issuer A does them; issuer B only follows the barrier phases
 #pragma unroll 1
         for (int l = 0; l < 4; l++) {
             const int nd = l == 0 ? plan.nt_l1 : 2, ntl = nd + (l == 3 ? 1 : 0);
@@ -248,23 +257,30 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 wait_epi(h);
-                product(t0, nd, l == 3, oper + h * HALF_BYTES + koff, 2048, pool + h * (HC / 8) * 256, id224, 256u * h, h == 0, false);
-                commit1(&sm.acc[h]);
+                if (who == 0) {
+                    product(t0, nd, l == 3, oper + h * HALF_BYTES + koff, 2048, pool + h * (HC / 8) * 256, id224, 256u * h, h == 0, false);
+                    commit1(&sm.acc[h]);
+                }
             }
-            for (int j = 0; j < ntl; j++) commit1(&sm.empty[(t0 + j) % RING]);
+            if (who == 0)
+                for (int j = 0; j < ntl; j++) commit1(&sm.empty[(t0 + j) % RING]);
             t0 += ntl;
         }
-        // 1d layers, N = 64 leaves
+        // 1d layers, N = 64 leaves: the weight tiles of a layer alternate between the two issuers, each accumulates its share of K into its
+        // own 64 columns (A: 0..63, B: 64..127), the epilogue adds the two; both commits arrive on acc1d
+        const uint32_t dc = 64u * (uint32_t)who;
         wait_epi(0); wait_epi(1);                                                                                     // L4: both halves of the 704-row operand
-        product(t0, 11, false, oper, FLAT_SBO, 0u, id64, 0u, true, true); commit1(&sm.acc[0]); t0 += 11;
-        wait_epi(0); product(t0, 2, false, oper + VEC_OFF + 2 * 128, 2048, 0u, id64, 0u, true, true); commit1(&sm.acc[0]); t0 += 2;   // G4
-        wait_epi(0); product(t0, 2, true, oper + VEC_OFF, 2048, pool, id64, 0u, true, true); commit1(&sm.acc[0]); t0 += 3;          // L5a
-        wait_epi(0); product(t0, 2, false, oper + VEC_OFF, 2048, 0u, id64, 0u, true, true); commit1(&sm.acc[0]); t0 += 2;           // L5b
-        wait_epi(0); product(t0, 2, false, oper + VEC_OFF + 2 * 128, 2048, 0u, id64, 0u, true, true); commit1(&sm.acc[0]); t0 += 2;   // G5
-        wait_epi(0);                                                                                                   // head: 4 M tiles
+        product(t0, 11, false, oper, FLAT_SBO, 0u, id64, dc, true, true, true); commit1(&sm.acc1d); t0 += 11;
+        wait_epi(0); product(t0, 2, false, oper + VEC_OFF + 2 * 128, 2048, 0u, id64, dc, true, true, true); commit1(&sm.acc1d); t0 += 2;   // G4
+        wait_epi(0); product(t0, 2, true, oper + VEC_OFF, 2048, pool, id64, dc, true, true, true); commit1(&sm.acc1d); t0 += 3;          // L5a
+        wait_epi(0); product(t0, 2, false, oper + VEC_OFF, 2048, 0u, id64, dc, true, true, true); commit1(&sm.acc1d); t0 += 2;           // L5b
+        wait_epi(0); product(t0, 2, false, oper + VEC_OFF + 2 * 128, 2048, 0u, id64, dc, true, true, true); commit1(&sm.acc1d); t0 += 2;   // G5
+        // head: 4 M tiles of 3 weight tiles each, stored in the order 0, 2, 1, 3: A takes M tiles 0 and 1, B takes 2 and 3 (whole products,
+        // columns 64 m as before)
+        wait_epi(0);
 #pragma unroll 1
-        for (int m = 0; m < 4; m++) { product(t0, 2, true, oper + VEC_OFF, 2048, pool, id64, 64u * m, true, true); t0 += 3; }
-        commit1(&sm.acc[0]);
+        for (int i = 0; i < 2; i++) product(t0 + 6 * i + 3 * who, 2, true, oper + VEC_OFF, 2048, pool, id64, 64u * (uint32_t)(2 * who + i), true, true);
+        commit1(&sm.acc1d);
     } else {
         // ---------------------------------------------------------------- epilogue warps: thread = TMEM lane f (output feature), column group cg
         const int q = warp & 3, cg = warp >> 2, f = 32 * q + lane;
@@ -537,9 +553,16 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
                 vraw[r][j] = fl == 2 ? alt_mask[(size_t)j * alt_mask_stride + row] : (fl == 1 && a < NN_ACTIONS) ? (uint32_t)valids[row * NN_ACTIONS + a] : 0u;
             }
         }
+        uint32_t acc1d_n = 0u;
+        auto wait_acc1d = [&]() {
+            if (lane == 0) wait(&sm.acc1d, acc1d_n & 1u);
+            acc1d_n++;
+            __syncwarp();
+            umma::fence_after_sync();
+        };
 #pragma unroll
         for (int l = 0; l < 5; l++) {      // L4, G4, L5a, L5b, G5
-            wait_acc(0);
+            wait_acc1d();
             if (l == 0) {
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -548,9 +571,12 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
                     for (int j = 0; j < 13; j++) vbits[r] |= (words ? ((vraw[r][j] >> lane) & 1u) : (vraw[r][j] != 0u ? 1u : 0u)) << j;
                 }
             }
-            float v[16];
-            tld16(lane_addr + 16u * cg, v);
+            float v[16], v2[16];
+            tld16(lane_addr + 16u * cg, v);                 // issuer A's share of K
+            tld16(lane_addr + 64u + 16u * cg, v2);          // issuer B's
             tld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] += v2[j];
             const bool live = !((l == 1 || l == 4) && f >= 120);
             const float b = b1d[l];
             uint32_t pk[8];
@@ -574,7 +600,7 @@ __global__ void __launch_bounds__(THREADS, 1) nnet2_forward_kernel(const unsigne
 
         // ---- head: logits of action 128 m + f (+ bias) as fp32 rows in shared memory; the value rows 406 .. 406 + n - 1 go out as tanh
         {
-            wait_acc(0);
+            wait_acc1d();
             float* logits = reinterpret_cast<float*>(sm.oper);
             float v[64];
 #pragma unroll
@@ -749,8 +775,8 @@ int pack(int n, const float* const* T, void* blob, size_t blob_bytes_) {
     after_pool([&](int r, int k) { return (double)T[24][(size_t)r * 128 + k] * bn5.s[0]; }, 128);      // L5a
     dense(T[30], 128, 128, 0, 128, 1.0);                                // L5b
     dense(T[32], 120, 112, 0, 112, bng5.s[0]);                          // G5
-    for (int m = 0; m < 4; m++)
-        after_pool([&](int r, int k) { return WH[(size_t)(128 * m + r) * 128 + k]; }, 128);             // head
+    for (int m : {0, 2, 1, 3})       // head: M tiles 0 and 1 belong to issuer A, 2 and 3 to issuer B; stored in the order they are consumed
+        after_pool([&](int r, int k) { return WH[(size_t)(128 * m + r) * 128 + k]; }, 128);
     if (t != p.nt) return spl_fail_(SPL_E_ARG, "spl_nnet_pack: internal tile count mismatch");
     return SPL_OK;
 }
