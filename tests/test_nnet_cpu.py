@@ -94,6 +94,6 @@ def test_blob_packer_folds_batchnorm_like_the_torch_path(n):
     assert torch.allclose(T[t], bf(g4[:, :64]), rtol=8e-3, atol=1e-6) and torch.allclose(T[t + 1], bf(g4[:, 64:]), rtol=8e-3, atol=1e-6); t += 2
     t += 3 + 2 + 2                                                                      # L5a, L5b, G5: same packers
     full = torch.cat([heads["PI"][0], heads["V"][0], torch.zeros(512 - 406 - n, 128, dtype=torch.float64)], 0)
-    for m in range(4):                                                                  # head: 4 M tiles of the folded [406 + n][128] matrix
+    for m in (0, 2, 1, 3):                                                              # head: 4 M tiles of the folded [406 + n][128] matrix
         t = after_pool(full[128 * m:128 * m + 128], t)
     assert t == len(T)
