@@ -657,7 +657,7 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
     const int n_rows = m->A.n_trees * m->A.n_slots;
     DISPATCH_N(m->ctx->n, {
         m->P.rules = rules;
-        if (m->fuse_rules && m->pdl) {
+        if (m->fuse_rules && m->pdl && m->rounds <= 1) {
             // stream: [expand + descend + rules] -> [network] -> next wave, both launched as programmatic dependents of their
             // predecessor (their blocks become resident - and the network does its set-up: parameters, TMEM, first weight tiles -
             // while the predecessor drains; griddepcontrol.wait guards the first dependent read); the attach kernel runs on the
@@ -680,12 +680,22 @@ int spl_mcts_wave_nnet(spl_mcts* m, const void* nnet_blob, float* pi, float* v, 
             CU(cudaGetLastError());
             return SPL_OK;
         }
-        if (m->fuse_rules) {
+        if (m->fuse_rules && m->rounds <= 1) {
             mcts_expand_descend_kernel<N, true, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
         } else {
             if (vl) mcts_expand_descend_kernel<N, false, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
             else mcts_expand_descend_kernel<N, false, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, pi, v, dir_values, m->max_levels, leaf_states, leaf_valids);
             CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
+            // rounds > 1 (lock-step callers): a tree whose descent ran into a transposition or backed a terminal value up gets another
+            // (attach, descend, rules) pass before the network runs, so that the wave still ends with a leaf for it. Scheduling only:
+            // every tree runs the same sequential search
+            for (int r = 1; r < m->rounds; r++) {
+                if (vl) mcts_attach_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, nullptr, false);
+                else mcts_attach_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, leaf_states, leaf_valids, leaf_flags, nullptr, false);
+                if (vl) mcts_descend_kernel<N, true><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+                else mcts_descend_kernel<N, false><<<grid, MW * 32, 0, st>>>(m->A, m->P, m->max_levels, leaf_states, leaf_valids);
+                CU(launch_rules<N>(m->A, rules, m->rules_tpw, st));
+            }
         }
         // fork: the network reads the rows the descent (leaf rows) or the rules kernel (staging rows) just wrote, while the
         // attach kernel links the new children into the trees; join before the next wave's expansion reads pi / v

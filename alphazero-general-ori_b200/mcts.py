@@ -75,7 +75,6 @@ class MCTSArena:
                            game_base=game_base, edge_reserve=edge_reserve, gc_reachable=int(bool(gc_reachable)), rounds=int(rounds), max_levels=int(max_levels))
         self.set_params()
         self.launches = 0
-        self.wave_nnet_launches = 3 if (self.T <= 6144 and self.K == 1) else 4      # descent (+ rules step inside it up to 6144 trees), attach, network
         self._nn_pending, self._nn_dir = None, None
         self.reset()
 
@@ -90,6 +89,15 @@ class MCTSArena:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def wave_nnet_launches(self):
+        """kernels of one spl_mcts_wave_nnet call: descent (+ the rules step inside it up to 6144 trees), attach, network; every further
+        round (`rounds` > 1) is an (attach, descend, rules) pass more"""
+        r = int(self.params.get("rounds", 1))
+        if r <= 1:
+            return 3 if (self.T <= 6144 and self.K == 1) else 4
+        return 4 + 3 * (r - 1)
 
     def set_params(self, **kw):
         self.params.update(kw)

@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--max-levels", type=int, default=16, help="edges a descend call walks before it yields to the next wave (0: no limit)")
     ap.add_argument("--overlap", type=int, default=1, help="1: the fused network runs next to the attach kernel (spl_mcts_wave_nnet); 0: one stream")
     ap.add_argument("--e2e-max-levels", type=int, default=0, help="max_levels of the lock-step e2e leg (0: a descent never yields)")
+    ap.add_argument("--e2e-rounds", type=int, default=1, help="(attach, descend, rules) passes per wave of the lock-step e2e leg: a tree whose descent crossed a "
+                                                              "transposition or a terminal node still ends the wave with a leaf (measured at 16,384 trees: 2 passes cost more per wave than they save in waves)")
     ap.add_argument("--node-cap", type=int, default=0)
     ap.add_argument("--fixed-net", action="store_true", help="use the deterministic stand-in network instead of SplendorNNet")
     ap.add_argument("--opening-plies", type=int, default=24, help="random plies before the first search (mid-game positions)")
@@ -511,7 +513,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     import numpy as np
     boards = eng.env.states().cpu().numpy()
     ar.reset()
-    ar.set_params(max_levels=args.e2e_max_levels)     # lock-step calls wait for the slowest tree (0: no yielding inside a descent)
+    ar.set_params(max_levels=args.e2e_max_levels, rounds=args.e2e_rounds)     # lock-step calls wait for the slowest tree (0: no yielding inside a descent)
     ke = 3
     h2d = d2h = 0
     launches0 = ar.launches

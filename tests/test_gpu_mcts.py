@@ -414,6 +414,36 @@ def test_overlapped_wave_equals_classic_wave(n, T):
         env.step(probs.argmax(1).to(torch.int16), player=0, chance="philox", rotate=True)
 
 
+@pytest.mark.parametrize("n,T", [(2, 7000), (3, 200)])
+def test_wave_with_two_rounds_is_only_scheduling(n, T):
+    """rounds = 2 in spl_mcts_wave_nnet (a tree whose descent crossed a transposition or a terminal node gets another attach / descend /
+    rules pass before the network runs; the lock-step e2e leg of bench.py): bit-identical trees, fewer waves. 7000 trees take the branch
+    with the separate rules kernel, 200 trees the one that otherwise fuses the rules step into the descent"""
+    az = _azg()
+    sims = 40
+    env = az.SplendorEnv(n, T, seed=9)
+    env.reset(); env.rollout(30 * n, rotate=True)       # late positions: terminal nodes and transpositions are frequent
+    net = az.FusedSplendorNNet(n, seed=4)
+    a = az.MCTSArena(n, T, node_cap=512, cpuct=1.1, fpu=0.1, pool_nodes=256)
+    b = az.MCTSArena(n, T, node_cap=512, cpuct=1.1, fpu=0.1, pool_nodes=256, rounds=2)
+    simt = torch.full((T,), sims, dtype=torch.int32, device=a.device)
+    waves = []
+    for move in range(2):
+        roots = env.states().clone()
+        for ar in (a, b):
+            l0 = ar.launches
+            ar.search(roots, simt, net)
+            ar.check_status()
+            waves.append((ar.launches - l0) / ar.wave_nnet_launches)
+        sa, sb = a.root_stats(), b.root_stats()
+        assert torch.equal(sa["nsa"], sb["nsa"]) and torch.equal(sa["qsa"], sb["qsa"]) and torch.equal(sa["ps"], sb["ps"]), move
+        assert torch.equal(sa["sims_done"], sb["sims_done"]) and torch.equal(sa["nn_calls"], sb["nn_calls"]) and torch.equal(sa["ns"], sb["ns"])
+        assert torch.equal(sa["nodes"], sb["nodes"])
+        probs, _ = a.policy(1.0)
+        env.step(probs.argmax(1).to(torch.int16), player=0, chance="philox", rotate=True)
+    assert waves[1] <= waves[0] and waves[3] <= waves[2], waves
+
+
 def test_train_batches_from_selfplay_examples_stay_on_the_device():
     """N4: the examples batched self-play produced feed the training mini-batch assembly without leaving the GPU"""
     az = _azg()
