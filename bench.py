@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="both", choices=["both", "mcts", "env"])
     ap.add_argument("--players", type=int, default=2)
     # MCTS (configs[1])
-    ap.add_argument("--trees", type=int, default=16384, help="parallel games (trees) per GPU")
+    ap.add_argument("--trees", type=int, default=18944, help="parallel games (trees) per GPU (18,944 = 148 SMs x 128: the evaluator's CTAs of 64 leaves fill two whole rounds)")
     ap.add_argument("--sims", type=int, default=1600, help="simulations per move")
     ap.add_argument("--nn-dtype", default="fused", choices=["fp32", "bf16", "fused"],
                     help="fp32 / bf16: torch evaluator; fused: the one-launch bf16 tensor-core kernel (csrc/spl_nnet.cu)")
