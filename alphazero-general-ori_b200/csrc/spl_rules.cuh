@@ -207,6 +207,21 @@ SPL_D void spl_card_bits(const S& s, int p, int i, const int* have, int gold, ui
 
 // pre (may be NULL): {buyable, present} of the 15 candidate cards, computed elsewhere by spl_card_bits (the tree kernels spread
 // them over the lanes of a warp)
+// the generated masks as immediates (the tables are constexpr: read them in constant expressions only)
+template <int C>
+SPL_D void spl_combo_fail(const int* b, const int* g, uint32_t& t_fail, uint32_t& g_fail) {
+    constexpr uint32_t M = SPL_COMBO_WITH[C];
+    t_fail |= b[C] >= 1 ? 0u : M;
+    g_fail |= g[C] >= 1 ? 0u : M;
+    if constexpr (C < 4) spl_combo_fail<C + 1>(b, g, t_fail, g_fail);
+}
+template <int C>
+SPL_D void spl_give3_fail(const int* g, uint64_t& fail) {
+    constexpr uint64_t M1 = SPL_GIVE3_NEEDS[C][0], M2 = SPL_GIVE3_NEEDS[C][1], M3 = SPL_GIVE3_NEEDS[C][2];
+    fail |= (g[C] >= 1 ? 0ull : M1) | (g[C] >= 2 ? 0ull : M2) | (g[C] >= 3 ? 0ull : M3);
+    if constexpr (C < 4) spl_give3_fail<C + 1>(g, fail);
+}
+
 template <int N, class S>
 SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint32_t* pre = nullptr) {
     typedef SplLay<N> L;
@@ -246,28 +261,19 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint
     const uint32_t rsv = rsv_blocked ? 0u : rsv_nolimit;
 
     // --- bank-can-supply flags T (30) and player-can-give flags G (20)
-    const uint32_t bn = spl_nib5(b), gn = spl_nib5(g);
     bool bank_neg = false;
 #pragma unroll
     for (int c = 0; c < 5; c++) bank_neg |= b[c] < 0;
     // The 25 "different gems" rows need one gem of each colour of the row: a subset test on the 5-bit set of colours
     // the bank (or the player) holds. Rows 25..29 / 15..19 ("identical") look at one colour's count.
-    uint32_t T = 0, G = 0;
-    uint32_t bank_has = 0, mine_has = 0;
+    // _valid_get_gems, is_limit=False :562-568; _valid_give_gems :595 (first 15 rows): a row is possible iff no colour it needs is missing,
+    // rows = ~OR_{c missing} SPL_COMBO_WITH[c] (compile-time masks: five selects per side instead of 25 subset tests)
+    uint32_t t_fail = 0, g_fail = 0;
     bool g_neg = false;
+    spl_combo_fail<0>(b, g, t_fail, g_fail);
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
-        bank_has |= (uint32_t)(b[c] >= 1) << c;
-        mine_has |= (uint32_t)(g[c] >= 1) << c;
-        g_neg |= g[c] < 0;
-    }
-#pragma unroll 1
-    for (int i = 0; i < 25; i++) {   // _valid_get_gems, is_limit=False :562-568; _valid_give_gems :595 (first 15 rows)
-        const uint32_t need = SPL_COMBO_BITS[i];
-        T |= (uint32_t)((bank_has & need) == need) << i;
-        G |= (uint32_t)((mine_has & need) == need) << i;
-    }
-    G &= 0x7FFFu;
+    for (int c = 0; c < 5; c++) g_neg |= g[c] < 0;
+    uint32_t T = ~t_fail & 0x1FFFFFFu, G = ~g_fail & 0x7FFFu;
     if (bank_neg) T = 0;
 #pragma unroll
     for (int c = 0; c < 5; c++) {
@@ -300,13 +306,13 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint
         spl_ex_words(m, T, G, regime);
         if (regime == 2) {
             if ((r.flags & SPL_F_GIVEBACK) && !g_neg) {   // take 3 / give 3 (:672, _valid_give_gems3 :602-607): actions 365..404
-                uint64_t g3 = 0;
-#pragma unroll 1
-                for (int tk = 0; tk < 10; tk++) {
-                    const uint64_t on = (T >> (15 + tk)) & 1u;
+                // pattern 4 tk + q is legal iff take row 15 + tk is possible and the player holds what the pattern gives: the patterns
+                // that fail are the OR, over the (colour, count) pairs the player cannot supply, of SPL_GIVE3_NEEDS (compile-time masks)
+                uint64_t g3_fail = 0, on = 0;
+                spl_give3_fail<0>(g, g3_fail);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) g3 |= (on & spl_ge5(gn, SPL_GIVE3[4 * tk + q])) << (4 * tk + q);
-                }
+                for (int tk = 0; tk < 10; tk++) on |= (uint64_t)((T >> (15 + tk)) & 1u) << (4 * tk);
+                const uint64_t g3 = (on * 15ull) & ~g3_fail;
                 m[11] |= (uint32_t)(g3 << 13);    // 365 = 11 * 32 + 13
                 m[12] |= (uint32_t)(g3 >> 19);
             }
