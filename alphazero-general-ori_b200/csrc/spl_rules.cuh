@@ -205,8 +205,6 @@ SPL_D void spl_card_bits(const S& s, int p, int i, const int* have, int gold, ui
     present |= (uint32_t)card << i;
 }
 
-// pre (may be NULL): {buyable, present} of the 15 candidate cards, computed elsewhere by spl_card_bits (the tree kernels spread
-// them over the lanes of a warp)
 // the generated masks as immediates (the tables are constexpr: read them in constant expressions only)
 template <int C>
 SPL_D void spl_combo_fail(const int* b, const int* g, uint32_t& t_fail, uint32_t& g_fail) {
@@ -222,6 +220,8 @@ SPL_D void spl_give3_fail(const int* g, uint64_t& fail) {
     if constexpr (C < 4) spl_give3_fail<C + 1>(g, fail);
 }
 
+// pre (may be NULL): {buyable, present} of the 15 candidate cards, computed elsewhere by spl_card_bits (the tree kernels spread
+// them over the lanes of a warp)
 template <int N, class S>
 SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint32_t* pre = nullptr) {
     typedef SplLay<N> L;
@@ -247,7 +247,11 @@ SPL_D void spl_valid_mask(const S& s, int p, SplRules r, uint32_t* m, const uint
     if (pre) {
         buyable = pre[0]; present = pre[1];
     } else {
-#pragma unroll 1
+#ifndef SPL_CARD_UNROLL
+#define SPL_CARD_UNROLL 1
+#endif
+        constexpr int kCardUnroll = SPL_CARD_UNROLL;
+#pragma unroll kCardUnroll
         for (int i = 0; i < 15; i++) spl_card_bits<N>(s, p, i, have, gold, buyable, present);
     }
     const uint32_t buy = buyable & 0xFFFu, buyres = (buyable >> 12) & 7u;
