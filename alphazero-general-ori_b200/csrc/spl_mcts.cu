@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSe
 }
 
 template <int N, bool VL>
-__global__ void __launch_bounds__(MW * 32, MINB(7)) mcts_descend_kernel(MctsArena A, MctsSearchParams P, int max_levels, int8_t* leaf_states,
+__global__ void __launch_bounds__(MW * 32, MINB(7)) mcts_descend_kernel(const __grid_constant__ MctsArena A, const __grid_constant__ MctsSearchParams P, int max_levels, int8_t* leaf_states,
                                                                   uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
@@ -199,7 +199,7 @@ static cudaError_t launch_rules(const MctsArena& A, const SplRules& rules, int t
 }
 
 template <int N, bool VL>
-__global__ void __launch_bounds__(MW * 32, MINB(ATT_MINB)) mcts_attach_kernel(MctsArena A, MctsSearchParams P, int8_t* leaf_states, uint8_t* leaf_valids,
+__global__ void __launch_bounds__(MW * 32, MINB(ATT_MINB)) mcts_attach_kernel(const __grid_constant__ MctsArena A, const __grid_constant__ MctsSearchParams P, int8_t* leaf_states, uint8_t* leaf_valids,
                                                                  uint8_t* leaf_flags, int32_t* counters, bool emit_rows) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     if (t >= A.n_trees) return;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(MW * 32, MINB(ATT_MINB)) mcts_attach_kernel(Mc
 }
 
 template <int N, bool VL>
-__global__ void __launch_bounds__(MW * 32, MINB(8)) mcts_expand_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir) {
+__global__ void __launch_bounds__(MW * 32, MINB(8)) mcts_expand_kernel(const __grid_constant__ MctsArena A, const __grid_constant__ MctsSearchParams P, const float* pi, const float* v, const double* dir) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);
     if (t >= A.n_trees) return;
@@ -338,7 +338,7 @@ __device__ __forceinline__ void rules_for_own_tree(const MctsArena& A, int t, co
 // expansion of the previous wave's leaf and the next descent of the same tree in one launch (both are warp-per-tree);
 // RULES: followed by the rules step of the tree's pending edge (spl_mcts_wave_nnet; otherwise mcts_rules_kernel does it)
 template <int N, bool RULES, bool VL>
-__global__ void __launch_bounds__(MW * 32, MINB(DESC_MINB)) mcts_expand_descend_kernel(MctsArena A, MctsSearchParams P, const float* pi, const float* v, const double* dir,
+__global__ void __launch_bounds__(MW * 32, MINB(DESC_MINB)) mcts_expand_descend_kernel(const __grid_constant__ MctsArena A, const __grid_constant__ MctsSearchParams P, const float* pi, const float* v, const double* dir,
                                                                          int max_levels, int8_t* leaf_states, uint8_t* leaf_valids) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
     WarpScratch sc = warp_scratch(warp);

@@ -869,8 +869,19 @@ const W& w, const MctsArena& A, int t, int s, uint32_t node, int depth, int sims
 // into a node or an edge another slot of the tree already waits at is given up for this wave (returns 0).
 // ------------------------------------------------------------------------------------------
 template <int N, bool VL, class W>
+SPL_D int mcts_descend_tree_impl(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, int max_terminal, int max_levels,
+                                 int8_t* leaf_state, uint8_t* leaf_valid, int& spec_hits);
+template <int N, bool VL, class W>
 SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, int max_terminal, int max_levels,
                             int8_t* leaf_state, uint8_t* leaf_valid) {
+    int spec_hits = 0;   // diagnostics (early-fetch hit rate): counted in a register, written once per call - the tree belongs to this warp
+    const int r = mcts_descend_tree_impl<N, VL>(w, A, t, s, P, max_terminal, max_levels, leaf_state, leaf_valid, spec_hits);
+    if (spec_hits != 0 && w.lane == 0) A.trees[t].spec_hits += spec_hits;
+    return r;
+}
+template <int N, bool VL, class W>
+SPL_D int mcts_descend_tree_impl(const W& w, const MctsArena& A, int t, int s, const MctsSearchParams& P, int max_terminal, int max_levels,
+                                 int8_t* leaf_state, uint8_t* leaf_valid, int& spec_hits) {
     MctsTree* T = A.trees + t;
     MctsSlot* S = T->slot + s;
     if (S->leaf != 0u) return 1;
@@ -985,9 +996,7 @@ SPL_D int mcts_descend_tree(const W& w, const MctsArena& A, int t, int s, const 
             cur = child;
             ne = child_ne;
             have_spec = ei == hp;
-#ifdef __CUDACC__
-            if (have_spec && w.lane == 0) atomicAdd(&T->spec_hits, 1);
-#endif
+            spec_hits += have_spec ? 1 : 0;
         }
         {   // terminal: return Es up the path
             float v[N];
