@@ -71,7 +71,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(int warp) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(MctsArena A, MctsSearchParams P, const int8_t* roots, const int32_t* sims,
+__global__ void __launch_bounds__(MW * 32) mcts_begin_kernel(const __grid_constant__ MctsArena A, const __grid_constant__ MctsSearchParams P, const int8_t* roots, const int32_t* sims,
                                                              const uint8_t* move_flags, const uint8_t* tree_select, const double* dir,
                                                              const uint32_t* episodes, int gc_reachable) {
     const int warp = threadIdx.x >> 5, t = blockIdx.x * MW + warp;
