@@ -221,7 +221,9 @@ struct AosAcc {   // the reference's own array order: cell (row, col) = byte 7*r
 };
 
 // record accessors: [MctsNode 32][compact state cp][Q double[k]][MctsPN[k]][MctsCA[k]], padded to a multiple of 32 bytes
-SPL_D uint32_t* mcts_path(const MctsArena& A, int t, int s) { return A.path + ((size_t)t * A.n_slots + s) * A.max_depth * 2; }
+SPL_D uint32_t* mcts_path(const MctsArena& A, int t, int s) {   // (rows x 2 max_depth words stay far below 2^32: 32-bit index arithmetic)
+    return A.path + (uint32_t)(t * A.n_slots + s) * (uint32_t)(2 * A.max_depth);
+}
 SPL_D int mcts_row(const MctsArena& A, int t, int s) { return t * A.n_slots + s; }
 // with several simulations in flight (virtual loss) the top byte of an edge's N counts the simulations currently below it
 #define MCTS_VL_ONE 0x01000000

@@ -484,7 +484,7 @@ def bench_mcts(args, torch, dist, azg, world, rank, local, dev, barrier):
     bf16_peak = float(peaks.get("bf16_tflops_sustained", 1409.8))
     nn_tflops = NN_FLOPS_PER_LEAF[n] * T / (nnt * 1e-3) / 1e12
     roofline_nn = {"bound": "tensor", "achieved": nn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": nn_tflops / bf16_peak, "traffic": None,
-                   "kernel": "nnet_forward_kernel (one launch = the whole SplendorNNet forward for every tree's leaf)", "avg_launch_ms": nnt,
+                   "kernel": "nn2::nnet2_forward_kernel (one launch = the whole SplendorNNet forward for every tree's leaf)", "avg_launch_ms": nnt,
                    "flops_per_leaf": NN_FLOPS_PER_LEAF[n], "leaves_per_launch": T, "leaves_per_s": T / (nnt * 1e-3),
                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a long step)" if peaks else "fallback 1409.8 TFLOP/s"}
     nn_name = {"fused": "bf16 network (bf16 x bf16 -> fp32 accumulate, tensor cores)", "bf16": "bf16 network (torch)", "fp32": "f32 network (torch)"}[args.nn_dtype]
