@@ -280,6 +280,47 @@ struct RolloutParams {
     int n_tiles;
 };
 
+// swap_players by ONE seat for the WHOLE lane tile (every lane just moved and passes the turn: the persistent ply loop), as a job of
+// the warp: a block of SIZE rows is SIZE x 224 contiguous bytes of the tile (row-major cells, 32 lanes per cell), rolling it by SHIFT
+// rows moves 32-bit words - ~40 LDS.32 + 40 STS.32 per lane for two players instead of ~450 byte accesses per lane (spl_rotate walks
+// every cell of every lane). Same row permutation as spl_roll_block<SIZE, SHIFT>: new[j] = old[(j + SHIFT) mod SIZE].
+template <int SIZE, int SHIFT>
+__device__ __forceinline__ void tile_roll_block(int8_t* sm, int row0, int lane) {
+    if (SIZE <= 1 || SHIFT % SIZE == 0) return;
+    constexpr int W = SIZE * 7 * TL / 4, SW = (SHIFT % SIZE) * 7 * TL / 4, PER = (W + 31) / 32;
+    uint32_t* blk = reinterpret_cast<uint32_t*>(sm + (size_t)row0 * 7 * TL);
+    uint32_t v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int d = lane + 32 * i;
+        int src = d + SW;
+        src = src >= W ? src - W : src;
+        v[i] = d < W ? blk[src] : 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int d = lane + 32 * i;
+        if (d < W) blk[d] = v[i];
+    }
+    __syncwarp();
+}
+template <int N>
+static __device__ __noinline__ void lane_rotate_cold(int8_t* lane_base, int k, SplRules r) {   // the rare per-lane path, kept out of the hot loop's code
+    TileAcc s{lane_base};
+    spl_rotate<N>(s, k, r);
+}
+template <int N>
+__device__ __forceinline__ void tile_rotate1(int8_t* sm, int lane, SplRules r) {
+    typedef SplLay<N> L;
+    __syncwarp();
+    tile_roll_block<N, 1>(sm, L::PGEMS, lane);
+    if ((r.flags & SPL_F_REFCOMPAT) || N == 2) tile_roll_block<N * (N + 1), 3 % (N * (N + 1))>(sm, L::PNOBLES, lane);   // :345 (F7a)
+    else tile_roll_block<N * (N + 1), N + 1>(sm, L::PNOBLES, lane);
+    tile_roll_block<N, 1>(sm, L::PCARDS, lane);
+    tile_roll_block<6 * N, 6>(sm, L::PRES, lane);
+}
+
 template <int N, bool TMA, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) spl_rollout_kernel(const RolloutParams P) {
     typedef SplLay<N> L;
@@ -312,19 +353,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) spl_rollout_kernel(const Rol
         }
         int first_plies = 0;
         bool have_first = false;
-        for (int it = 0; it < A.plies; it++) {   // every lane of the warp runs the loop (padding lanes idle): the restart below is a warp job
+        for (int it = 0; it < A.plies; it++) {   // every lane of the warp runs the loop (padding lanes idle): the rotation and the restart below are warp jobs
             bool restart = false;
+            int nxt = 0;
+            uint32_t ply = 0;
             if (active) {
                 uint32_t m[SPL_MASK_WORDS];
                 spl_valid_mask<N>(s, cur, P.rules, m);
-                const uint32_t ply = (uint32_t)(uint8_t)s.get(L::BANK, SPL_PTS);
+                ply = (uint32_t)(uint8_t)s.get(L::BANK, SPL_PTS);
                 const int a = spl_pick_random(m, A.seed, game, episode, ply);
                 SplChance ch;
                 ch.mode = SPL_CHANCE_PHILOX; ch.code = 0; ch.seed = A.seed; ch.game = game; ch.episode = episode; ch.ply = ply;
-                int nxt = spl_apply_move<N>(s, a, cur, ch);
+                nxt = spl_apply_move<N>(s, a, cur, ch);
                 if (nxt < 0) nxt = (cur + 1) % N;   // cannot happen for a legal action
                 ply_acc++;
-                if (A.rotate) { spl_rotate<N>(s, nxt, P.rules); nxt = 0; }
+            }
+            if (A.rotate) {
+                // canonical lanes (cur == 0) all pass the turn to seat 1: one rotation of the whole tile by the warp (padding lanes hold zeros);
+                // anything else (lanes that came in with another player to move) takes the per-lane path
+                if (__all_sync(0xffffffffu, !active || nxt == 1)) tile_rotate1<N>(sm, lane, P.rules);
+                else if (active) lane_rotate_cold<N>(sm + lane, nxt, P.rules);
+                __syncwarp();
+                nxt = 0;
+            }
+            if (active) {
                 cur = nxt;
                 float res[N];
                 if (spl_game_ended<N>(s, P.rules, res)) {
