@@ -94,3 +94,26 @@ def test_deterministic_tree_steps_vs_oracle():
                 assert np.array_equal(o.check_end_game(), s.check_end_game())
                 if o.check_end_game().any():
                     break
+
+
+def test_generated_fail_masks_match_their_source_tables():
+    """SPL_COMBO_WITH / SPL_GIVE3_NEEDS (the compile-time masks spl_valid_mask ORs together for what a player or the bank lacks) are
+    derived tables: re-derive them from SPL_COMBO_BITS / SPL_GIVE3 as they stand in the generated header"""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(__file__), "..", "alphazero-general-ori_b200", "csrc", "spl_tables.cuh")
+    src = open(path).read()
+
+    def table(name):
+        m = re.search(name + r"(?:\[\d+\])+ = \{([^}]*)\}", src)
+        assert m, name
+        return [int(x.strip().rstrip("ul"), 0) for x in m.group(1).split(",")]
+    combo, give3 = table("SPL_COMBO_BITS"), table("SPL_GIVE3")
+    assert len(combo) == 25 and len(give3) == 40
+    assert table("SPL_COMBO_WITH") == [sum(1 << i for i in range(25) if (combo[i] >> c) & 1) for c in range(5)]
+    needs = table("SPL_GIVE3_NEEDS")
+    for c in range(5):
+        for lvl in range(3):
+            assert needs[3 * c + lvl] == sum(1 << i for i in range(40) if ((give3[i] >> (4 * c)) & 15) == lvl + 1)
+    # every give-3 pattern hands over exactly three gems
+    assert all(sum((p >> (4 * c)) & 15 for c in range(5)) == 3 for p in give3)
